@@ -1,0 +1,831 @@
+/*
+ * rbpf_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, float64, CPU restatement of the per-scan RBPF update of
+ * amansanghvi/Thesis.  It exists to check the CUDA path (thesis_b200/csrc) and
+ * to serve as the timed CPU baseline.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it; nothing under
+ * thesis_b200/ does.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * the reference checkout).  Data layout deliberately follows the reference, not
+ * the GPU: a map is a list of 40 m x 40 m tiles of 800x800 float64 log-odds in
+ * allocation order (hybridmap.py:63-70, gridmap.py:31-32), a duplicate particle
+ * is a deep copy (robot.py:141-149).
+ *
+ * Parity status
+ *   - pinned against the reference's own Python (imported with stubs, see
+ *     oracle/ref_shim.py and tests/golden/make_golden.py): beam geometry, tile
+ *     lookup, ray-cast map integration, sample weights, moments, resampling,
+ *     motion models, nearby-occupied gather.
+ *   - PARITY UNPINNED: orc_match().  The reference delegates the search to
+ *     MathWorks matchScansGrid/matchScans (matchScanCustom.m:9-37), whose source
+ *     is not in the reference tree and cannot run here.  orc_match() is OUR
+ *     restatement of a correlative grid search honouring the call contract
+ *     (matchScanCustom.m:1-58, hybridmap.py:210-261); see DESIGN.md section 4.
+ *
+ * Declared deviations from the reference (same ones the GPU path makes):
+ *   - np.longdouble accumulators (robot.py:25,92-94,119,124) are float64.
+ *   - every particle owns a private tile list (the class-level list at
+ *     hybridmap.py:64 aliases all particles' maps).
+ *   - proposal samples use the lower Cholesky factor of the matcher covariance
+ *     on caller-supplied standard normals instead of NumPy's SVD transform
+ *     (robot.py:81); same distribution, different individual draws.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CS 0.05            /* hybridmap.py:67  cell size, metres */
+#define TILE_LEN 40        /* hybridmap.py:68  tile side, metres (an int in the reference) */
+#define DIM 800            /* gridmap.py:31    round(40/0.05) */
+#define L_OCC 0.80         /* gridmap.py:20 */
+#define L_NEAR 0.20        /* gridmap.py:21 */
+#define L_MAX 3.0          /* gridmap.py:22 */
+#define L_EMP (-0.30)      /* gridmap.py:23 */
+#define L_MIN (-3.0)       /* gridmap.py:24 */
+#define MATCH_MAX_R 11.0   /* hybridmap.py:20  VALID_DIST_THRESHOLD */
+#define MATCH_MIN_R 1e-3   /* hybridmap.py:218 */
+#define CLIP_R 15.0        /* hybridmap.py:107-108 */
+#define W_MAX_R 25.0       /* robot.py:130 */
+#define W_MIN_R 0.01       /* robot.py:130 */
+#define RESAMPLE_TRIGGER 200.0 /* main.py:50 */
+#define ROT_RANGE (M_PI / 6.0) /* hybridmap.py:249 */
+#define MAX_NT 14          /* window clamp 0.7 m (robot.py:64-65) / 0.05 m */
+
+/* ------------------------------------------------------------------ map -- */
+
+typedef struct {
+    int cx, cy;            /* tile centre, metres, on the 40 m lattice (hybridmap.py:193-208) */
+    double *cells;         /* [ix*DIM + iy], x is the row index (gridmap.py:87) */
+} orc_tile;
+
+typedef struct {
+    orc_tile *tiles;       /* allocation order == lookup order (hybridmap.py:269-272) */
+    int n, cap;
+} orc_map;
+
+static void map_push(orc_map *m, int cx, int cy)
+{
+    if (m->n == m->cap) {
+        m->cap = m->cap ? 2 * m->cap : 4;
+        m->tiles = (orc_tile *)realloc(m->tiles, (size_t)m->cap * sizeof(orc_tile));
+    }
+    m->tiles[m->n].cx = cx;
+    m->tiles[m->n].cy = cy;
+    m->tiles[m->n].cells = (double *)calloc((size_t)DIM * DIM, sizeof(double));
+    m->n++;
+}
+
+/* HybridMap.__init__ hybridmap.py:66-70 : one blank tile centred on (0,0). */
+orc_map *orc_map_new(void)
+{
+    orc_map *m = (orc_map *)calloc(1, sizeof(orc_map));
+    map_push(m, 0, 0);
+    return m;
+}
+
+void orc_map_free(orc_map *m)
+{
+    if (!m) return;
+    for (int i = 0; i < m->n; i++) free(m->tiles[i].cells);
+    free(m->tiles);
+    free(m);
+}
+
+/* HybridMap.copy hybridmap.py:315-320 -> HybridMapEntry.copy :56-61 -> GridMap.copy
+ * gridmap.py:336-342 : deep copy of every tile. */
+orc_map *orc_map_copy(const orc_map *src)
+{
+    orc_map *m = (orc_map *)calloc(1, sizeof(orc_map));
+    m->cap = src->n > 4 ? src->n : 4;
+    m->tiles = (orc_tile *)malloc((size_t)m->cap * sizeof(orc_tile));
+    for (int i = 0; i < src->n; i++) {
+        m->tiles[i].cx = src->tiles[i].cx;
+        m->tiles[i].cy = src->tiles[i].cy;
+        m->tiles[i].cells = (double *)malloc((size_t)DIM * DIM * sizeof(double));
+        memcpy(m->tiles[i].cells, src->tiles[i].cells, (size_t)DIM * DIM * sizeof(double));
+    }
+    m->n = src->n;
+    return m;
+}
+
+int orc_map_ntiles(const orc_map *m) { return m->n; }
+void orc_map_tile_centre(const orc_map *m, int i, int *cx, int *cy)
+{
+    *cx = m->tiles[i].cx;
+    *cy = m->tiles[i].cy;
+}
+double *orc_map_tile_cells(orc_map *m, int i) { return m->tiles[i].cells; }
+
+/* Tile with this centre, or NULL. */
+double *orc_map_find_tile(orc_map *m, int cx, int cy)
+{
+    for (int i = 0; i < m->n; i++)
+        if (m->tiles[i].cx == cx && m->tiles[i].cy == cy) return m->tiles[i].cells;
+    return NULL;
+}
+
+/* HybridMapEntry.is_in_map hybridmap.py:44-45 with the bounds of :31-36. */
+static int tile_has(const orc_tile *t, double x, double y)
+{
+    double r = TILE_LEN / 2.0;
+    return x >= t->cx - r && x < t->cx + r && y >= t->cy - r && y < t->cy + r;
+}
+
+/* HybridMap.get_map_with_pos hybridmap.py:263-272 : first match in list order. */
+static orc_tile *map_with_pos(const orc_map *m, double x, double y)
+{
+    for (int i = 0; i < m->n; i++)
+        if (tile_has(&m->tiles[i], x, y)) return &m->tiles[i];
+    return NULL;
+}
+
+/* GridMap.get_cell gridmap.py:120-128 (tile-relative metres -> indices). */
+static int get_cell(double x, double y, int *ix, int *iy)
+{
+    double h = TILE_LEN / 2.0;
+    if (y < -h || y >= h) return 0;
+    if (x < -h || x >= h) return 0;
+    *ix = (int)(x / TILE_LEN * DIM + DIM / 2.0);
+    *iy = (int)(y / TILE_LEN * DIM + DIM / 2.0);
+    return 1;
+}
+
+/* GridMap.index_to_distance gridmap.py:333-334. */
+static double index_to_distance(int i) { return (double)(i - DIM / 2.0) * TILE_LEN / DIM; }
+
+/* HybridMap.get_odds_at hybridmap.py:85-93.  Returns 1 and *out when a tile
+ * holds the point, 0 for the reference's None. */
+int orc_get_odds_at(const orc_map *m, double x, double y, double *out)
+{
+    orc_tile *t = map_with_pos(m, x, y);
+    int ix, iy;
+    if (!t) return 0;
+    if (!get_cell(x - t->cx, y - t->cy, &ix, &iy)) return 0;
+    *out = t->cells[(size_t)ix * DIM + iy];
+    return 1;
+}
+
+/* HybridMap._get_map_centre hybridmap.py:193-208. */
+static void map_centre(double x, double y, int *cx, int *cy)
+{
+    int ax = (int)nearbyint(x / TILE_LEN);     /* Python round(): half to even, like nearbyint */
+    int ay = (int)nearbyint(y / TILE_LEN);
+    *cx = 0;
+    *cy = 0;
+    for (int a = ax - 1; a < ax + 2; a++) {
+        int mc = a * TILE_LEN;
+        if (x < mc + TILE_LEN / 2.0 && x >= mc - TILE_LEN / 2.0) { *cx = mc; break; }
+    }
+    for (int a = ay - 1; a < ay + 2; a++) {
+        int mc = a * TILE_LEN;
+        if (y < mc + TILE_LEN / 2.0 && y >= mc - TILE_LEN / 2.0) { *cy = mc; break; }
+    }
+}
+
+/* Python negative indices wrap (ndarray[-1]); keep that behaviour visible. */
+static size_t wrap_idx(int ix, int iy)
+{
+    if (ix < 0) ix += DIM;
+    if (iy < 0) iy += DIM;
+    return (size_t)ix * DIM + iy;
+}
+
+/* GridMap.set_occupied_pos / set_empty_pos / set_nearby_pos gridmap.py:86-117. */
+static void set_pos(orc_tile *t, double rx, double ry, int kind)
+{
+    int ix = (int)(rx / CS + DIM / 2.0);
+    int iy = (int)(ry / CS + DIM / 2.0);
+    double *c = &t->cells[wrap_idx(ix, iy)];
+    if (kind == 0) *c = fmax(*c + L_EMP, L_MIN);
+    else if (kind == 1) *c = fmin(*c + L_OCC, L_MAX);
+    else *c = fmin(*c + L_NEAR, L_MAX);
+}
+
+/* ---------------------------------------------------------------- beams -- */
+
+/* Scan.__init__ lidar.py:76-80 plus the per-beam range used by the gates
+ * (hybridmap.py:105,217; robot.py:129). */
+void orc_scan_prepare(const double *ranges, const double *angles, int B,
+                      double *px, double *py, double *dist)
+{
+    for (int j = 0; j < B; j++) {
+        px[j] = ranges[j] * cos(angles[j]);
+        py[j] = ranges[j] * sin(angles[j]);
+        dist[j] = sqrt(px[j] * px[j] + py[j] * py[j]);
+    }
+}
+
+/* Scan.from_global_reference lidar.py:111-128 : [c -s x; s c y; 0 0 1] . [px;py;1]. */
+static inline void xform(double c, double s, double x, double y, double px, double py,
+                         double *gx, double *gy)
+{
+    /* np.matmul of the 3x3 by 3xB (lidar.py:123) accumulates k = 0,1,2 with fused
+     * multiply-adds on the build container's BLAS: round(c*px), fma(-s,py,.), + x.
+     * Replaying that order makes endpoints bit-identical to the reference there. */
+    *gx = fma(-s, py, c * px) + x;
+    *gy = fma(c, py, s * px) + y;
+}
+
+void orc_transform(const double *pose, const double *px, const double *py, int B,
+                   double *gx, double *gy)
+{
+    double c = cos(pose[2]), s = sin(pose[2]);
+    for (int j = 0; j < B; j++) xform(c, s, pose[0], pose[1], px[j], py[j], &gx[j], &gy[j]);
+}
+
+/* ------------------------------------------------------ map integration -- */
+
+/* HybridMap.get_affected_points hybridmap.py:274-301, including the empty list
+ * for axis-aligned rays that point in the negative direction (:278-281).
+ * Returns the number of cells written to out (capacity cap). */
+int orc_bresenham(int x0, int y0, int x1, int y1, int *out, int cap)
+{
+    int dx = abs(x1 - x0), dy = abs(y1 - y0), n = 0;
+    if (dx == 0) {
+        for (int y = y0; y < y1 + 1; y++) { if (n < cap) { out[2 * n] = x0; out[2 * n + 1] = y; } n++; }
+        return n;
+    }
+    if (dy == 0) {
+        for (int x = x0; x < x1 + 1; x++) { if (n < cap) { out[2 * n] = x; out[2 * n + 1] = y0; } n++; }
+        return n;
+    }
+    int xs = x1 - x0 > 0 ? 1 : -1, ys = y1 - y0 > 0 ? 1 : -1;
+    int steep = dy > dx;
+    if (steep) { int t = dx; dx = dy; dy = t; }
+    int D = 2 * dy - dx, y = 0;
+    for (int x = 0; x < dx + 1; x++) {
+        if (n < cap) {
+            if (steep) { out[2 * n] = x0 + xs * y; out[2 * n + 1] = y0 + ys * x; }
+            else       { out[2 * n] = x0 + xs * x; out[2 * n + 1] = y0 + ys * y; }
+        }
+        n++;
+        if (D >= 0) { y += 1; D -= 2 * dx; }
+        D += 2 * dy;
+    }
+    return n;
+}
+
+/* HybridMap.update hybridmap.py:95-145. */
+void orc_map_update(orc_map *m, const double *pose, const double *px, const double *py,
+                    const double *dist, int B)
+{
+    if (!map_with_pos(m, pose[0], pose[1])) return;               /* :98-100 */
+    int sx = (int)(pose[0] / CS), sy = (int)(pose[1] / CS);      /* :102 */
+    double c = cos(pose[2]), s = sin(pose[2]);
+    int cap = 4096, *pts = (int *)malloc(sizeof(int) * 2 * (size_t)cap);
+    for (int j = 0; j < B; j++) {
+        double gx, gy;
+        xform(c, s, pose[0], pose[1], px[j], py[j], &gx, &gy);
+        int occ = 1;
+        int ex = (int)(gx / CS), ey = (int)(gy / CS);             /* :106 */
+        if (dist[j] > CLIP_R) {                                   /* :107-113 */
+            double scale = 15.0 / dist[j];
+            int nex = (int)(sx + scale * (ex - sx));
+            int ney = (int)(sy + scale * (ey - sy));
+            ex = nex; ey = ney; occ = 0;
+        }
+        int n = orc_bresenham(sx, sy, ex, ey, pts, cap);
+        if (n > cap) {
+            cap = n; pts = (int *)realloc(pts, sizeof(int) * 2 * (size_t)cap);
+            n = orc_bresenham(sx, sy, ex, ey, pts, cap);
+        }
+        for (int q = 0; q < n; q++) {                             /* :122-144 */
+            double X = pts[2 * q] * CS, Y = pts[2 * q + 1] * CS;
+            orc_tile *t = map_with_pos(m, X, Y);
+            if (!t) {
+                int cx, cy;
+                map_centre(X, Y, &cx, &cy);
+                t = map_with_pos(m, (double)cx, (double)cy);
+                if (!t) { map_push(m, cx, cy); t = &m->tiles[m->n - 1]; }
+            }
+            if (occ && pts[2 * q] == ex && pts[2 * q + 1] == ey) {
+                set_pos(t, X - t->cx, Y - t->cy, 1);
+                if (q > 0) {
+                    double NX = pts[2 * q - 2] * CS, NY = pts[2 * q - 1] * CS;
+                    if (tile_has(t, NX, NY)) set_pos(t, NX - t->cx, NY - t->cy, 2);
+                }
+            } else {
+                set_pos(t, X - t->cx, Y - t->cy, 0);
+            }
+        }
+    }
+    free(pts);
+}
+
+/* GridMap.get_nearby_occ_points via HybridMap.get_scan_match hybridmap.py:230-234
+ * and gridmap.py:130-155 : cells with log-odds > 1.0 in the 72x72 window around
+ * a point, over every tile.  Writes (x,y) metre pairs; returns the count. */
+int orc_nearby_occ(const orc_map *m, double cpx, double cpy, double *out, int cap)
+{
+    int n = 0, pr = (int)(1.8 / CS);
+    for (int i = 0; i < m->n; i++) {
+        const orc_tile *t = &m->tiles[i];
+        double x = cpx - t->cx, y = cpy - t->cy;
+        int decx = 0, decy = 0;
+        if (y < -TILE_LEN / 2.0) decy = 1; else if (x < -TILE_LEN / 2.0) decx = 1;   /* :131-136 */
+        int jx = (int)(x / TILE_LEN * DIM + DIM / 2.0) - decx;
+        int jy = (int)(y / TILE_LEN * DIM + DIM / 2.0) - decy;
+        int x0 = jx - pr > 0 ? jx - pr : 0, y0 = jy - pr > 0 ? jy - pr : 0;
+        int x1 = jx + pr < DIM ? jx + pr : DIM, y1 = jy + pr < DIM ? jy + pr : DIM;
+        for (int a = x0; a < x1; a++)
+            for (int b = y0; b < y1; b++)
+                if (t->cells[(size_t)a * DIM + b] > 1.0) {
+                    if (n < cap) { out[2 * n] = index_to_distance(a) + t->cx; out[2 * n + 1] = index_to_distance(b) + t->cy; }
+                    n++;
+                }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------- weights -- */
+
+/* Robot._generate_sample_weight robot.py:118-139 for K guesses. */
+void orc_sample_weight(const orc_map *m, const double *guesses, int K, const double *px,
+                       const double *py, const double *dist, int B, const double *prs, double *w)
+{
+    for (int k = 0; k < K; k++) {
+        const double *g = guesses + 3 * k;
+        double c = cos(g[2]), s = sin(g[2]), obs = 1.0;
+        for (int j = 0; j < B; j++) {
+            if (dist[j] < W_MAX_R && dist[j] > W_MIN_R) {
+                double gx, gy, L;
+                xform(c, s, g[0], g[1], px[j], py[j], &gx, &gy);
+                if (orc_get_odds_at(m, gx, gy, &L)) obs += L;
+            }
+        }
+        w[k] = obs * prs[k];
+    }
+}
+
+/* Lower Cholesky factor of a symmetric 3x3 (row-major); our sampling transform. */
+static void chol3(const double *c, double *l)
+{
+    l[0] = sqrt(c[0]);
+    l[1] = c[3] / l[0];
+    l[2] = c[6] / l[0];
+    l[3] = sqrt(c[4] - l[1] * l[1]);
+    l[4] = (c[7] - l[2] * l[1]) / l[3];
+    l[5] = sqrt((c[8] - l[2] * l[2]) - l[4] * l[4]);
+}
+
+/* guesses = mean + L z  (stands in for np.random.multivariate_normal, robot.py:81)
+ * prs     = N(guess; mean, cov) * 10   (robot.py:87) */
+void orc_propose(const double *mean, const double *cov, const double *z, int K,
+                 double *guesses, double *prs)
+{
+    double l[6];
+    chol3(cov, l);
+    double nrm = (2.0 * M_PI) * sqrt(2.0 * M_PI) * ((l[0] * l[3]) * l[5]);
+    for (int k = 0; k < K; k++) {
+        const double *zz = z + 3 * k;
+        double *g = guesses + 3 * k;
+        g[0] = mean[0] + l[0] * zz[0];
+        g[1] = mean[1] + (l[1] * zz[0] + l[3] * zz[1]);
+        g[2] = mean[2] + ((l[2] * zz[0] + l[4] * zz[1]) + l[5] * zz[2]);
+        double d0 = g[0] - mean[0], d1 = g[1] - mean[1], d2 = g[2] - mean[2];
+        double y0 = d0 / l[0];
+        double y1 = (d1 - l[1] * y0) / l[3];
+        double y2 = ((d2 - l[2] * y0) - l[4] * y1) / l[5];
+        double maha = (y0 * y0 + y1 * y1) + y2 * y2;
+        prs[k] = exp(-0.5 * maha) / nrm * 10.0;
+    }
+}
+
+/* Weight normalisation and weighted moments, robot.py:88-108.  Returns norm. */
+double orc_moments(const double *guesses, const double *w, int K, double *mean, double *sigma)
+{
+    double mn = w[0];
+    for (int k = 1; k < K; k++) if (w[k] < mn) mn = w[k];
+    double norm = 0.0;
+    mean[0] = mean[1] = mean[2] = 0.0;
+    for (int k = 0; k < K; k++) {
+        double wk = (w[k] - mn) + 1e-2;
+        for (int a = 0; a < 3; a++) mean[a] = mean[a] + guesses[3 * k + a] * wk;
+        norm = norm + wk;
+    }
+    for (int a = 0; a < 3; a++) mean[a] = mean[a] / norm;
+    for (int a = 0; a < 9; a++) sigma[a] = 0.0;
+    for (int k = 0; k < K; k++) {
+        double wk = (w[k] - mn) + 1e-2, d[3];
+        for (int a = 0; a < 3; a++) d[a] = guesses[3 * k + a] + (-mean[a]);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) sigma[3 * a + b] = sigma[3 * a + b] + (d[a] * d[b]) * wk;
+    }
+    for (int a = 0; a < 9; a++) sigma[a] = sigma[a] / norm;
+    return norm + mn * K;
+}
+
+/* ------------------------------------------------------------- matcher -- */
+
+/* Rotation lattice of OUR restated matcher: step = acos(1 - d^2/(2 r^2)) with
+ * d = cell size and r = the matcher's range gate, so that a point at the gate
+ * moves at most one cell per step. */
+double orc_rot_step(void) { return acos(1.0 - (CS * CS) / (2.0 * MATCH_MAX_R * MATCH_MAX_R)); }
+int orc_rot_count(void) { return (int)floor(ROT_RANGE / orc_rot_step()); }
+
+/* Window half-width in cells for a clamp value from robot.py:64-65. */
+int orc_window_cells(double r)
+{
+    int n = (int)floor(r / CS + 1e-9);
+    return n > MAX_NT ? MAX_NT : n;
+}
+
+/* Robot.map_update robot.py:62-65 : search window from the pose covariance. */
+void orc_pose_range(const double *cov, double *rx, double *ry)
+{
+    double p0 = sqrt(cov[0]) * 30.0, p1 = sqrt(cov[4]) * 30.0;
+    *rx = fmax(fmin(4 * p0, 0.7), 0.1);
+    *ry = fmax(fmin(4 * p1, 0.7), 0.1);
+}
+
+/* Integer "tenths" of a log-odds value (values are sums of +0.8/+0.2/-0.3). */
+static int tenths(double L) { return (int)lround(L * 10.0); }
+
+/* Occupancy of a cell of the global read lattice: G = 800*t + ix - 400. */
+static int occ_cell(const orc_map *m, int Gx, int Gy)
+{
+    int tx = (int)floor((Gx + 400) / 800.0), ty = (int)floor((Gy + 400) / 800.0);
+    int ix = Gx + 400 - 800 * tx, iy = Gy + 400 - 800 * ty;
+    for (int i = 0; i < m->n; i++)
+        if (m->tiles[i].cx == tx * TILE_LEN && m->tiles[i].cy == ty * TILE_LEN)
+            return tenths(m->tiles[i].cells[(size_t)ix * DIM + iy]) > 10;    /* gridmap.py:153 (L > 1.0) */
+    return 0;
+}
+
+static int64_t match_key(int score, int i, int j, int k)
+{
+    /* higher score first; then smaller |k|, |i|, |j|; then negative before positive */
+    int64_t key = (int64_t)score << 32;
+    key |= (int64_t)(255 - abs(k)) << 24;
+    key |= (int64_t)(31 - abs(i)) << 19;
+    key |= (int64_t)(31 - abs(j)) << 14;
+    key |= (int64_t)(k < 0) << 13;
+    key |= (int64_t)(i < 0) << 12;
+    key |= (int64_t)(j < 0) << 11;
+    return key;
+}
+
+/*
+ * Restated scan-to-map matcher (G1 + G2 of SURVEY section 8a).
+ *   front-end  hybridmap.py:210-240 : curr points = beam endpoints at the guess
+ *              (range gate 1e-3 < r < 11), snapped to the corner of their cell in
+ *              an existing tile, relative to the guess position, |c| < 11.
+ *   search     contract of matchScanCustom.m:9-17 : correlative search over
+ *              |dx|<=rx, |dy|<=ry on the 0.05 m lattice and |dth|<=pi/6 on the
+ *              orc_rot_step() lattice; score = number of curr points whose
+ *              rotated+shifted cell is occupied (tenths > 10) in the particle's
+ *              own tiles.
+ *   gate       matchScanCustom.m:52-57 isValidPose : strictly inside the window
+ *              and not the zero correction, else cov = NaN, score = 0 (:26-28).
+ *   covariance weights 2^(score - best) over the translation slice at the best
+ *              rotation and over the rotation line at the best translation,
+ *              cross terms zero, plus the lattice quantisation variance.
+ *   result     guess + correction, hybridmap.py:253-255.
+ * No NDT refinement (matchScanCustom.m:32-50): declared, see DESIGN.md.
+ * out_pose[3], out_cov[9]; returns 1 if valid else 0.  dbg (nullable) receives
+ * {M, best_i, best_j, best_k, nx, ny}; slice (nullable, 29*29 ints) the scores of
+ * the translation slice at the best rotation, row j, column i.
+ */
+/* Front-end of HybridMap.get_scan_match hybridmap.py:216-228,236,240: the
+ * `valid_curr_points` list handed to the matcher.  cx, cy have room for B. */
+static int match_curr(const orc_map *m, const double *guess, const double *px, const double *py,
+                      const double *dist, int B, double *cx, double *cy)
+{
+    int M = 0;
+    double c0 = cos(guess[2]), s0 = sin(guess[2]);
+    for (int j = 0; j < B; j++) {
+        if (!(dist[j] < MATCH_MAX_R && dist[j] > MATCH_MIN_R)) continue;      /* :217-218 */
+        double gx, gy;
+        xform(c0, s0, guess[0], guess[1], px[j], py[j], &gx, &gy);
+        orc_tile *t = map_with_pos(m, gx, gy);                                /* :220-221 */
+        int ix, iy;
+        if (!t || !get_cell(gx - t->cx, gy - t->cy, &ix, &iy)) continue;
+        double qx = (index_to_distance(ix) + t->cx) - guess[0];               /* :226-228,236 */
+        double qy = (index_to_distance(iy) + t->cy) - guess[1];
+        if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;               /* :240 */
+        cx[M] = qx; cy[M] = qy; M++;
+    }
+    return M;
+}
+
+int orc_match_curr(const orc_map *m, const double *guess, const double *px, const double *py,
+                   const double *dist, int B, double *out_xy)
+{
+    double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
+    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
+    for (int q = 0; q < M; q++) { out_xy[2 * q] = cx[q]; out_xy[2 * q + 1] = cy[q]; }
+    free(cx); free(cy);
+    return M;
+}
+
+int orc_match(const orc_map *m, const double *guess, const double *px, const double *py,
+              const double *dist, int B, double rx, double ry,
+              double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
+{
+    double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
+    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
+    /* cell of the guess position and the guess's offset inside it */
+    int t0x = (int)floor(guess[0] / TILE_LEN + 0.5), t0y = (int)floor(guess[1] / TILE_LEN + 0.5);
+    if (guess[0] < t0x * TILE_LEN - 20.0) t0x--; else if (guess[0] >= t0x * TILE_LEN + 20.0) t0x++;
+    if (guess[1] < t0y * TILE_LEN - 20.0) t0y--; else if (guess[1] >= t0y * TILE_LEN + 20.0) t0y++;
+    int i0x = (int)((guess[0] - t0x * TILE_LEN) / TILE_LEN * DIM + DIM / 2.0);
+    int i0y = (int)((guess[1] - t0y * TILE_LEN) / TILE_LEN * DIM + DIM / 2.0);
+    int G0x = 800 * t0x + i0x - 400, G0y = 800 * t0y + i0y - 400;
+    double fx = guess[0] - (index_to_distance(i0x) + t0x * TILE_LEN);
+    double fy = guess[1] - (index_to_distance(i0y) + t0y * TILE_LEN);
+
+    int nx = orc_window_cells(rx), ny = orc_window_cells(ry), nk = orc_rot_count();
+    double step = orc_rot_step();
+    int W = 2 * MAX_NT + 1;
+    /* dense occupancy window around the guess cell: every lookup of the search
+     * lands inside it (|c| < 11 m = 220 cells, +1 rounding, +14 shift) */
+    enum { R = 240, S = 2 * R + 1 };
+    unsigned char *win = (unsigned char *)malloc((size_t)S * S);
+    for (int b = -R; b <= R; b++)
+        for (int a = -R; a <= R; a++) win[(size_t)(b + R) * S + (a + R)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+    int *vol = (int *)calloc((size_t)(2 * nk + 1) * W * W, sizeof(int));
+    int *bx = (int *)malloc(sizeof(int) * (size_t)(M ? M : 1)), *by = (int *)malloc(sizeof(int) * (size_t)(M ? M : 1));
+    int64_t best = -1; int bi = 0, bj = 0, bk = 0;
+    for (int k = -nk; k <= nk; k++) {
+        double ck = cos(k * step), sk = sin(k * step);
+        int *sl = vol + (size_t)(k + nk) * W * W;
+        for (int q = 0; q < M; q++) {
+            double rxq = (ck * cx[q] - sk * cy[q]) + fx;
+            double ryq = (sk * cx[q] + ck * cy[q]) + fy;
+            bx[q] = (int)floor(rxq * 20.0);      /* cell offsets from the guess cell */
+            by[q] = (int)floor(ryq * 20.0);
+            if (abs(bx[q]) + nx > R || abs(by[q]) + ny > R) { fprintf(stderr, "orc_match: window overflow\n"); abort(); }
+        }
+        for (int q = 0; q < M; q++)
+            for (int j = -ny; j <= ny; j++) {
+                const unsigned char *row = win + (size_t)(by[q] + j + R) * S + (bx[q] + R);
+                int *o = sl + (j + MAX_NT) * W + MAX_NT;
+                for (int i = -nx; i <= nx; i++) o[i] += row[i];
+            }
+        for (int j = -ny; j <= ny; j++)
+            for (int i = -nx; i <= nx; i++) {
+                int64_t key = match_key(sl[(j + MAX_NT) * W + (i + MAX_NT)], i, j, k);
+                if (key > best) { best = key; bi = i; bj = j; bk = k; }
+            }
+    }
+    free(win);
+    int bs = (int)(best >> 32);
+    if (dbg) { dbg[0] = M; dbg[1] = bi; dbg[2] = bj; dbg[3] = bk; dbg[4] = nx; dbg[5] = ny; }
+    if (slice)
+        for (int j = 0; j < W; j++)
+            for (int i = 0; i < W; i++) slice[j * W + i] = vol[((size_t)(bk + nk) * W + j) * W + i];
+    out_pose[0] = guess[0] + bi * CS;                                          /* hybridmap.py:253-255 */
+    out_pose[1] = guess[1] + bj * CS;
+    out_pose[2] = guess[2] + bk * step;
+    int valid = fabs(bi * CS) < rx && fabs(bj * CS) < ry && fabs(bk * step) < ROT_RANGE &&
+                (bi != 0 || bj != 0 || bk != 0);                                /* matchScanCustom.m:52-57 */
+    if (!valid) {
+        for (int a = 0; a < 9; a++) out_cov[a] = NAN;                          /* matchScanCustom.m:26-28 */
+        *out_score = 0.0;
+    } else {
+        int64_t W0 = 0, Wx = 0, Wy = 0, Wxx = 0, Wyy = 0, Wxy = 0;
+        for (int j = -ny; j <= ny; j++)
+            for (int i = -nx; i <= nx; i++) {
+                int d = bs - vol[((size_t)(bk + nk) * W + (j + MAX_NT)) * W + (i + MAX_NT)];
+                if (d > 40) continue;
+                int64_t w = (int64_t)1 << (40 - d);
+                W0 += w; Wx += w * i; Wy += w * j; Wxx += w * i * i; Wyy += w * j * j; Wxy += w * i * j;
+            }
+        int64_t T0 = 0, T1 = 0, T2 = 0;
+        for (int k = -nk; k <= nk; k++) {
+            int d = bs - vol[((size_t)(k + nk) * W + (bj + MAX_NT)) * W + (bi + MAX_NT)];
+            if (d > 40) continue;
+            int64_t w = (int64_t)1 << (40 - d);
+            T0 += w; T1 += w * k; T2 += w * k * k;
+        }
+        double mx = (double)Wx / (double)W0, my = (double)Wy / (double)W0, mt = (double)T1 / (double)T0;
+        double q = CS * CS, qt = step * step;
+        for (int a = 0; a < 9; a++) out_cov[a] = 0.0;
+        out_cov[0] = ((double)Wxx / (double)W0 - mx * mx) * q + q / 12.0;
+        out_cov[4] = ((double)Wyy / (double)W0 - my * my) * q + q / 12.0;
+        out_cov[1] = out_cov[3] = ((double)Wxy / (double)W0 - mx * my) * q;
+        out_cov[8] = ((double)T2 / (double)T0 - mt * mt) * qt + qt / 12.0;
+        *out_score = (double)bs;
+    }
+    free(cx); free(cy); free(vol); free(bx); free(by);
+    return valid;
+}
+
+/* -------------------------------------------------------------- motion -- */
+
+/* Robot.imu_update robot.py:45-57 with the three loader families:
+ *   0 absolute-set       IntelIMUData.py:22-36   u = (x, y, theta)
+ *   1 additive velocity  IntelRawIMUData.py:33-55 (same shape: Aces, Freid*, Obero, Bele)
+ *                        u = (vx, vy, w), par = (a_xy, b_xy, a_th, b_th)
+ *   2 unicycle           DefaultIMUData.py:25-54  u = (v, w)
+ * dt is in seconds (the loaders divide the 1e-4 s tick count by 1e4). */
+static void mat3mul(const double *a, const double *b, double *o)
+{
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+            o[3 * r + c] = (a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c]) + a[3 * r + 2] * b[6 + c];
+}
+
+void orc_motion(int family, const double *u, double dt, const double *par, double *pose, double *cov)
+{
+    double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, np_[3];
+    if (family == 0) {
+        np_[0] = u[0]; np_[1] = u[1]; np_[2] = u[2];
+        F[0] = 0.01 * 0.01; F[4] = 0.01 * 0.01; F[8] = (0.2 * M_PI / 180) * (0.2 * M_PI / 180);
+        Q[0] = Q[4] = Q[8] = 1.0;
+        Q[2] = u[0] - pose[0];
+        Q[5] = u[1] - pose[1];
+    } else if (family == 1) {
+        np_[0] = pose[0] + u[0] * dt; np_[1] = pose[1] + u[1] * dt; np_[2] = pose[2] + u[2] * dt;
+        double q0 = par[0] + par[1] * fabs(u[0]) * dt, q1 = par[0] + par[1] * fabs(u[1]) * dt,
+               q2 = par[2] + par[3] * fabs(u[2]) * dt;
+        Q[0] = fabs(q0 * q0); Q[4] = fabs(q1 * q1); Q[8] = fabs(q2 * q2);
+    } else {
+        double th = pose[2] + dt * u[1];
+        np_[0] = pose[0] + dt * u[0] * cos(th);
+        np_[1] = pose[1] + dt * u[0] * sin(th);
+        np_[2] = th;
+        double cp = cos(pose[2]), sp = sin(pose[2]);
+        F[2] = dt * u[0] * cp;
+        F[5] = dt * u[0] * sp;
+        double g0 = dt * cp, g1 = dt * sp, g2 = dt, m0 = 0.05 * 0.05, m1 = (M_PI / 180 / 2) * (M_PI / 180 / 2);
+        /* |G M G^T| + noise, DefaultIMUData.py:44-54 ; G = [[g0,0],[g1,0],[0,g2]] */
+        Q[0] = fabs((g0 * m0) * g0) + 0.01 * 0.01;
+        Q[1] = fabs((g0 * m0) * g1);
+        Q[3] = fabs((g1 * m0) * g0);
+        Q[4] = fabs((g1 * m0) * g1) + 0.01 * 0.01;
+        Q[8] = fabs((g2 * m1) * g2) + (0.2 * M_PI / 180) * (0.2 * M_PI / 180);
+    }
+    double t1[9], Ft[9], t2[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Ft[3 * r + c] = F[3 * c + r];
+    mat3mul(F, cov, t1);                                    /* robot.py:50 */
+    mat3mul(t1, Ft, t2);
+    for (int a = 0; a < 9; a++) cov[a] = t2[a] + Q[a];      /* robot.py:51 */
+    pose[0] = np_[0]; pose[1] = np_[1]; pose[2] = np_[2];
+}
+
+/* ------------------------------------------------------------ resample -- */
+
+/* main.resample main.py:46-79 on float64 weights (declared pin).
+ * Returns 0 = no resample (ancestors = identity), 1 = resampled, -1 = the
+ * reference's AssertionError("Incorrect number of resampled weights."). */
+int orc_resample(const double *weights, int N, double u01, int *anc)
+{
+    double mx = weights[0], mn = weights[0];
+    for (int i = 1; i < N; i++) { if (weights[i] > mx) mx = weights[i]; if (weights[i] < mn) mn = weights[i]; }
+    for (int i = 0; i < N; i++) anc[i] = i;
+    if (!(mx - mn > RESAMPLE_TRIGGER)) return 0;                          /* :50 */
+    double *w = (double *)malloc(sizeof(double) * (size_t)N);
+    for (int i = 0; i < N; i++) w[i] = weights[i] == -INFINITY ? 0.0 : weights[i];   /* :53 */
+    mn = w[0];
+    for (int i = 1; i < N; i++) if (w[i] < mn) mn = w[i];
+    if (mn < 0) { double a = fabs(mn); for (int i = 0; i < N; i++) if (w[i] != 0) w[i] += a; }  /* :54-55 */
+    double tot = 0.0;
+    for (int i = 0; i < N; i++) tot = tot + w[i];                          /* :57 builtin sum, left to right */
+    double slice = tot / N;
+    double start = u01 * slice;                                            /* :59 */
+    double cur = 0.0;
+    long emitted = 0;
+    int ok = 1;
+    for (int i = 0; i < N; i++) {                                          /* :61-64 */
+        cur += w[i];
+        double f = floor((cur - start) / slice);
+        if (!(f > -4e18 && f < 4e18)) { ok = 0; break; }                  /* math.floor raises on nan/inf */
+        long num = (long)f - emitted + 1;
+        for (long q = 0; q < num; q++) { if (emitted < N) anc[emitted] = i; emitted++; }
+    }
+    free(w);
+    if (!ok || emitted != N) return -1;                                    /* :66-67 */
+    return 1;
+}
+
+/* -------------------------------------------------------- whole filter -- */
+
+typedef struct {
+    int N, B, K;
+    double *pose;      /* N*3 */
+    double *cov;       /* N*9 */
+    double *weight;    /* N   current weight = weight()[-1] */
+    orc_map **map;     /* N   */
+    int *valid;        /* N   last match validity */
+    double *px, *py, *dist;
+} orc_filter;
+
+/* particles = [Robot(eng) ...] main.py:87 ; Robot.__init__ robot.py:20-28. */
+orc_filter *orc_filter_new(int N, int B, int K)
+{
+    orc_filter *f = (orc_filter *)calloc(1, sizeof(orc_filter));
+    f->N = N; f->B = B; f->K = K;
+    f->pose = (double *)calloc((size_t)N * 3, sizeof(double));
+    f->cov = (double *)calloc((size_t)N * 9, sizeof(double));
+    f->weight = (double *)malloc(sizeof(double) * (size_t)N);
+    f->map = (orc_map **)malloc(sizeof(orc_map *) * (size_t)N);
+    f->valid = (int *)calloc((size_t)N, sizeof(int));
+    f->px = (double *)calloc((size_t)B, sizeof(double));
+    f->py = (double *)calloc((size_t)B, sizeof(double));
+    f->dist = (double *)calloc((size_t)B, sizeof(double));
+    for (int i = 0; i < N; i++) { f->weight[i] = 1.0; f->map[i] = orc_map_new(); }
+    return f;
+}
+
+void orc_filter_free(orc_filter *f)
+{
+    if (!f) return;
+    for (int i = 0; i < f->N; i++) orc_map_free(f->map[i]);
+    free(f->pose); free(f->cov); free(f->weight); free(f->map); free(f->valid);
+    free(f->px); free(f->py); free(f->dist); free(f);
+}
+
+double *orc_filter_pose(orc_filter *f) { return f->pose; }
+double *orc_filter_cov(orc_filter *f) { return f->cov; }
+double *orc_filter_weight(orc_filter *f) { return f->weight; }
+int *orc_filter_valid(orc_filter *f) { return f->valid; }
+orc_map *orc_filter_map(orc_filter *f, int i) { return f->map[i]; }
+
+void orc_filter_set_scan(orc_filter *f, const double *ranges, const double *angles)
+{
+    orc_scan_prepare(ranges, angles, f->B, f->px, f->py, f->dist);
+}
+
+/* [p.imu_update(reading) for p in particles] main.py:144. */
+void orc_filter_motion(orc_filter *f, int family, const double *u, double dt, const double *par)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < f->N; i++) orc_motion(family, u, dt, par, f->pose + 3 * i, f->cov + 9 * i);
+}
+
+/* Integrate the current scan at every particle's pose (the commented-out map
+ * seeding at main.py:89-90). */
+void orc_filter_integrate(orc_filter *f)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < f->N; i++) orc_map_update(f->map[i], f->pose + 3 * i, f->px, f->py, f->dist, f->B);
+}
+
+/* One particle of Robot.map_update robot.py:59-115 (scan-to-map branch), z = K*3 normals. */
+static void particle_map_update(orc_filter *f, int i, const double *z)
+{
+    double *pose = f->pose + 3 * i, *cov = f->cov + 9 * i;
+    orc_map *m = f->map[i];
+    double rx, ry, mp[3], mc[9], sc;
+    orc_pose_range(cov, &rx, &ry);
+    int valid = orc_match(m, pose, f->px, f->py, f->dist, f->B, rx, ry, mp, mc, &sc, NULL, NULL);
+    f->valid[i] = valid;
+    if (!valid) {                                                          /* :73-78 */
+        double one = 1.0, w;
+        orc_map_update(m, pose, f->px, f->py, f->dist, f->B);
+        orc_sample_weight(m, pose, 1, f->px, f->py, f->dist, f->B, &one, &w);
+        f->weight[i] = w + f->weight[i];
+        return;
+    }
+    int K = f->K;
+    double *g = (double *)malloc(sizeof(double) * (size_t)K * 5), *prs = g + 3 * K, *w = g + 4 * K;
+    double mean[3], sigma[9];
+    orc_propose(mp, mc, z, K, g, prs);                                     /* :80-87 */
+    orc_sample_weight(m, g, K, f->px, f->py, f->dist, f->B, prs, w);       /* :88 */
+    double norm = orc_moments(g, w, K, mean, sigma);                       /* :89-108 */
+    for (int a = 0; a < 3; a++) pose[a] = mean[a];                         /* :109-113 */
+    for (int a = 0; a < 9; a++) cov[a] = sigma[a];
+    f->weight[i] = norm + f->weight[i];                                    /* :114 */
+    orc_map_update(m, pose, f->px, f->py, f->dist, f->B);                  /* :115 */
+    free(g);
+}
+
+/* [p.map_update(scan, last_scan, False) for p in particles] main.py:157.
+ * z holds N*K*3 standard normals, particle-major. */
+void orc_filter_map_update(orc_filter *f, const double *z)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i);
+}
+
+/* particles = resample(particles) main.py:160 with Robot.copy robot.py:141-149. */
+int orc_filter_resample(orc_filter *f, double u01, int *anc)
+{
+    int N = f->N, rc = orc_resample(f->weight, N, u01, anc);
+    if (rc != 1) return rc;
+    double *pose = (double *)malloc(sizeof(double) * (size_t)N * 3), *cov = (double *)malloc(sizeof(double) * (size_t)N * 9);
+    orc_map **map = (orc_map **)malloc(sizeof(orc_map *) * (size_t)N);
+    char *used = (char *)calloc((size_t)N, 1);
+    for (int j = 0; j < N; j++) {                                          /* :69-75 */
+        int a = anc[j];
+        memcpy(pose + 3 * j, f->pose + 3 * a, 3 * sizeof(double));
+        memcpy(cov + 9 * j, f->cov + 9 * a, 9 * sizeof(double));
+        if (!used[a]) { map[j] = f->map[a]; used[a] = 1; } else map[j] = NULL;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int j = 0; j < N; j++) if (!map[j]) map[j] = orc_map_copy(f->map[anc[j]]);
+    for (int a = 0; a < N; a++) if (!used[a]) orc_map_free(f->map[a]);
+    memcpy(f->pose, pose, sizeof(double) * (size_t)N * 3);
+    memcpy(f->cov, cov, sizeof(double) * (size_t)N * 9);
+    memcpy(f->map, map, sizeof(orc_map *) * (size_t)N);
+    for (int j = 0; j < N; j++) f->weight[j] = 1.0;                        /* :77-78 */
+    free(pose); free(cov); free(map); free(used);
+    return 1;
+}
