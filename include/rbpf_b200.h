@@ -1,0 +1,168 @@
+/*
+ * rbpf_b200.h -- C ABI of the B200-native RBPF per-scan update.
+ *
+ * Drop-in boundary for the hot path of amansanghvi/Thesis (motion -> scan match
+ * -> likelihood weighting -> log-odds ray-cast -> systematic resampling).  The
+ * reference has no FFI of its own for this path: it is driven through Python
+ * duck-typed objects (Robot, robot.py:19-157; Map ABC, Map.py:16-102) from three
+ * list comprehensions and one function in main.py:144,157-160, and its only
+ * foreign call is the MATLAB engine RPC eng.matchScanCustom(...)
+ * (hybridmap.py:244-251).  Each entry point below names the reference interface
+ * it replaces; thesis_b200/particles.py is the ctypes host side that keeps the
+ * reference's Python signatures on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative rbpf_status; the text of
+ *     the last error of a handle is rbpf_last_error(h).
+ *   - host pointers are caller-owned, read during the call (inputs) or written
+ *     before return (outputs).  Pointers documented as DEVICE pointers must be
+ *     device memory on the handle's GPU.
+ *   - a handle is not thread-safe; all work is enqueued on the stream given at
+ *     creation (0 = the legacy default stream) and calls that return data to the
+ *     host synchronise that stream.
+ *   - there is no CPU fallback: without a CUDA device rbpf_create fails with
+ *     RBPF_ERR_CUDA.
+ *   - poses are (x, y, theta) float64, covariances row-major 3x3 float64, maps
+ *     are int8 log-odds in tenths (reference float64 value = tenths / 10, exact
+ *     to 1.1e-14).
+ */
+#ifndef RBPF_B200_H
+#define RBPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbpf_ctx *rbpf_handle;
+
+typedef enum {
+    RBPF_OK = 0,
+    RBPF_ERR_ARG = -1,        /* bad argument / configuration */
+    RBPF_ERR_CUDA = -2,       /* CUDA runtime failure (text in rbpf_last_error) */
+    RBPF_ERR_POOL = -3,       /* tile pool exhausted */
+    RBPF_ERR_RESAMPLE = -4,   /* main.py:66-67 AssertionError("Incorrect number of resampled weights.") */
+    RBPF_ERR_WORLD = -5       /* a ray left the configured world extent (cells were dropped) */
+} rbpf_status;
+
+/* Motion-model families of the reference's IMU loaders (robot.py:45-57). */
+typedef enum {
+    RBPF_MOTION_ABSOLUTE = 0, /* IntelIMUData.py:22-36     u = (x, y, theta) */
+    RBPF_MOTION_VELOCITY = 1, /* IntelRawIMUData.py:33-55 (Aces, Freid*, Obero, Bele) u = (vx, vy, w),
+                                 par = (a_xy, b_xy, a_th, b_th) of get_cov_input_uncertainty */
+    RBPF_MOTION_UNICYCLE = 2  /* DefaultIMUData.py:25-54   u = (v, w) */
+} rbpf_motion_family;
+
+typedef struct {
+    int32_t n_particles;      /* particles owned by THIS handle (rank-local slice), main.py:44,87 */
+    int32_t n_beams;          /* beams per sweep, <= 384 (180 Intel/ACES, 360 Freiburg, 361 UNSW/Bele) */
+    int32_t n_samples;        /* proposal samples per particle, robot.py:17 NUM_SAMPLE_POINTS = 30; <= 32 */
+    int32_t world_tiles_x;    /* odd number of 40 m reference tiles along x, centred on tile (0,0); x*y <= 64 */
+    int32_t world_tiles_y;
+    uint32_t pool_subtiles;   /* capacity of the copy-on-write pool in 160x160-cell sub-tiles (25,600 B each) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t rank;             /* rank / world of the particle sharding (0 / 1 on a single GPU) */
+    int32_t world;
+    int32_t reserved0;
+    uint64_t stream;          /* cudaStream_t to enqueue on, 0 = legacy default stream */
+    uint64_t seed;            /* Philox key for device-side draws when the caller supplies none */
+} rbpf_config;
+
+typedef struct {
+    uint32_t pool_subtiles;   /* capacity */
+    uint32_t pool_in_use;     /* sub-tiles currently referenced */
+    uint64_t cow_copies;      /* sub-tiles copied because they were shared (cumulative) */
+    uint64_t fresh_allocs;    /* zero-filled sub-tiles handed out (cumulative) */
+    uint64_t cells_dropped;   /* ray cells outside the world extent (cumulative) */
+    uint64_t resamples;       /* scans whose resample triggered (cumulative) */
+    uint64_t match_failed;    /* particle-scans whose match failed the isValidPose gate (cumulative) */
+    uint64_t shared_refs;     /* page-table entries whose sub-tile is shared by >1 particle (snapshot) */
+    uint64_t total_refs;      /* allocated page-table entries over all particles (snapshot) */
+} rbpf_stats_t;
+
+/* Replaces `particles = [Robot(eng) for _ in range(NUM_PARTICLES)]` (main.py:87,
+ * Robot.__init__ robot.py:20-28, HybridMap.__init__ hybridmap.py:66-70): N
+ * particles at pose 0, zero covariance, weight 1.0, one blank tile at (0,0). */
+int rbpf_create(const rbpf_config *cfg, rbpf_handle *out);
+int rbpf_destroy(rbpf_handle h);
+const char *rbpf_last_error(rbpf_handle h);
+
+/* Replaces `Lidar.__getitem__` -> `Scan.__init__` (lidar.py:28-31,76-80): one
+ * sweep, ranges[B] in metres and angles[B] in radians, host pointers. */
+int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams);
+
+/* Replaces `[p.imu_update(reading) for p in particles]` (main.py:144,
+ * robot.py:45-57).  u[4], par[4] (unused entries 0), dt in seconds. */
+int rbpf_motion(rbpf_handle h, int32_t family, const double *u, double dt, const double *par);
+
+/* Replaces the matcher half of Robot.map_update (robot.py:62-71):
+ * HybridMap.get_scan_match (hybridmap.py:210-261) + eng.matchScanCustom
+ * (matchScanCustom.m:1-58).  Results stay on the device (see getters). */
+int rbpf_scan_match(rbpf_handle h);
+
+/* Replaces the sampling/weighting half of Robot.map_update (robot.py:73-114):
+ * proposal samples, _generate_sample_weight (robot.py:118-139), moments, weight
+ * accumulation.  z = N*K*3 standard normals (host, particle-major) or NULL for
+ * device Philox draws.  Particles whose match failed are left for
+ * rbpf_integrate (their weight needs the updated map, robot.py:75-77). */
+int rbpf_weight(rbpf_handle h, const double *z);
+
+/* Replaces HybridMap.update (hybridmap.py:95-145) at every particle's current
+ * pose, then the NaN-covariance weight fallback (robot.py:76-77) for particles
+ * whose last match failed.  Also the map seeding of main.py:89-90 when called
+ * before any match (fallback_weights = 0). */
+int rbpf_integrate(rbpf_handle h, int32_t fallback_weights);
+
+/* Replaces `particles = resample(particles)` (main.py:46-79,160) and the deep
+ * copies of Robot.copy (robot.py:141-149) by copy-on-write page-table sharing.
+ * u01 = the uniform of main.py:59 or NULL (device Philox).  ancestors_out
+ * (nullable, host, N_global int32) and did_resample (nullable) synchronise. */
+int rbpf_resample(rbpf_handle h, const double *u01, int32_t *ancestors_out, int32_t *did_resample);
+
+/* One lidar event for throughput runs: set_scan + scan_match + weight +
+ * integrate + resample with device-side draws and no host synchronisation. */
+int rbpf_step(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams);
+
+/* State access (host pointers; each call synchronises the stream). */
+int rbpf_get_poses(rbpf_handle h, double *out_n3);        /* Robot.get_latest_pose robot.py:42-43 */
+int rbpf_get_covs(rbpf_handle h, double *out_n9);         /* Robot._cov */
+int rbpf_get_weights(rbpf_handle h, double *out_n);       /* Robot.weight()[-1] robot.py:39-40 */
+int rbpf_set_poses(rbpf_handle h, const double *in_n3);
+int rbpf_set_covs(rbpf_handle h, const double *in_n9);
+int rbpf_set_weights(rbpf_handle h, const double *in_n);
+/* Matcher results of the last rbpf_scan_match: pose[N*3], cov[N*9] (NaN when
+ * invalid), score[N], valid[N], best[N*4] = (i, j, k, n_curr_points). */
+int rbpf_get_match(rbpf_handle h, double *pose_n3, double *cov_n9, double *score_n, int32_t *valid_n, int32_t *best_n4);
+/* Inject matcher results (pose[N*3], cov[N*9], valid[N]) in place of
+ * rbpf_scan_match -- the seam at which the reference calls MATLAB
+ * (hybridmap.py:244-256); lets the weighting stage be checked against the
+ * reference with a canned matcher answer. */
+int rbpf_set_match(rbpf_handle h, const double *pose_n3, const double *cov_n9, const int32_t *valid_n);
+/* Score slice (29x29 int32, row j, column i) at the best rotation of one particle. */
+int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *out_29x29);
+
+/* One 40 m reference tile of one particle as the reference stores it: 800x800
+ * float64 [ix][iy] (gridmap.py:32).  *exists = 0 when the particle has no such
+ * HybridMapEntry (out is zero-filled).  cx, cy = tile centre in metres. */
+int rbpf_export_tile(rbpf_handle h, int32_t particle, int32_t cx, int32_t cy, double *out_800x800, int32_t *exists);
+/* Centres of the particle's existing tiles: out_xy[2*max_tiles]; returns count in *n. */
+int rbpf_list_tiles(rbpf_handle h, int32_t particle, int32_t *out_xy, int32_t max_tiles, int32_t *n);
+
+int rbpf_stats(rbpf_handle h, rbpf_stats_t *out);
+int rbpf_synchronize(rbpf_handle h);
+
+/* Constants of the restated matcher, for callers that need the lattice. */
+double rbpf_rot_step(void);
+int32_t rbpf_rot_count(void);
+
+/* ---- multi-GPU resampling (one handle per rank; the caller moves the bytes
+ * with NCCL, see thesis_b200/dist.py).  Pointers here are DEVICE pointers. */
+
+/* Local weights of this rank, contiguous N doubles, to be all-gathered. */
+int rbpf_weights_device_ptr(rbpf_handle h, uint64_t *dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBPF_B200_H */

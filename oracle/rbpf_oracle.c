@@ -547,8 +547,21 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
      * lands inside it (|c| < 11 m = 220 cells, +1 rounding, +14 shift) */
     enum { R = 240, S = 2 * R + 1 };
     unsigned char *win = (unsigned char *)malloc((size_t)S * S);
-    for (int b = -R; b <= R; b++)
-        for (int a = -R; a <= R; a++) win[(size_t)(b + R) * S + (a + R)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+    unsigned char *raw = (unsigned char *)malloc((size_t)(S + 2) * (S + 2));
+    for (int b = -R - 1; b <= R + 1; b++)
+        for (int a = -R - 1; a <= R + 1; a++)
+            raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+    /* 3x3 proximity kernel: a lookup cell counts when it or one of its 8
+     * neighbours is occupied (stands in for the smoothed grid matchScansGrid
+     * rasterises from the reference points) */
+    for (int b = 0; b < S; b++)
+        for (int a = 0; a < S; a++) {
+            unsigned char v = 0;
+            for (int db = 0; db < 3; db++)
+                for (int da = 0; da < 3; da++) v |= raw[(size_t)(b + db) * (S + 2) + (a + da)];
+            win[(size_t)b * S + a] = v;
+        }
+    free(raw);
     int *vol = (int *)calloc((size_t)(2 * nk + 1) * W * W, sizeof(int));
     int *bx = (int *)malloc(sizeof(int) * (size_t)(M ? M : 1)), *by = (int *)malloc(sizeof(int) * (size_t)(M ? M : 1));
     int64_t best = -1; int bi = 0, bj = 0, bk = 0;

@@ -1,0 +1,201 @@
+// common.cuh -- shared constants, device context and device helpers of the
+// B200-native RBPF update.  Compiled with -fmad=false: every a*b+c below is two
+// IEEE roundings unless written as fma(), because cell indices must replay the
+// reference's float64 expressions exactly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// ---- constants of the reference (file:line into the reference checkout) ----
+#define RB_CS 0.05              // hybridmap.py:67  cell size [m]
+#define RB_TILE_LEN 40.0        // hybridmap.py:68  reference tile side [m]
+#define RB_DIM 800              // gridmap.py:31    cells per reference tile side
+#define RB_T_OCC 8              // gridmap.py:20    +0.80 in tenths
+#define RB_T_NEAR 2             // gridmap.py:21    +0.20
+#define RB_T_EMP 3              // gridmap.py:23    -0.30 (magnitude)
+#define RB_T_MAX 30             // gridmap.py:22,24 caps +-3.0
+#define RB_T_OCC_THRESH 10      // gridmap.py:17    occupied iff L > 1.0
+#define RB_MATCH_MAX_R 11.0     // hybridmap.py:20
+#define RB_MATCH_MIN_R 1e-3     // hybridmap.py:218
+#define RB_CLIP_R 15.0          // hybridmap.py:107-108
+#define RB_W_MAX_R 25.0         // robot.py:130
+#define RB_W_MIN_R 0.01         // robot.py:130
+#define RB_RESAMPLE_TRIGGER 200.0 // main.py:50
+#define RB_NT_MAX 14            // 0.7 m window clamp (robot.py:64-65) in cells
+
+// ---- device layout ----
+#define RB_SUB 160                          // cells per sub-tile side (divides 800; rows are 5 sectors)
+#define RB_SUB_BYTES (RB_SUB * RB_SUB)      // int8 tenths
+#define RB_SUBS_PER_TILE (RB_DIM / RB_SUB)  // 5
+#define RB_NONE 0xFFFFFFFFu                 // unallocated page-table entry (reads as log-odds 0)
+#define RB_MAXB 384                         // max beams per sweep
+#define RB_MAXK 32                          // max proposal samples (one lane each)
+
+// matcher window (see k_match.cu)
+#define RB_WIN_R 237
+#define RB_BM_ROWS (2 * RB_WIN_R + 1)       // 475
+#define RB_BM_STRIDE 17                     // 16 data words + 1 (funnel-shift hi), odd => conflict-free rows
+#define RB_RAW_ROWS (RB_BM_ROWS + 2)
+#define RB_RAW_STRIDE 18
+#define RB_SLICE_W (2 * RB_NT_MAX + 1)      // 29
+
+struct RbStats {                            // device-side counters
+    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed;
+};
+
+struct RbFlags {                            // device-side status words
+    int pool_exhausted;                     // set by raycast prepare
+    int resample_error;                     // main.py:66-67 assertion would have fired
+    int did_resample;                       // last resample triggered
+    int world_overflow;                     // matcher window left the world / internal bound hit
+    int remote_needed;                      // multi-GPU: local slots whose ancestor is remote
+    int pad[3];
+};
+
+struct RbCtx {
+    int N, B, K;                            // local particles, beams, samples
+    int rank, world, n_global;              // sharding
+    int tiles_x, tiles_y, txh, tyh;         // world extent in reference tiles, half extents
+    int subs_x, subs_y, nsub;               // sub-tile grid of the world
+    int ux_max, uy_max;                     // storage extent in cells
+    int lut_h;                              // half extent (tiles) covered by the write LUT
+    uint32_t pool_tiles;
+    // tile pool
+    int8_t *pool;
+    uint32_t *refcnt;
+    uint32_t *free_list;
+    int *free_count;
+    // particle state (current buffers)
+    double *pose, *cov, *weight;
+    uint32_t *pt;                           // N * nsub page table
+    unsigned long long *exists;             // N  bitmask of existing reference tiles
+    // alternate buffers (resample target)
+    double *pose2, *cov2;
+    uint32_t *pt2;
+    unsigned long long *exists2;
+    // scan
+    const double *px, *py, *dist;
+    // matcher
+    const double *rot_cs;                   // (2*nk+1) * 2 : cos, sin of k*step
+    int nk;
+    double rot_step;
+    double *m_pose, *m_cov, *m_score;
+    int *m_valid, *m_best;
+    // write-path LUT (lattice cell k -> storage coordinate)
+    const uint16_t *lut;
+    // resample
+    double *w_all;                          // n_global adjusted weights / cumsum scratch
+    int *ancestors;                         // n_global
+    int *mult;                              // N  local descendants of each old local particle
+    RbStats *stats;
+    RbFlags *flags;
+    unsigned long long seed;
+    unsigned long long step_no;
+};
+
+// ---------------------------------------------------------------- helpers --
+
+// Python int(): truncation toward zero of a float64.
+__device__ __forceinline__ int rb_trunc(double v) { return __double2int_rz(v); }
+
+// Scan.from_global_reference lidar.py:111-128 with np.matmul's accumulation
+// order (round(c*px), fma(-s,py,.), + x), see oracle/rbpf_oracle.c xform().
+__device__ __forceinline__ void rb_xform(double c, double s, double x, double y, double px, double py,
+                                         double &gx, double &gy)
+{
+    gx = fma(-s, py, c * px) + x;
+    gy = fma(c, py, s * px) + y;
+}
+
+// Read path, one axis: HybridMapEntry.is_in_map hybridmap.py:44-45 on the 40 m
+// lattice followed by GridMap.get_cell gridmap.py:120-128.  Returns the tile
+// lattice index in t and the tile-local index in idx.
+__device__ __forceinline__ void rb_read_axis(double g, int &t, int &idx)
+{
+    t = __double2int_rd(g / RB_TILE_LEN + 0.5);
+    double c = RB_TILE_LEN * (double)t;
+    if (g < c - 20.0) { t--; c -= RB_TILE_LEN; }
+    else if (g >= c + 20.0) { t++; c += RB_TILE_LEN; }
+    double rel = g - c;
+    idx = rb_trunc(rel / RB_TILE_LEN * 800.0 + 400.0);
+}
+
+// GridMap.index_to_distance gridmap.py:333-334 plus the tile centre.
+__device__ __forceinline__ double rb_cell_corner(int idx, int t)
+{
+    return ((double)idx - 400.0) * RB_TILE_LEN / 800.0 + RB_TILE_LEN * (double)t;
+}
+
+// int8 log-odds (tenths) at storage cell (ux, uy) of particle p; 0 when the
+// sub-tile is unallocated or the cell is outside the world (reference: None -> 0).
+__device__ __forceinline__ int rb_cell_tenths(const RbCtx &c, int p, int ux, int uy)
+{
+    if ((unsigned)ux >= (unsigned)c.ux_max || (unsigned)uy >= (unsigned)c.uy_max) return 0;
+    int sub = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
+    uint32_t t = c.pt[(size_t)p * c.nsub + sub];
+    if (t == RB_NONE) return 0;
+    return c.pool[(size_t)t * RB_SUB_BYTES + (uy % RB_SUB) * RB_SUB + (ux % RB_SUB)];
+}
+
+// HybridMap.get_odds_at hybridmap.py:85-93 in tenths (None -> 0).
+__device__ __forceinline__ int rb_odds_tenths(const RbCtx &c, int p, double gx, double gy)
+{
+    int tx, ty, ix, iy;
+    rb_read_axis(gx, tx, ix);
+    rb_read_axis(gy, ty, iy);
+    if (tx < -c.txh || tx > c.txh || ty < -c.tyh || ty > c.tyh) return 0;
+    return rb_cell_tenths(c, p, 800 * (tx + c.txh) + ix, 800 * (ty + c.tyh) + iy);
+}
+
+__device__ __forceinline__ bool rb_tile_exists(const RbCtx &c, unsigned long long mask, int tx, int ty)
+{
+    if (tx < -c.txh || tx > c.txh || ty < -c.tyh || ty > c.tyh) return false;
+    return (mask >> ((ty + c.tyh) * c.tiles_x + (tx + c.txh))) & 1ull;
+}
+
+// Write path, one axis: lattice cell k -> storage coordinate through the LUT
+// built on the host from int((k*0.05 - c)/0.05 + 400.0) (gridmap.py:92-95).
+// Returns -1 outside the world.
+__device__ __forceinline__ int rb_write_axis(const RbCtx &c, int k, int half_tiles)
+{
+    int q = k + 800 * c.lut_h + 400;
+    if (q < 0 || q >= 800 * (2 * c.lut_h + 1)) return -1;
+    int u = (int)__ldg(&c.lut[q]) - 800 * (c.lut_h - half_tiles);
+    if (u < 0 || u >= 800 * (2 * half_tiles + 1)) return -1;
+    return u;
+}
+
+// Philox4x32-10 (counter-based RNG) for device-side draws.
+__device__ __forceinline__ void rb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, unsigned long long key,
+                                          uint32_t out[4])
+{
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double rb_u01(uint32_t hi, uint32_t lo)   // (0,1), 53 bits
+{
+    unsigned long long v = (((unsigned long long)hi << 32) | lo) >> 11;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ---- launchers (one per kernel file) ----
+void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, const double *par, cudaStream_t s);
+void rb_launch_match(const RbCtx &c, cudaStream_t s);
+void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s);
+void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s);
+void rb_launch_raycast(const RbCtx &c, cudaStream_t s);
+void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s);
+void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s);
+void rb_launch_export_tile(const RbCtx &c, int particle, int tx, int ty, double *out_dev, cudaStream_t s);
+void rb_launch_init(const RbCtx &c, cudaStream_t s);
+void rb_launch_refstats(const RbCtx &c, unsigned long long *out2_dev, cudaStream_t s);
+size_t rb_match_smem_bytes();

@@ -1,0 +1,459 @@
+// ctx.cu -- host side of the C ABI (include/rbpf_b200.h): handle, device
+// memory, the write-path LUT, launch sequencing.  No torch types, no CPU
+// fallback: every compute entry point enqueues CUDA kernels.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rbpf_b200.h"
+#include "common.cuh"
+
+struct rbpf_ctx {
+    rbpf_config cfg;
+    RbCtx d;                       // device pointers + dims, passed to kernels by value
+    cudaStream_t stream;
+    std::string err;
+    std::vector<void *> allocs;
+    double *d_ranges_unused;
+    double *d_px, *d_py, *d_dist;  // scan
+    double *d_rot;                 // rotation table
+    uint16_t *d_lut;
+    double *d_z;                   // N*K*3 host-supplied normals
+    double *d_u01;
+    double *d_tile;                // 800*800 export buffer
+    int *d_slice;                  // 29*29 debug slice
+    unsigned long long *d_refstats;
+    double *h_scan;                // pinned staging: px, py, dist
+    int have_scan;
+};
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return RBPF_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(rbpf_ctx *h, T **p, size_t n)
+{
+    void *v = nullptr;
+    cudaError_t e = cudaMalloc(&v, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+    if (e == cudaSuccess) { h->allocs.push_back(v); *p = (T *)v; }
+    return e;
+}
+
+static double rot_step_host() { return acos(1.0 - (RB_CS * RB_CS) / (2.0 * RB_MATCH_MAX_R * RB_MATCH_MAX_R)); }
+static int rot_count_host() { return (int)floor((M_PI / 6.0) / rot_step_host()); }
+
+extern "C" double rbpf_rot_step(void) { return rot_step_host(); }
+extern "C" int32_t rbpf_rot_count(void) { return rot_count_host(); }
+
+// Write-path LUT: lattice cell k -> storage coordinate, replaying
+// int((k*0.05 - c)/0.05 + 400.0) of GridMap.set_*_pos (gridmap.py:92-95) for the
+// tile that contains k*0.05 (hybridmap.py:44-45,193-208).  The float64 result is
+// one cell low for some k; negative indices wrap like ndarray[-1].
+static void build_lut(int h, std::vector<uint16_t> &lut)
+{
+    const int n = 800 * (2 * h + 1);
+    lut.resize(n);
+    for (int q = 0; q < n; q++) {
+        const int k = q - 800 * h - 400;
+        volatile double X = (double)k * RB_CS;
+        int t = (int)floor((double)(k + 400) / 800.0);
+        for (int tt = t - 1; tt <= t + 1; tt++) {                 // containment on the 40 m lattice
+            double c = 40.0 * tt;
+            if (X >= c - 20.0 && X < c + 20.0) { t = tt; break; }
+        }
+        if (t < -h) t = -h;
+        if (t > h) t = h;
+        volatile double rel = X - 40.0 * t;
+        volatile double qd = rel / RB_CS;
+        int idx = (int)(qd + 400.0);
+        if (idx < 0) idx += RB_DIM;
+        if (idx >= RB_DIM) idx = RB_DIM - 1;
+        lut[q] = (uint16_t)(800 * (t + h) + idx);
+    }
+}
+
+extern "C" const char *rbpf_last_error(rbpf_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int rbpf_destroy(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->h_scan) cudaFreeHost(h->h_scan);
+    delete h;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
+{
+    if (!cfg || !out) return RBPF_ERR_ARG;
+    *out = nullptr;
+    rbpf_ctx *h = new rbpf_ctx();
+    h->cfg = *cfg;
+    h->h_scan = nullptr;
+    h->have_scan = 0;
+    auto fail = [&](int code, const std::string &msg) {
+        static std::string last;
+        last = msg;
+        fprintf(stderr, "rbpf_create: %s\n", msg.c_str());
+        for (void *p : h->allocs) cudaFree(p);
+        if (h->h_scan) cudaFreeHost(h->h_scan);
+        delete h;
+        return code;
+    };
+    if (cfg->n_particles < 1 || cfg->n_beams < 1 || cfg->n_beams > RB_MAXB || cfg->n_samples < 1 ||
+        cfg->n_samples > RB_MAXK || cfg->world_tiles_x < 1 || cfg->world_tiles_y < 1 ||
+        (cfg->world_tiles_x & 1) == 0 || (cfg->world_tiles_y & 1) == 0 ||
+        cfg->world_tiles_x * cfg->world_tiles_y > 64 || cfg->pool_subtiles < 1 || cfg->world < 1 || cfg->rank < 0 ||
+        cfg->rank >= cfg->world)
+        return fail(RBPF_ERR_ARG, "bad configuration");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device < 0 || cfg->device >= ndev)
+        return fail(RBPF_ERR_CUDA, "no usable CUDA device (there is no CPU fallback)");
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(RBPF_ERR_CUDA, "cudaSetDevice failed");
+    h->stream = (cudaStream_t)(uintptr_t)cfg->stream;
+
+    RbCtx &d = h->d;
+    memset(&d, 0, sizeof(d));
+    d.N = cfg->n_particles; d.B = cfg->n_beams; d.K = cfg->n_samples;
+    d.rank = cfg->rank; d.world = cfg->world; d.n_global = cfg->n_particles * cfg->world;
+    d.tiles_x = cfg->world_tiles_x; d.tiles_y = cfg->world_tiles_y;
+    d.txh = (d.tiles_x - 1) / 2; d.tyh = (d.tiles_y - 1) / 2;
+    d.subs_x = d.tiles_x * RB_SUBS_PER_TILE; d.subs_y = d.tiles_y * RB_SUBS_PER_TILE;
+    d.nsub = d.subs_x * d.subs_y;
+    d.ux_max = d.tiles_x * RB_DIM; d.uy_max = d.tiles_y * RB_DIM;
+    d.lut_h = d.txh > d.tyh ? d.txh : d.tyh;
+    d.pool_tiles = cfg->pool_subtiles;
+    d.seed = cfg->seed;
+    d.step_no = 0;
+    d.nk = rot_count_host();
+    d.rot_step = rot_step_host();
+
+    const size_t N = (size_t)d.N;
+    cudaError_t e = cudaSuccess;
+#define A(ptr, n) if (e == cudaSuccess) e = dalloc(h, &(ptr), (size_t)(n))
+    A(d.pool, (size_t)d.pool_tiles * RB_SUB_BYTES);
+    A(d.refcnt, d.pool_tiles);
+    A(d.free_list, d.pool_tiles);
+    A(d.free_count, 4);
+    A(d.pose, N * 3); A(d.pose2, N * 3);
+    A(d.cov, N * 9); A(d.cov2, N * 9);
+    A(d.weight, N);
+    A(d.pt, N * d.nsub); A(d.pt2, N * d.nsub);
+    A(d.exists, N); A(d.exists2, N);
+    A(h->d_px, RB_MAXB); A(h->d_py, RB_MAXB); A(h->d_dist, RB_MAXB);
+    A(h->d_rot, 2 * (2 * d.nk + 1));
+    A(h->d_lut, 800 * (2 * d.lut_h + 1));
+    A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4);
+    A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N);
+    A(d.stats, 1); A(d.flags, 1);
+    A(h->d_z, N * d.K * 3);
+    A(h->d_u01, 2);
+    A(h->d_tile, RB_DIM * RB_DIM);
+    A(h->d_slice, RB_SLICE_W * RB_SLICE_W);
+    A(h->d_refstats, 2);
+#undef A
+    if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (cudaMallocHost((void **)&h->h_scan, 3 * RB_MAXB * sizeof(double)) != cudaSuccess)
+        return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
+    d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist;
+    d.rot_cs = h->d_rot;
+    d.lut = h->d_lut;
+
+    std::vector<double> rot(2 * (2 * d.nk + 1));
+    for (int k = -d.nk; k <= d.nk; k++) {
+        rot[2 * (k + d.nk)] = cos(k * d.rot_step);
+        rot[2 * (k + d.nk) + 1] = sin(k * d.rot_step);
+    }
+    std::vector<uint16_t> lut;
+    build_lut(d.lut_h, lut);
+    if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(RBPF_ERR_CUDA, "table upload failed");
+    rb_launch_init(d, h->stream);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
+        return fail(RBPF_ERR_CUDA, std::string("init: ") + cudaGetErrorString(e));
+    *out = h;
+    return RBPF_OK;
+}
+
+static int check_flags(rbpf_ctx *h)
+{
+    RbFlags f;
+    CK(cudaMemcpyAsync(&f, h->d.flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (f.pool_exhausted) { h->err = "tile pool exhausted (raise pool_subtiles)"; return RBPF_ERR_POOL; }
+    if (f.world_overflow) { h->err = "matcher window / ray-cast internal bound hit"; return RBPF_ERR_WORLD; }
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_synchronize(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return check_flags(h);
+}
+
+extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams)
+{
+    if (!h || !ranges || !angles || n_beams != h->d.B) { if (h) h->err = "set_scan: bad arguments"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));                        // the pinned staging buffer may still be in flight
+    double *px = h->h_scan, *py = px + RB_MAXB, *dist = py + RB_MAXB;
+    for (int j = 0; j < n_beams; j++) {                          // Scan.__init__ lidar.py:76-80 (host libm, like the reference)
+        px[j] = ranges[j] * cos(angles[j]);
+        py[j] = ranges[j] * sin(angles[j]);
+        dist[j] = sqrt(px[j] * px[j] + py[j] * py[j]);          // hybridmap.py:105,217 ; robot.py:129
+    }
+    CK(cudaMemcpyAsync(h->d_px, px, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_py, py, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_dist, dist, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->have_scan = 1;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_motion(rbpf_handle h, int32_t family, const double *u, double dt, const double *par)
+{
+    if (!h || !u || family < 0 || family > 2) { if (h) h->err = "motion: bad arguments"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    rb_launch_motion(h->d, family, u, dt, par, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_scan_match(rbpf_handle h)
+{
+    if (!h || !h->have_scan) { if (h) h->err = "scan_match: no scan set"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    rb_launch_match(h->d, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_weight(rbpf_handle h, const double *z)
+{
+    if (!h || !h->have_scan) { if (h) h->err = "weight: no scan set"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    const double *zd = nullptr;
+    if (z) {
+        CK(cudaMemcpyAsync(h->d_z, z, (size_t)h->d.N * h->d.K * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        zd = h->d_z;
+    }
+    rb_launch_weight(h->d, zd, 0, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
+{
+    if (!h || !h->have_scan) { if (h) h->err = "integrate: no scan set"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    rb_launch_raycast(h->d, h->stream);
+    if (fallback_weights) rb_launch_weight(h->d, nullptr, 1, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+static void swap_buffers(rbpf_ctx *h)
+{
+    RbCtx &d = h->d;
+    std::swap(d.pose, d.pose2);
+    std::swap(d.cov, d.cov2);
+    std::swap(d.pt, d.pt2);
+    std::swap(d.exists, d.exists2);
+}
+
+static int resample_common(rbpf_ctx *h, const double *weights_all_dev, const double *u01, int32_t *ancestors_out,
+                           int32_t *did_resample)
+{
+    const double *ud = nullptr;
+    if (u01) {
+        CK(cudaMemcpyAsync(h->d_u01, u01, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ud = h->d_u01;
+    }
+    rb_launch_resample(h->d, weights_all_dev, ud, h->stream);
+    CK(cudaGetLastError());
+    if (ancestors_out || did_resample) {
+        RbFlags f;
+        CK(cudaMemcpyAsync(&f, h->d.flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+        if (ancestors_out)
+            CK(cudaMemcpyAsync(ancestors_out, h->d.ancestors, sizeof(int) * (size_t)h->d.n_global,
+                               cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (did_resample) *did_resample = f.did_resample;
+        if (f.resample_error) {
+            h->err = "Incorrect number of resampled weights.";            // main.py:67
+            return RBPF_ERR_RESAMPLE;
+        }
+    }
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_resample(rbpf_handle h, const double *u01, int32_t *ancestors_out, int32_t *did_resample)
+{
+    if (!h) return RBPF_ERR_ARG;
+    if (h->d.world != 1) { h->err = "resample: sharded handle, use rbpf_resample_global"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = resample_common(h, h->d.weight, u01, ancestors_out, did_resample);
+    rb_launch_resample_apply(h->d, h->stream);                  // identity gather when nothing triggered / on error
+    CK(cudaGetLastError());
+    swap_buffers(h);
+    h->d.step_no++;
+    return rc;
+}
+
+extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams)
+{
+    if (!h) return RBPF_ERR_ARG;
+    if (h->d.world != 1) { h->err = "step: sharded handle, drive the stages from thesis_b200.dist"; return RBPF_ERR_ARG; }
+    int rc = rbpf_set_scan(h, ranges, angles, n_beams);
+    if (rc) return rc;
+    rb_launch_match(h->d, h->stream);
+    rb_launch_weight(h->d, nullptr, 0, h->stream);
+    rb_launch_raycast(h->d, h->stream);
+    rb_launch_weight(h->d, nullptr, 1, h->stream);
+    rb_launch_resample(h->d, h->d.weight, nullptr, h->stream);
+    rb_launch_resample_apply(h->d, h->stream);
+    CK(cudaGetLastError());
+    swap_buffers(h);
+    h->d.step_no++;
+    return RBPF_OK;
+}
+
+// ---- state access -----------------------------------------------------------
+
+static int copy_out(rbpf_ctx *h, void *dst, const void *src, size_t bytes)
+{
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBPF_OK;
+}
+
+static int copy_in(rbpf_ctx *h, void *dst, const void *src, size_t bytes)
+{
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_get_poses(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.pose, sizeof(double) * 3 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_get_covs(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.cov, sizeof(double) * 9 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_get_weights(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.weight, sizeof(double) * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_set_poses(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.pose, i, sizeof(double) * 3 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_set_covs(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.cov, i, sizeof(double) * 9 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_set_weights(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.weight, i, sizeof(double) * h->d.N) : RBPF_ERR_ARG; }
+
+extern "C" int rbpf_get_match(rbpf_handle h, double *pose, double *cov, double *score, int32_t *valid, int32_t *best)
+{
+    if (!h) return RBPF_ERR_ARG;
+    const size_t N = h->d.N;
+    int rc = RBPF_OK;
+    if (pose && !rc) rc = copy_out(h, pose, h->d.m_pose, sizeof(double) * 3 * N);
+    if (cov && !rc) rc = copy_out(h, cov, h->d.m_cov, sizeof(double) * 9 * N);
+    if (score && !rc) rc = copy_out(h, score, h->d.m_score, sizeof(double) * N);
+    if (valid && !rc) rc = copy_out(h, valid, h->d.m_valid, sizeof(int) * N);
+    if (best && !rc) rc = copy_out(h, best, h->d.m_best, sizeof(int) * 4 * N);
+    return rc;
+}
+
+extern "C" int rbpf_set_match(rbpf_handle h, const double *pose, const double *cov, const int32_t *valid)
+{
+    if (!h || !pose || !cov || !valid) return RBPF_ERR_ARG;
+    const size_t N = h->d.N;
+    int rc = copy_in(h, h->d.m_pose, pose, sizeof(double) * 3 * N);
+    if (!rc) rc = copy_in(h, h->d.m_cov, cov, sizeof(double) * 9 * N);
+    if (!rc) rc = copy_in(h, h->d.m_valid, valid, sizeof(int) * N);
+    return rc;
+}
+
+extern "C" int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *out)
+{
+    if (!h || !out || particle < 0 || particle >= h->d.N || !h->have_scan) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(h->d_slice, 0, sizeof(int) * RB_SLICE_W * RB_SLICE_W, h->stream));
+    rb_launch_match_slice(h->d, particle, h->d_slice, h->stream);
+    CK(cudaGetLastError());
+    return copy_out(h, out, h->d_slice, sizeof(int) * RB_SLICE_W * RB_SLICE_W);
+}
+
+extern "C" int rbpf_export_tile(rbpf_handle h, int32_t particle, int32_t cx, int32_t cy, double *out, int32_t *exists)
+{
+    if (!h || !out || particle < 0 || particle >= h->d.N || cx % 40 || cy % 40) return RBPF_ERR_ARG;
+    const int tx = cx / 40, ty = cy / 40;
+    memset(out, 0, sizeof(double) * RB_DIM * RB_DIM);
+    if (exists) *exists = 0;
+    if (tx < -h->d.txh || tx > h->d.txh || ty < -h->d.tyh || ty > h->d.tyh) return RBPF_OK;
+    unsigned long long mask = 0;
+    int rc = copy_out(h, &mask, h->d.exists + particle, sizeof(mask));
+    if (rc) return rc;
+    if (!((mask >> ((ty + h->d.tyh) * h->d.tiles_x + (tx + h->d.txh))) & 1ull)) return RBPF_OK;
+    if (exists) *exists = 1;
+    rb_launch_export_tile(h->d, particle, tx, ty, h->d_tile, h->stream);
+    CK(cudaGetLastError());
+    return copy_out(h, out, h->d_tile, sizeof(double) * RB_DIM * RB_DIM);
+}
+
+extern "C" int rbpf_list_tiles(rbpf_handle h, int32_t particle, int32_t *out_xy, int32_t max_tiles, int32_t *n)
+{
+    if (!h || !n || particle < 0 || particle >= h->d.N) return RBPF_ERR_ARG;
+    unsigned long long mask = 0;
+    int rc = copy_out(h, &mask, h->d.exists + particle, sizeof(mask));
+    if (rc) return rc;
+    int cnt = 0;
+    for (int ty = -h->d.tyh; ty <= h->d.tyh; ty++)
+        for (int tx = -h->d.txh; tx <= h->d.txh; tx++)
+            if ((mask >> ((ty + h->d.tyh) * h->d.tiles_x + (tx + h->d.txh))) & 1ull) {
+                if (out_xy && cnt < max_tiles) { out_xy[2 * cnt] = 40 * tx; out_xy[2 * cnt + 1] = 40 * ty; }
+                cnt++;
+            }
+    *n = cnt;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
+{
+    if (!h || !out) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    RbStats s;
+    int fc = 0;
+    unsigned long long rs[2];
+    rb_launch_refstats(h->d, h->d_refstats, h->stream);
+    CK(cudaMemcpyAsync(&s, h->d.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&fc, h->d.free_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rs, h->d_refstats, sizeof(rs), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out->pool_subtiles = h->d.pool_tiles;
+    out->pool_in_use = h->d.pool_tiles - (uint32_t)(fc < 0 ? 0 : fc);
+    out->cow_copies = s.cow_copies;
+    out->fresh_allocs = s.fresh_allocs;
+    out->cells_dropped = s.cells_dropped;
+    out->resamples = s.resamples;
+    out->match_failed = s.match_failed;
+    out->shared_refs = rs[0];
+    out->total_refs = rs[1];
+    return RBPF_OK;
+}
+
+// ---- multi-GPU resampling -------------------------------------------------------
+
+extern "C" int rbpf_weights_device_ptr(rbpf_handle h, uint64_t *dev_ptr)
+{
+    if (!h || !dev_ptr) return RBPF_ERR_ARG;
+    *dev_ptr = (uint64_t)(uintptr_t)h->d.weight;
+    return RBPF_OK;
+}

@@ -1,0 +1,420 @@
+// k_match.cu -- stage 2: per-particle correlative scan-to-map matching.
+//
+// Reference contract: HybridMap.get_scan_match hybridmap.py:210-261 (front-end:
+// which beams become "curr" points, snapped to cell corners, relative to the
+// guess) and matchScanCustom.m:1-58 (search window, isValidPose gate, NaN
+// covariance on failure).  The search arithmetic itself lives in MathWorks'
+// matchScansGrid, which is not in the reference tree: the algorithm below is the
+// restatement defined in oracle/rbpf_oracle.c orc_match() -- PARITY UNPINNED
+// against MATLAB, bit-exact against the oracle.
+//
+// One CTA per particle.
+//   1. curr points (<= B) -> shared memory.
+//   2. the particle's occupancy around the guess cell is gathered from the tile
+//      pool with 32-byte vector loads (one aligned 32-cell word per thread),
+//      thresholded (tenths > 10) into a bitmap, 3x3-dilated (proximity kernel):
+//      475 rows x 512 bits in shared memory.
+//   3. every warp takes rotations k = warp, warp + W, ...; lanes first rotate and
+//      rasterise the points of that rotation, then each lane owns one row shift
+//      j of the translation window: for every point it funnel-shifts the 29 bits
+//      [x - nx, x + nx] of bitmap row (y + j) out of two shared-memory words
+//      (row stride 17 words -> the 29 lanes hit 29 different banks) and adds
+//      them into bit-sliced counters with carry-save adders (LOP3).  One pass
+//      over the points therefore scores 29 x 29 translations.
+//   4. bit-sliced max + tie-break key per lane, warp-shuffle argmax, CTA argmax.
+//   5. covariance from the score slice at the best rotation and the score line
+//      at the best translation (integer moments, weights 2^(score - best)).
+#include "common.cuh"
+
+#define MT_WARPS 8
+#define MT_THREADS (MT_WARPS * 32)
+#define MT_PLANES 9                     // bit-sliced counters up to 511 >= RB_MAXB
+
+struct MatchShared {
+    double gx, gy, gth, cs0, sn0, fx, fy, rx, ry;
+    int M, nx, ny, g0xu, g0yu, x0, y0, t0x, t0y, ok, overflow;
+    unsigned long long warp_key[MT_WARPS];
+    unsigned long long best_key;
+    long long mom[9];                   // W0 Wx Wy Wxx Wyy Wxy T0 T1 T2
+};
+
+__host__ __device__ inline size_t mt_bm_words() { return ((size_t)RB_BM_ROWS * RB_BM_STRIDE + 3) & ~(size_t)3; }  // keeps raw/pts 16-B aligned
+__host__ __device__ inline size_t mt_raw_words() { return (size_t)RB_RAW_ROWS * RB_RAW_STRIDE; }
+
+size_t rb_match_smem_bytes()
+{
+    size_t words = mt_bm_words() + mt_raw_words();
+    words = (words + 1) & ~(size_t)1;
+    return words * 4 + 2 * RB_MAXB * sizeof(double) + sizeof(MatchShared);
+}
+
+__device__ __forceinline__ unsigned long long mt_key(int score, int i, int j, int k)
+{
+    // higher score; then smaller |k|, |i|, |j|; then negative before positive (oracle match_key)
+    unsigned long long key = (unsigned long long)(unsigned)score << 32;
+    key |= (unsigned long long)(255 - abs(k)) << 24;
+    key |= (unsigned long long)(31 - abs(i)) << 19;
+    key |= (unsigned long long)(31 - abs(j)) << 14;
+    key |= (unsigned long long)(k < 0) << 13;
+    key |= (unsigned long long)(i < 0) << 12;
+    key |= (unsigned long long)(j < 0) << 11;
+    return key;
+}
+
+__device__ __forceinline__ void mt_key_decode(unsigned long long key, int &score, int &i, int &j, int &k)
+{
+    score = (int)(key >> 32);
+    int ak = 255 - (int)((key >> 24) & 0xff), ai = 31 - (int)((key >> 19) & 0x1f), aj = 31 - (int)((key >> 14) & 0x1f);
+    k = ((key >> 13) & 1) ? -ak : ak;
+    i = ((key >> 12) & 1) ? -ai : ai;
+    j = ((key >> 11) & 1) ? -aj : aj;
+}
+
+// carry-save adder: (h, l) = a + b + c per bit
+#define CSA(h, l, a, b, c)                          \
+    {                                               \
+        uint32_t u_ = (a) ^ (b);                    \
+        h = ((a) & (b)) | (u_ & (c));               \
+        l = u_ ^ (c);                               \
+    }
+
+// 32 thresholded cells -> 32 bits (bit b = cell x0 + b)
+__device__ __forceinline__ uint32_t mt_pack4(uint32_t bytes)
+{
+    uint32_t m = __vcmpgts4(bytes, 0x0A0A0A0Au) & 0x80808080u;              // tenths > 10  (gridmap.py:153)
+    return (m * 0x00204081u) >> 28;
+}
+
+// Accumulate the hit masks of all points of one rotation into bit-sliced
+// counters.  pts[q] = (word address << 5) | bit shift for row shift 0.
+__device__ __forceinline__ void mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
+                                              int lane_off, uint32_t pl[MT_PLANES])
+{
+    uint32_t ones = 0, twos = 0, fours = 0;
+#pragma unroll
+    for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
+    int q = 0;
+    for (; q + 8 <= M; q += 8) {
+        uint32_t h[8];
+        const uint4 pa = *reinterpret_cast<const uint4 *>(pts + q);
+        const uint4 pb = *reinterpret_cast<const uint4 *>(pts + q + 4);
+        const uint32_t pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const uint32_t a = (pk[e] >> 5) + lane_off;
+            h[e] = __funnelshift_r(bm[a], bm[a + 1], pk[e]);
+        }
+        uint32_t t0, t1, f0, f1, e8;
+        CSA(t0, ones, ones, h[0], h[1]);
+        CSA(t1, ones, ones, h[2], h[3]);
+        CSA(f0, twos, twos, t0, t1);
+        CSA(t0, ones, ones, h[4], h[5]);
+        CSA(t1, ones, ones, h[6], h[7]);
+        CSA(f1, twos, twos, t0, t1);
+        CSA(e8, fours, fours, f0, f1);
+        // ripple the eights into planes 3..8
+#pragma unroll
+        for (int p = 3; p < MT_PLANES; p++) { uint32_t t = pl[p] & e8; pl[p] ^= e8; e8 = t; }
+    }
+    pl[0] = ones; pl[1] = twos; pl[2] = fours;
+    for (; q < M; q++) {                                                   // tail: plain ripple add
+        const uint32_t pk = pts[q];
+        const uint32_t a = (pk >> 5) + lane_off;
+        uint32_t carry = __funnelshift_r(bm[a], bm[a + 1], pk);
+#pragma unroll
+        for (int p = 0; p < MT_PLANES; p++) { uint32_t t = pl[p] & carry; pl[p] ^= carry; carry = t; }
+    }
+}
+
+__device__ __forceinline__ int mt_decode(const uint32_t pl[MT_PLANES], int bit)
+{
+    int s = 0;
+#pragma unroll
+    for (int p = 0; p < MT_PLANES; p++) s |= (int)((pl[p] >> bit) & 1u) << p;
+    return s;
+}
+
+// Rasterise the curr points for rotation k into packed bitmap addresses.
+__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
+                                             uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j)
+{
+    const double ck = c.rot_cs[2 * (k + c.nk)], sk = c.rot_cs[2 * (k + c.nk) + 1];
+    const int M = sh->M;
+    const int xoff = sh->g0xu - sh->x0 + shift_i, yoff = RB_WIN_R + shift_j;
+    for (int q = lane; q < M; q += 32) {
+        double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
+        double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
+        int ox = __double2int_rd(rxq * 20.0), oy = __double2int_rd(ryq * 20.0);
+        int bx = ox + xoff, by = oy + yoff;
+        if (bx < 0 || bx + span_i >= 32 * (RB_BM_STRIDE - 1) || by < 0 || by + span_j >= RB_BM_ROWS) {
+            sh->overflow = 1;                                              // cannot happen for |c| < 11 m
+            bx = 0; by = 0;
+        }
+        pts[q] = ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << 5) | (uint32_t)(bx & 31);
+    }
+}
+
+__global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *bm = smem;
+    uint32_t *raw = bm + mt_bm_words();
+    size_t w_end = (mt_bm_words() + mt_raw_words() + 1) & ~(size_t)1;
+    double *ccx = reinterpret_cast<double *>(smem + w_end);
+    double *ccy = ccx + RB_MAXB;
+    MatchShared *sh = reinterpret_cast<MatchShared *>(ccy + RB_MAXB);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = blockIdx.x + p_offset;
+    const double *pose = c.pose + 3 * (size_t)p, *cov = c.cov + 9 * (size_t)p;
+
+    // ---- 0. per-particle frame -------------------------------------------
+    if (tid == 0) {
+        sh->gx = pose[0]; sh->gy = pose[1]; sh->gth = pose[2];
+        sh->cs0 = cos(pose[2]); sh->sn0 = sin(pose[2]);
+        // search window, robot.py:62-65
+        double p0 = sqrt(cov[0]) * 30.0, p1 = sqrt(cov[4]) * 30.0;
+        sh->rx = fmax(fmin(4 * p0, 0.7), 0.1);
+        sh->ry = fmax(fmin(4 * p1, 0.7), 0.1);
+        sh->nx = min(__double2int_rd(sh->rx / RB_CS + 1e-9), RB_NT_MAX);
+        sh->ny = min(__double2int_rd(sh->ry / RB_CS + 1e-9), RB_NT_MAX);
+        int tx, ty, ix, iy;
+        rb_read_axis(pose[0], tx, ix);
+        rb_read_axis(pose[1], ty, iy);
+        sh->ok = !(tx < -c.txh || tx > c.txh || ty < -c.tyh || ty > c.tyh);
+        sh->t0x = tx; sh->t0y = ty;
+        sh->g0xu = 800 * (tx + c.txh) + ix;
+        sh->g0yu = 800 * (ty + c.tyh) + iy;
+        sh->fx = pose[0] - rb_cell_corner(ix, tx);
+        sh->fy = pose[1] - rb_cell_corner(iy, ty);
+        sh->x0 = (sh->g0xu - RB_WIN_R) & ~31;
+        sh->y0 = sh->g0yu - RB_WIN_R;
+        sh->M = 0;
+        sh->overflow = 0;
+        sh->best_key = 0ull;
+#pragma unroll
+        for (int q = 0; q < 9; q++) sh->mom[q] = 0;
+    }
+    __syncthreads();
+
+    // ---- 1. curr points, hybridmap.py:216-228,236,240 ----------------------
+    const unsigned long long exists = c.exists[p];
+    for (int j = tid; j < c.B; j += MT_THREADS) {
+        double d = c.dist[j];
+        if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) continue;
+        double gx, gy;
+        rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, c.px[j], c.py[j], gx, gy);
+        int tx, ty, ix, iy;
+        rb_read_axis(gx, tx, ix);
+        rb_read_axis(gy, ty, iy);
+        if (!rb_tile_exists(c, exists, tx, ty)) continue;
+        double qx = rb_cell_corner(ix, tx) - sh->gx, qy = rb_cell_corner(iy, ty) - sh->gy;
+        if (!(sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R)) continue;
+        int slot = atomicAdd(&sh->M, 1);
+        ccx[slot] = qx;
+        ccy[slot] = qy;
+    }
+
+    // ---- 2. occupancy bitmap around the guess cell ---------------------------
+    {
+        const int x0 = sh->x0, y0 = sh->y0;
+        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
+        for (int idx = tid; idx < RB_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) {
+            const int rr = idx / RB_RAW_STRIDE, rw = idx - rr * RB_RAW_STRIDE;
+            const int uy = y0 - 1 + rr, ux = x0 - 32 + 32 * rw;
+            uint32_t word = 0;
+            if (uy >= 0 && uy < c.uy_max && ux >= 0 && ux < c.ux_max) {
+                const uint32_t t = pt[(uy / RB_SUB) * c.subs_x + ux / RB_SUB];
+                if (t != RB_NONE) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES +
+                                                                       (uy % RB_SUB) * RB_SUB + (ux % RB_SUB));
+                    const uint4 a = src[0], b = src[1];
+                    word = mt_pack4(a.x) | (mt_pack4(a.y) << 4) | (mt_pack4(a.z) << 8) | (mt_pack4(a.w) << 12) |
+                           (mt_pack4(b.x) << 16) | (mt_pack4(b.y) << 20) | (mt_pack4(b.z) << 24) |
+                           (mt_pack4(b.w) << 28);
+                }
+            }
+            raw[idx] = word;
+        }
+    }
+    __syncthreads();
+    // 3x3 dilation: a lookup counts when the cell or one of its 8 neighbours is occupied
+    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
+        const int r = idx / RB_BM_STRIDE, w = idx - r * RB_BM_STRIDE;
+        uint32_t v = 0;
+        if (w < RB_BM_STRIDE - 1) {
+#pragma unroll
+            for (int dr = 0; dr < 3; dr++) {
+                const uint32_t *row = raw + (r + dr) * RB_RAW_STRIDE + w;
+                const uint32_t lw = row[0], cw = row[1], rw = row[2];
+                v |= cw | (cw << 1) | (cw >> 1) | (lw >> 31) | (rw << 31);
+            }
+        }
+        bm[idx] = v;
+    }
+    __syncthreads();
+
+    const int M = sh->M, nx = sh->nx, ny = sh->ny;
+    const int nrows = 2 * ny + 1, ncols = 2 * nx + 1;
+    const uint32_t colmask = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
+    uint32_t *pts = raw + warp * RB_MAXB;                                   // raw is dead now: per-warp point lists
+    const int lane_off = (lane < nrows ? lane : 0) * RB_BM_STRIDE;
+    unsigned long long best = 0ull;
+
+    // ---- 3. score all rotations ---------------------------------------------
+    if (sh->ok) {
+        for (int k = -c.nk + warp; k <= c.nk; k += MT_WARPS) {
+            __syncwarp();
+            mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+            __syncwarp();
+            uint32_t pl[MT_PLANES];
+            mt_accumulate(bm, pts, M, lane_off, pl);
+            if (lane < nrows) {
+                // bit-sliced max over the ncols translation bits
+                uint32_t cand = colmask;
+                int sc = 0;
+#pragma unroll
+                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+                    uint32_t t = cand & pl[pbit];
+                    if (t) { cand = t; sc |= 1 << pbit; }
+                }
+                // closest to the window centre, negative side first
+                uint32_t lowm = cand & ((2u << nx) - 1u);                    // bits 0..nx   (i <= 0)
+                uint32_t highm = cand >> nx;                                 // bit d = i = +d
+                int dn = lowm ? nx - (31 - __clz(lowm)) : 99;
+                int dp = highm ? __ffs(highm) - 1 : 99;
+                int i = dn <= dp ? -dn : dp;
+                unsigned long long key = mt_key(sc, i, lane - ny, k);
+                if (key > best) best = key;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other > best) best = other;
+    }
+    if (lane == 0) sh->warp_key[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = 0ull;
+        for (int q = 0; q < MT_WARPS; q++) if (sh->warp_key[q] > b) b = sh->warp_key[q];
+        sh->best_key = b;
+    }
+    __syncthreads();
+    int bs, bi, bj, bk;
+    mt_key_decode(sh->best_key, bs, bi, bj, bk);
+    if (!sh->ok) { bs = 0; bi = bj = bk = 0; }
+
+    const double step = c.rot_step;
+    const bool valid = sh->ok && fabs((double)bi * RB_CS) < sh->rx && fabs((double)bj * RB_CS) < sh->ry &&
+                       fabs((double)bk * step) < 3.14159265358979323846 / 6.0 && (bi != 0 || bj != 0 || bk != 0);
+
+    // ---- 5. covariance --------------------------------------------------------
+    if (valid || slice_out) {
+        if (warp == 0) {                                                    // translation slice at the best rotation
+            mt_rasterise(c, sh, ccx, ccy, bk, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+            __syncwarp();
+            uint32_t pl[MT_PLANES];
+            mt_accumulate(bm, pts, M, lane_off, pl);
+            long long W0 = 0, Wx = 0, Wy = 0, Wxx = 0, Wyy = 0, Wxy = 0;
+            if (lane < nrows) {
+                const int j = lane - ny;
+                for (int b = 0; b < ncols; b++) {
+                    const int s = mt_decode(pl, b), i = b - nx, d = bs - s;
+                    if (slice_out) slice_out[(j + RB_NT_MAX) * RB_SLICE_W + (i + RB_NT_MAX)] = s;
+                    if (d > 40) continue;
+                    const long long w = 1ll << (40 - d);
+                    W0 += w; Wx += w * i; Wy += w * j; Wxx += w * i * i; Wyy += w * j * j; Wxy += w * i * j;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                W0 += __shfl_xor_sync(0xffffffffu, W0, o);
+                Wx += __shfl_xor_sync(0xffffffffu, Wx, o);
+                Wy += __shfl_xor_sync(0xffffffffu, Wy, o);
+                Wxx += __shfl_xor_sync(0xffffffffu, Wxx, o);
+                Wyy += __shfl_xor_sync(0xffffffffu, Wyy, o);
+                Wxy += __shfl_xor_sync(0xffffffffu, Wxy, o);
+            }
+            if (lane == 0) {
+                sh->mom[0] = W0; sh->mom[1] = Wx; sh->mom[2] = Wy; sh->mom[3] = Wxx; sh->mom[4] = Wyy; sh->mom[5] = Wxy;
+            }
+        } else {                                                            // rotation line at the best translation
+            long long T0 = 0, T1 = 0, T2 = 0;
+            for (int k = -c.nk + (warp - 1); k <= c.nk; k += MT_WARPS - 1) {
+                __syncwarp();
+                mt_rasterise(c, sh, ccx, ccy, k, pts, lane, bi, bj, 0, 0);
+                __syncwarp();
+                int s = 0;
+                for (int q = lane; q < M; q += 32) {
+                    const uint32_t pk = pts[q];
+                    s += (int)((bm[pk >> 5] >> (pk & 31)) & 1u);
+                }
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const int d = bs - s;
+                if (d <= 40) {
+                    const long long w = 1ll << (40 - d);
+                    T0 += w; T1 += w * k; T2 += w * k * k;
+                }
+            }
+            if (lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[6]), (unsigned long long)T0);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[7]), (unsigned long long)T1);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[8]), (unsigned long long)T2);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 6. result --------------------------------------------------------------
+    if (tid == 0) {
+        double *op = c.m_pose + 3 * (size_t)p, *oc = c.m_cov + 9 * (size_t)p;
+        op[0] = sh->gx + (double)bi * RB_CS;                                // hybridmap.py:253-255
+        op[1] = sh->gy + (double)bj * RB_CS;
+        op[2] = sh->gth + (double)bk * step;
+        int *ob = c.m_best + 4 * (size_t)p;
+        ob[0] = bi; ob[1] = bj; ob[2] = bk; ob[3] = M;
+        c.m_valid[p] = valid ? 1 : 0;
+        if (sh->overflow) atomicExch(&c.flags->world_overflow, 1);
+        if (!valid) {                                                       // matchScanCustom.m:26-28
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            for (int q = 0; q < 9; q++) oc[q] = nan;
+            c.m_score[p] = 0.0;
+            if (!slice_out) atomicAdd(&c.stats->match_failed, 1ull);
+        } else {
+            const double W0 = (double)sh->mom[0], T0 = (double)sh->mom[6];
+            const double mx = (double)sh->mom[1] / W0, my = (double)sh->mom[2] / W0, mt = (double)sh->mom[7] / T0;
+            const double q = RB_CS * RB_CS, qt = step * step;
+            for (int e = 0; e < 9; e++) oc[e] = 0.0;
+            oc[0] = ((double)sh->mom[3] / W0 - mx * mx) * q + q / 12.0;
+            oc[4] = ((double)sh->mom[4] / W0 - my * my) * q + q / 12.0;
+            oc[1] = oc[3] = ((double)sh->mom[5] / W0 - mx * my) * q;
+            oc[8] = ((double)sh->mom[8] / T0 - mt * mt) * qt + qt / 12.0;
+            c.m_score[p] = (double)bs;
+        }
+    }
+}
+
+static bool g_match_attr_set = false;
+
+static void match_set_attr()
+{
+    if (!g_match_attr_set) {
+        cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb_match_smem_bytes());
+        g_match_attr_set = true;
+    }
+}
+
+void rb_launch_match(const RbCtx &c, cudaStream_t s)
+{
+    match_set_attr();
+    match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr);
+}
+
+// Debug/test entry: re-run the matcher for one particle and dump the score slice
+// at its best rotation (29x29 int32).  Overwrites that particle's match outputs
+// with identical values.
+void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s)
+{
+    match_set_attr();
+    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev);
+}

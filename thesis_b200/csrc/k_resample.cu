@@ -1,0 +1,197 @@
+// k_resample.cu -- stage 5: systematic resampling and the copy-on-write
+// duplication that replaces the reference's deep copies.
+//
+// Reference: main.resample main.py:46-79 (weights pinned to float64, SURVEY
+// 3.4-7), Robot.copy robot.py:141-149, HybridMap.copy hybridmap.py:315-320.
+//
+// resample_plan   one CTA over the (all-gathered) weights of ALL ranks:
+//                   min/max and trigger (main.py:50), -inf -> 0 (:53), additive
+//                   shift of the non-zero entries (:54-55), the running sum in
+//                   the reference's left-to-right order (:57,:61-62 -- a single
+//                   thread, because float64 addition is not associative and the
+//                   ancestors must be bit-exact), then ancestors in parallel.
+//                 Every rank runs it on identical input and gets identical output.
+// resample_gather builds the new particle slots of this rank from the ancestor
+//                 vector: pose, covariance, weight <- 1.0 (main.py:77-78),
+//                 page table and tile-existence mask.  Slots whose ancestor
+//                 lives on another rank are left for the migration step.
+// resample_refs   fixes sub-tile reference counts: an old particle with m local
+//                 descendants contributes m - 1 (or releases its tiles if m = 0).
+#include "common.cuh"
+
+#define RS_THREADS 1024
+#define RS_CHUNK 4096
+
+__global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, const double *__restrict__ w_in,
+                                                                   const double *__restrict__ u01_in)
+{
+    __shared__ double red_mx[32], red_mn[32];
+    __shared__ double chunk[RS_CHUNK];
+    __shared__ double s_mn2, s_carry, s_slice, s_start;
+    __shared__ int s_do;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NG = c.n_global;
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    double *w = c.w_all;                                                     // scratch: adjusted weights, then cumsum
+
+    // max / min of the raw weights (main.py:50)
+    double mx = -INF, mn = INF;
+    for (int i = tid; i < NG; i += RS_THREADS) { double v = w_in[i]; mx = fmax(mx, v); mn = fmin(mn, v); }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) { red_mx[warp] = mx; red_mn[warp] = mn; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < RS_THREADS / 32; k++) { mx = fmax(mx, red_mx[k]); mn = fmin(mn, red_mn[k]); }
+        s_do = (mx - mn > RB_RESAMPLE_TRIGGER) ? 1 : 0;
+        c.flags->did_resample = s_do;
+        c.flags->resample_error = 0;
+        c.flags->remote_needed = 0;
+        if (s_do) c.stats->resamples += 1ull;
+    }
+    __syncthreads();
+    if (!s_do) {                                                             // particles unchanged
+        for (int i = tid; i < NG; i += RS_THREADS) c.ancestors[i] = i;
+        return;
+    }
+    // -inf -> 0, then min of the result (main.py:53-54)
+    mn = INF;
+    for (int i = tid; i < NG; i += RS_THREADS) {
+        double v = w_in[i];
+        if (v == -INF) v = 0.0;
+        w[i] = v;
+        mn = fmin(mn, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    __syncthreads();
+    if (lane == 0) red_mn[warp] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < RS_THREADS / 32; k++) mn = fmin(mn, red_mn[k]);
+        s_mn2 = mn;
+        s_carry = 0.0;
+    }
+    __syncthreads();
+    const double shift = s_mn2 < 0.0 ? fabs(s_mn2) : 0.0;
+    const bool do_shift = s_mn2 < 0.0;
+    // running sum, chunk by chunk: all threads stage a chunk in shared memory,
+    // thread 0 runs the sequential float64 chain, all threads write it back.
+    for (int base = 0; base < NG; base += RS_CHUNK) {
+        const int n = min(RS_CHUNK, NG - base);
+        for (int i = tid; i < n; i += RS_THREADS) {
+            double v = w[base + i];
+            if (do_shift && v != 0.0) v += shift;                            // main.py:55
+            chunk[i] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double cur = s_carry;
+#pragma unroll 8
+            for (int i = 0; i < n; i++) { cur += chunk[i]; chunk[i] = cur; } // main.py:57 == :62
+            s_carry = cur;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += RS_THREADS) w[base + i] = chunk[i];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double slice = s_carry / (double)NG;                                 // main.py:57
+        double u;
+        if (u01_in) u = *u01_in;
+        else {
+            uint32_t r[4];
+            rb_philox(0x5eedu, 0u, (uint32_t)c.step_no, 0x52u, c.seed, r);
+            u = rb_u01(r[0], r[1]);
+        }
+        s_slice = slice;
+        s_start = u * slice;                                                 // main.py:59
+    }
+    __syncthreads();
+    const double slice = s_slice, start = s_start;
+    // emitted-after-i = max(0, floor((c_i - start)/slice) + 1)  (main.py:63-64;
+    // the running sum is non-decreasing because all adjusted weights are >= 0)
+    bool bad = false;
+    for (int i = tid; i < NG; i += RS_THREADS) {
+        double f = floor((w[i] - start) / slice);
+        double fp = i ? floor((w[i - 1] - start) / slice) : -1.0;
+        if (!(f > -4e18 && f < 4e18)) { bad = true; continue; }             // math.floor would raise
+        long long e1 = (long long)f + 1, e0 = i ? (long long)fp + 1 : 0;
+        if (e0 < 0) e0 = 0;
+        if (e1 < 0) e1 = 0;
+        if (i == NG - 1 && e1 != NG) bad = true;                             // main.py:66-67
+        if (e1 > NG) { e1 = NG; }
+        for (long long s = e0; s < e1; s++) c.ancestors[s] = i;
+    }
+    if (bad) c.flags->resample_error = 1;
+}
+
+// Local slot j of this rank is global slot rank*N + j.
+__global__ void __launch_bounds__(256) resample_gather_kernel(RbCtx c)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= c.N) return;
+    const int j = warp;
+    const int err = c.flags->resample_error;                                  // on error: particles unchanged
+    const int a = err ? j : c.ancestors[c.rank * c.N + j] - c.rank * c.N;
+    if (a < 0 || a >= c.N) {                                                  // remote ancestor: migration fills it
+        if (lane == 0) atomicAdd(&c.flags->remote_needed, 1);
+        return;
+    }
+    const int did = c.flags->did_resample && !err;
+    if (lane < 3) c.pose2[3 * (size_t)j + lane] = c.pose[3 * (size_t)a + lane];
+    if (lane < 9) c.cov2[9 * (size_t)j + lane] = c.cov[9 * (size_t)a + lane];
+    if (lane == 0) {
+        c.exists2[j] = c.exists[a];
+        if (did) c.weight[j] = 1.0;                                           // main.py:77-78 (a == j when !did)
+    }
+    const uint32_t *src = c.pt + (size_t)a * c.nsub;
+    uint32_t *dst = c.pt2 + (size_t)j * c.nsub;
+    for (int e = lane; e < c.nsub; e += 32) dst[e] = src[e];
+}
+
+// Number of local descendants of every old local particle.
+__global__ void __launch_bounds__(256) resample_mult_kernel(RbCtx c)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.N) return;
+    const int a = c.flags->resample_error ? j : c.ancestors[c.rank * c.N + j] - c.rank * c.N;
+    if (a >= 0 && a < c.N) atomicAdd(&c.mult[a], 1);
+}
+
+__global__ void __launch_bounds__(256) resample_refs_kernel(RbCtx c)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= c.N) return;
+    const int m = c.mult[warp];
+    if (m == 1) return;
+    const uint32_t *src = c.pt + (size_t)warp * c.nsub;
+    for (int e = lane; e < c.nsub; e += 32) {
+        uint32_t t = src[e];
+        if (t == RB_NONE) continue;
+        if (m == 0) {
+            if (atomicSub(&c.refcnt[t], 1u) == 1u) {                          // last reference: back to the free list
+                int idx = atomicAdd(c.free_count, 1);
+                c.free_list[idx] = t;
+            }
+        } else {
+            atomicAdd(&c.refcnt[t], (unsigned)(m - 1));
+        }
+    }
+}
+
+void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s)
+{
+    resample_plan_kernel<<<1, RS_THREADS, 0, s>>>(c, weights_all, u01_dev);
+}
+
+// Applies the planned ancestors to this rank's particles (local part).
+void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s)
+{
+    cudaMemsetAsync(c.mult, 0, sizeof(int) * (size_t)c.N, s);
+    resample_mult_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
+    int blocks = (c.N * 32 + 255) / 256;
+    resample_gather_kernel<<<blocks, 256, 0, s>>>(c);
+    resample_refs_kernel<<<blocks, 256, 0, s>>>(c);
+}
