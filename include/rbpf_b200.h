@@ -124,6 +124,13 @@ int rbpf_resample(rbpf_handle h, const double *u01, int32_t *ancestors_out, int3
  * integrate + resample with device-side draws and no host synchronisation. */
 int rbpf_step(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams);
 
+/* Per-stage device timing of rbpf_step with CUDA events on the handle's stream
+ * (bench.py's roofline figures).  Enable for up to max_steps steps; read sums
+ * ms[8] = set_scan, match, weight, raycast_prepare, raycast_cast,
+ * weight_fallback, resample_plan, resample_apply and the number of steps. */
+int rbpf_timing_enable(rbpf_handle h, int32_t max_steps);
+int rbpf_timing_read(rbpf_handle h, double *ms_out8, int32_t *steps_out);
+
 /* State access (host pointers; each call synchronises the stream). */
 int rbpf_get_poses(rbpf_handle h, double *out_n3);        /* Robot.get_latest_pose robot.py:42-43 */
 int rbpf_get_covs(rbpf_handle h, double *out_n9);         /* Robot._cov */

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rbpf_integrate": (C.c_int, [_H, C.c_int32]),
     "rbpf_resample": (C.c_int, [_H, _dp, _ip, _ip]),
     "rbpf_step": (C.c_int, [_H, _dp, _dp, C.c_int32]),
+    "rbpf_timing_enable": (C.c_int, [_H, C.c_int32]),
+    "rbpf_timing_read": (C.c_int, [_H, _dp, _ip]),
     "rbpf_get_poses": (C.c_int, [_H, _dp]),
     "rbpf_get_covs": (C.c_int, [_H, _dp]),
     "rbpf_get_weights": (C.c_int, [_H, _dp]),

@@ -192,7 +192,8 @@ void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, co
 void rb_launch_match(const RbCtx &c, cudaStream_t s);
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s);
 void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s);
-void rb_launch_raycast(const RbCtx &c, cudaStream_t s);
+void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);
+void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s);
 void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s);
 void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s);
 void rb_launch_export_tile(const RbCtx &c, int particle, int tx, int ty, double *out_dev, cudaStream_t s);

@@ -29,7 +29,12 @@ struct rbpf_ctx {
     unsigned long long *d_refstats;
     double *h_scan;                // pinned staging: px, py, dist
     int have_scan;
+    // optional per-stage CUDA-event timing of rbpf_step
+    std::vector<cudaEvent_t> tev;  // (RB_NSTAGES + 1) events per recorded step
+    int t_max_steps, t_steps;
 };
+
+#define RB_NSTAGES 8               // set_scan, match, weight, raycast_prepare, raycast_cast, weight_fallback, resample_plan, resample_apply
 
 #define CK(call)                                                                             \
     do {                                                                                     \
@@ -90,6 +95,7 @@ extern "C" int rbpf_destroy(rbpf_handle h)
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     if (h->h_scan) cudaFreeHost(h->h_scan);
     delete h;
     return RBPF_OK;
@@ -103,6 +109,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     h->cfg = *cfg;
     h->h_scan = nullptr;
     h->have_scan = 0;
+    h->t_max_steps = 0;
+    h->t_steps = 0;
     auto fail = [&](int code, const std::string &msg) {
         static std::string last;
         last = msg;
@@ -261,7 +269,8 @@ extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
 {
     if (!h || !h->have_scan) { if (h) h->err = "integrate: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
-    rb_launch_raycast(h->d, h->stream);
+    rb_launch_raycast_prepare(h->d, h->stream);
+    rb_launch_raycast_cast(h->d, h->stream);
     if (fallback_weights) rb_launch_weight(h->d, nullptr, 1, h->stream);
     CK(cudaGetLastError());
     return RBPF_OK;
@@ -319,17 +328,62 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
 {
     if (!h) return RBPF_ERR_ARG;
     if (h->d.world != 1) { h->err = "step: sharded handle, drive the stages from thesis_b200.dist"; return RBPF_ERR_ARG; }
+    const bool timed = h->t_max_steps > 0 && h->t_steps < h->t_max_steps;
+    cudaEvent_t *ev = timed ? &h->tev[(size_t)h->t_steps * (RB_NSTAGES + 1)] : nullptr;
+#define MARK(i) if (timed) cudaEventRecord(ev[i], h->stream)
+    MARK(0);
     int rc = rbpf_set_scan(h, ranges, angles, n_beams);
     if (rc) return rc;
+    MARK(1);
     rb_launch_match(h->d, h->stream);
+    MARK(2);
     rb_launch_weight(h->d, nullptr, 0, h->stream);
-    rb_launch_raycast(h->d, h->stream);
+    MARK(3);
+    rb_launch_raycast_prepare(h->d, h->stream);
+    MARK(4);
+    rb_launch_raycast_cast(h->d, h->stream);
+    MARK(5);
     rb_launch_weight(h->d, nullptr, 1, h->stream);
+    MARK(6);
     rb_launch_resample(h->d, h->d.weight, nullptr, h->stream);
+    MARK(7);
     rb_launch_resample_apply(h->d, h->stream);
+    MARK(8);
+#undef MARK
     CK(cudaGetLastError());
+    if (timed) h->t_steps++;
     swap_buffers(h);
     h->d.step_no++;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_timing_enable(rbpf_handle h, int32_t max_steps)
+{
+    if (!h || max_steps < 0) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    h->tev.clear();
+    h->tev.resize((size_t)max_steps * (RB_NSTAGES + 1));
+    for (auto &e : h->tev) CK(cudaEventCreate(&e));
+    h->t_max_steps = max_steps;
+    h->t_steps = 0;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_timing_read(rbpf_handle h, double *ms_out, int32_t *steps_out)
+{
+    if (!h || !ms_out || !steps_out) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < RB_NSTAGES; s++) ms_out[s] = 0.0;
+    for (int i = 0; i < h->t_steps; i++)
+        for (int s = 0; s < RB_NSTAGES; s++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->tev[(size_t)i * (RB_NSTAGES + 1) + s], h->tev[(size_t)i * (RB_NSTAGES + 1) + s + 1]));
+            ms_out[s] += ms;
+        }
+    *steps_out = h->t_steps;
+    h->t_steps = 0;
     return RBPF_OK;
 }
 

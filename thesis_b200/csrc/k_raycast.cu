@@ -288,9 +288,12 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     }
 }
 
-void rb_launch_raycast(const RbCtx &c, cudaStream_t s)
+void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s)
 {
-    int blocks = (c.N + RC_WARPS - 1) / RC_WARPS;
-    raycast_prepare_kernel<<<blocks, RC_WARPS * 32, 0, s>>>(c);
-    raycast_cast_kernel<<<blocks, RC_WARPS * 32, 0, s>>>(c);
+    raycast_prepare_kernel<<<(c.N + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, s>>>(c);
+}
+
+void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
+{
+    raycast_cast_kernel<<<(c.N + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, s>>>(c);
 }

@@ -118,6 +118,19 @@ class ParticleSet:
         a, ap = _d(angles)
         self._ck(self._lib.rbpf_step(self._h, rp, ap, len(r)))
 
+    STAGES = ("set_scan", "match", "weight", "raycast_prepare", "raycast_cast", "weight_fallback",
+              "resample_plan", "resample_apply")
+
+    def timing_enable(self, max_steps):
+        self._ck(self._lib.rbpf_timing_enable(self._h, int(max_steps)))
+
+    def timing_read(self):
+        """({stage: total ms}, steps) accumulated by step() since the last read."""
+        ms = np.zeros(8)
+        n = C.c_int32(0)
+        self._ck(self._lib.rbpf_timing_read(self._h, ms.ctypes.data_as(_dp), C.byref(n)))
+        return dict(zip(self.STAGES, ms.tolist())), n.value
+
     # -- state
     def _get(self, fn, shape):
         out = np.empty(shape, dtype=np.float64)
