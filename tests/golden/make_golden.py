@@ -285,6 +285,40 @@ for name, cls, data, dtt in mot:
 G["mot_pose0"] = pose0
 G["mot_cov0"] = cov0
 
+# -- end to end: the reference's own Robot / resample / HybridMap classes driven by the
+#    headless main.py loop (thesis_b200.harness) over the Intel excerpt, with the restated
+#    matcher plugged into the MATLAB seam (tests/ref_adapter.py), np.random.seed(0)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ref_adapter as RA  # noqa: E402
+from thesis_b200 import harness, sensors  # noqa: E402
+from excerpt import ExcerptIMU, ExcerptLidar  # noqa: E402
+
+E2E_N, E2E_FRAMES = 4, 12
+np.random.seed(0)
+ld = sensors.Lidar(ExcerptLidar())
+im = sensors.IMU(ExcerptIMU())
+rp = [RA.RefParticle(r) for r in RA.make_ref_particles(E2E_N)]
+anc_log = []
+pose_log = []
+
+
+def on_frame(frame, parts):
+    pose_log.append([[float(v) for v in (p.get_latest_pose().x(), p.get_latest_pose().y(), p.get_latest_pose().theta())]
+                     for p in parts])
+
+
+parts, log = harness.run_log(rp, ld, im, lambda p: RA.ref_resample(p, anc_log), seed_fn=RA.ref_seed,
+                             max_frames=E2E_FRAMES, on_frame=on_frame)
+G["e2e_n"] = np.int32(E2E_N)
+G["e2e_frames"] = np.int32(E2E_FRAMES)
+G["e2e_poses"] = np.array(pose_log, dtype=np.float64)            # [frame, particle, 3]
+G["e2e_ancestors"] = np.array(anc_log, dtype=np.int32)           # [update, particle]
+G["e2e_weights"] = np.array([float(p.weight()[-1]) for p in parts], dtype=np.float64)
+G["e2e_updated"] = np.array([l["updated"] for l in log])
+for i, p in enumerate(parts[:2]):
+    sparse_tiles(p.r._map, "e2e_p%d" % i)
+
 out = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
 np.savez_compressed(out, **G)
 print("wrote", out, os.path.getsize(out), "bytes,", len(G), "arrays")

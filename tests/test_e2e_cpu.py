@@ -1,0 +1,177 @@
+"""CPU: the oracle driven by the headless main.py loop reproduces what the
+reference's own Python classes produced on the Intel excerpt (golden e2e_*),
+and the host layer (loaders, sensors, harness) mirrors the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import ref_shim
+from excerpt import ExcerptIMU, ExcerptLidar
+from thesis_b200 import harness, loaders, sensors
+from thesis_b200.models import Pose
+
+import ref_adapter as RA
+
+DIM = 800
+
+
+def run_oracle_e2e(G):
+    n, frames = int(G["e2e_n"]), int(G["e2e_frames"])
+    np.random.seed(0)
+    ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
+    op = RA.OracleParticles(n, 180)
+    poses = []
+    parts, log = harness.run_log(op.views, ld, im, op.resample, seed_fn=op.seed, max_frames=frames,
+                                 on_frame=lambda f, ps: poses.append([list(p.get_latest_pose().as_tuple()) for p in ps]))
+    return op, np.array(poses), log
+
+
+def test_oracle_end_to_end_matches_reference_run(golden):
+    op, poses, log = run_oracle_e2e(golden)
+    assert np.array_equal([l["updated"] for l in log], golden["e2e_updated"])
+    assert np.array_equal(np.array(op.ancestors), golden["e2e_ancestors"])        # bit-exact ancestors
+    assert np.allclose(poses, golden["e2e_poses"], rtol=0, atol=1e-12)            # float64 vs np.longdouble accumulators
+    assert np.allclose(op.f.weight, golden["e2e_weights"], rtol=1e-12)
+    for i in range(2):
+        got = op.f.map(i).tiles()
+        cen = [tuple(int(v) for v in c) for c in golden["e2e_p%d_centres" % i]]
+        assert sorted(got.keys()) == sorted(cen)
+        for n, c in enumerate(cen):
+            a = np.zeros(DIM * DIM)
+            a[golden["e2e_p%d_t%d_idx" % (i, n)]] = golden["e2e_p%d_t%d_val" % (i, n)]
+            assert np.array_equal(got[c], a.reshape(DIM, DIM))
+
+
+class _Mock:
+    def __init__(self, log):
+        self.log, self.pose = log, [0.0, 0.0, 0.0]
+
+    def imu_update(self, reading):
+        self.pose = list(reading.get_data())
+        self.log.append(("imu", reading.dt()))
+
+    def map_update(self, scan, last_scan, adj):
+        self.log.append(("map", adj))
+
+    def get_latest_pose(self):
+        return Pose(*self.pose)
+
+
+def test_harness_gating_and_alternation():
+    """main.py:152-166: first two frames always update, then only after >= 0.33 m or
+    >= pi/9; adj alternates with frame % 5 (main.py:156-159)."""
+    class L:
+        _times = np.arange(10) * 1000
+        _scans = np.zeros((10, 4))
+        _angles = np.zeros(4)
+
+        def __getitem__(self, i):
+            return sensors.Scan(np.ones(4), np.zeros(4), self._times[i])
+
+        def timestamp_for_idx(self, i):
+            return self._times[i]
+
+        def __len__(self):
+            return 10
+
+    class I:
+        _times = np.arange(10) * 1000
+        _data = np.array([[0.1 * k if k < 5 else 0.4 + 0.5 * (k - 4), 0, 0] for k in range(10)], dtype=float)
+
+        def __getitem__(self, i):
+            from thesis_b200.models import Reading
+
+            return Reading(self._data[i], self._times[i], None, None, None, motion=(0, (0, 0, 0, 0)))
+
+        def __len__(self):
+            return 10
+
+    log = []
+    parts = [_Mock(log)]
+    harness.run_log(parts, L(), I(), lambda p: p)
+    maps = [e for e in log if e[0] == "map"]
+    # frames 0,1 (update_count < 2); x = 0.0, 0.1 -> then frame 4 (x = 0.4 >= 0.33 from 0.0) and every 0.5 m step after
+    assert [m[1] for m in maps][:2] == [False, False]
+    assert len(maps) == 2 + 1 + 5
+    assert maps[2][1] is True                                     # frame 4: 4 % 5 >= 2
+    assert maps[3][1] is False                                    # frame 5: 5 % 5 < 2
+
+
+def test_loaders_parse_carmen_fixture():
+    ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
+    assert len(ld) == 45 and len(ld[0]) == 180
+    assert im[0].motion == (loaders.MOTION_ABSOLUTE, (0.0, 0.0, 0.0, 0.0))
+    assert abs(ld._angles[0] + np.pi / 2) < 1e-15 and abs(ld._angles[-1] - np.pi / 2) < 1e-12
+    with pytest.raises(Exception):
+        ld["0"]
+
+
+needs_ref = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+
+
+@needs_ref
+def test_loaders_equal_reference_loaders():
+    ref_shim.install()
+    data = os.path.join(ref_shim.REF_ROOT, "data")
+    with ref_shim.ref_cwd():
+        import IntelLidarData as RL
+        import IntelIMUData as RI
+        import DefaultLidarData as DL
+        import DefaultIMUData as DI
+
+        pairs = [(RL.IntelLidarData(), loaders.IntelLidarData(data)), (DL.DefaultLidarData(), loaders.DefaultLidarData(data))]
+        ipairs = [(RI.IntelIMUData(), loaders.IntelIMUData(data)), (DI.DefaultIMUData(), loaders.DefaultIMUData(data))]
+    for r, m in pairs:
+        assert np.array_equal(r.get_times(), m.get_times())
+        assert np.array_equal(r.get_scans(), m.get_scans())
+        assert np.array_equal(r.get_angles(), m.get_angles())
+    for r, m in ipairs:
+        assert np.array_equal(r.get_times(), m.get_times())
+        assert np.array_equal(r.get_data(), m.get_data())
+
+
+@needs_ref
+def test_motion_callbacks_equal_reference():
+    ref_shim.install()
+    import models as refmodels
+    from AcesIMUData import AcesIMUData
+    from DefaultIMUData import DefaultIMUData
+    from IntelIMUData import IntelIMUData
+    from IntelRawIMUData import IntelRawIMUData
+    from thesis_b200.models import Reading
+
+    cases = [(IntelIMUData, loaders.IntelIMUData, [1.6, -2.2, 0.7]), (IntelRawIMUData, loaders.IntelRawIMUData, [0.3, -0.1, 0.2]),
+             (AcesIMUData, loaders.AcesIMUData, [-0.4, 0.2, -0.3]), (DefaultIMUData, loaders.DefaultIMUData, [0.8, -0.2])]
+    import contextlib, io
+
+    for rc, mc, data in cases:
+        d = np.array(data)
+        rr = refmodels.Reading(d, 0, rc.progress_pose, rc.get_cov_change_matrix, rc.get_cov_input_uncertainty)
+        mr = Reading(d, 0, mc.progress_pose, mc.get_cov_change_matrix, mc.get_cov_input_uncertainty)
+        rr.set_dt(870)
+        mr.set_dt(870)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = rr.get_moved_pose(refmodels.Pose(1.5, -2.25, 0.7))
+        b = mr.get_moved_pose(Pose(1.5, -2.25, 0.7))
+        assert (a.x(), a.y(), a.theta()) == (b.x(), b.y(), b.theta())
+        assert np.array_equal(np.array(rr.get_cov_change_matrix(refmodels.Pose(1.5, -2.25, 0.7)), dtype=float),
+                              mr.get_cov_change_matrix(Pose(1.5, -2.25, 0.7)))
+        assert np.allclose(np.array(rr.get_cov_input_uncertainty(refmodels.Pose(1.5, -2.25, 0.7)), dtype=float),
+                           mr.get_cov_input_uncertainty(Pose(1.5, -2.25, 0.7)), rtol=1e-15, atol=0)
+
+
+@needs_ref
+def test_scan_equals_reference_scan():
+    ref_shim.install()
+    import lidar as reflidar
+    import models as refmodels
+
+    r = np.random.default_rng(0).uniform(0.1, 30, 180)
+    a = np.linspace(-np.pi / 2, np.pi / 2, 180)
+    rs, ms = reflidar.Scan(r, a, 5), sensors.Scan(r, a, 5)
+    assert np.array_equal(rs.x(), ms.x()) and np.array_equal(rs.y(), ms.y())
+    g1 = rs.from_global_reference(refmodels.Pose(1.0, -2.0, 0.3))
+    g2 = ms.from_global_reference(Pose(1.0, -2.0, 0.3))
+    assert np.array_equal(g1.x(), g2.x()) and np.array_equal(g1.y(), g2.y())

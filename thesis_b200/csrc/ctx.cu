@@ -217,7 +217,8 @@ extern "C" int rbpf_synchronize(rbpf_handle h)
 
 extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *angles, int32_t n_beams)
 {
-    if (!h || !ranges || !angles || n_beams != h->d.B) { if (h) h->err = "set_scan: bad arguments"; return RBPF_ERR_ARG; }
+    if (!h || !ranges || !angles || n_beams < 1 || n_beams > RB_MAXB) { if (h) h->err = "set_scan: bad arguments"; return RBPF_ERR_ARG; }
+    h->d.B = n_beams;                                            // loaders differ in beam count; buffers hold RB_MAXB
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));                        // the pinned staging buffer may still be in flight
     double *px = h->h_scan, *py = px + RB_MAXB, *dist = py + RB_MAXB;

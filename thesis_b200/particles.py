@@ -210,3 +210,244 @@ class ParticleSet:
         p = C.c_uint64(0)
         self._ck(self._lib.rbpf_weights_device_ptr(self._h, C.byref(p)))
         return p.value
+
+
+# ---------------------------------------------------------------------------
+# The reference's particle API on top of the device-resident set.
+# ---------------------------------------------------------------------------
+
+class _SharedSet:
+    """State shared by all Robot views of one filter."""
+
+    def __init__(self, rng="numpy", keep_history=True, **set_kwargs):
+        self.views = []
+        self.ps = None
+        self.rng = rng                    # "numpy": draws from np.random like the reference; "device": Philox
+        self.keep_history = keep_history
+        self.set_kwargs = set_kwargs
+        self.motion_rounds = 0
+        self.update_rounds = 0
+        self._poses = None                # host cache of poses / weights, refreshed lazily
+        self._weights = None
+        self._covs = None
+        self.last_ancestors = None
+
+    def materialise(self, n_beams=384):
+        if self.ps is None:
+            kw = dict(self.set_kwargs)
+            kw.setdefault("n_beams", n_beams)
+            self.ps = ParticleSet(len(self.views), **kw)
+        return self.ps
+
+    def invalidate(self):
+        self._poses = self._weights = self._covs = None
+
+    def poses(self):
+        if self._poses is None:
+            self._poses = self.materialise().poses
+        return self._poses
+
+    def weights(self):
+        if self._weights is None:
+            self._weights = self.materialise().weights
+        return self._weights
+
+    def covs(self):
+        if self._covs is None:
+            self._covs = self.materialise().covs
+        return self._covs
+
+    def record_history(self):
+        if not self.keep_history:
+            return
+        p, w = self.poses(), self.weights()
+        for v in self.views:
+            v._x.append(p[v._slot, 0])
+            v._y.append(p[v._slot, 1])
+            v._theta.append(p[v._slot, 2])
+            if v._weight[-1] != w[v._slot]:
+                v._weight.append(w[v._slot])
+
+
+_DEFAULT_SET = None
+
+
+def new_filter(rng="numpy", keep_history=True, **set_kwargs):
+    """Start a new particle set; the Robot(...) constructions that follow join it.
+    set_kwargs go to ParticleSet (world_tiles, pool_subtiles, device, seed, ...)."""
+    global _DEFAULT_SET
+    _DEFAULT_SET = _SharedSet(rng=rng, keep_history=keep_history, **set_kwargs)
+    return _DEFAULT_SET
+
+
+class _MapView:
+    """What main.py touches on `robot._map` (hybridmap.py:63-327): `_cell_size`,
+    `get_occupied_points()`, `get_odds_at` / `get_pr_at`, `update`."""
+
+    def __init__(self, robot):
+        self._robot = robot
+        self._cell_size = 0.05
+        self._map_len_m = 40
+
+    def _tiles(self):
+        ps = self._robot._shared.materialise()
+        return {c: ps.export_tile(self._robot._slot, c[0], c[1]) for c in ps.list_tiles(self._robot._slot)}
+
+    def get_occupied_points(self):
+        """Cell coordinates of cells with log-odds > 1.0 (hybridmap.py:303-313)."""
+        xs, ys = [], []
+        for (cx, cy), t in self._tiles().items():
+            ix, iy = np.nonzero(np.rint(t * 10.0) > 10)
+            xs.append(((ix - 400) * self._cell_size + cx) / self._cell_size)
+            ys.append(((iy - 400) * self._cell_size + cy) / self._cell_size)
+        if not xs:
+            return [], []
+        return list(np.concatenate(xs)), list(np.concatenate(ys))
+
+    def get_odds_at(self, pos):
+        for (cx, cy), t in self._tiles().items():
+            if cx - 20.0 <= pos.x < cx + 20.0 and cy - 20.0 <= pos.y < cy + 20.0:
+                return t[int((pos.x - cx) / 40 * 800 + 400)][int((pos.y - cy) / 40 * 800 + 400)]
+        return None
+
+    def get_pr_at(self, pos):
+        v = self.get_odds_at(pos)
+        if v is None:
+            return None
+        o = np.exp(v)
+        return o / (1 + o)
+
+    def __str__(self):
+        return "Hybrid Map: %d maps" % len(self._robot._shared.materialise().list_tiles(self._robot._slot))
+
+
+class Robot:
+    """A particle (reference robot.py:19-157) as a view into the device set.
+
+    `Robot(eng)` joins the current filter (see `new_filter`); `imu_update`,
+    `map_update`, `weight`, `x`/`y`/`theta`, `get_latest_pose`, `copy` keep the
+    reference's signatures.  The first view called in a round runs the batched
+    CUDA kernels for every particle; the other calls of that round only catch up.
+    """
+
+    def __init__(self, matlab, _shared=None):
+        if matlab is None and _shared is None:
+            return                                        # Robot(None): the reference's empty shell (robot.py:20-21,142)
+        global _DEFAULT_SET
+        sh = _shared or _DEFAULT_SET or new_filter()
+        if sh.ps is not None:
+            raise RbpfError("the particle set is already on the device; call new_filter() before creating more Robots")
+        self._shared = sh
+        self._slot = len(sh.views)
+        sh.views.append(self)
+        self._map = _MapView(self)
+        self._weight = [1.0]
+        self._x, self._y, self._theta = [0.0], [0.0], [0.0]
+        self._motion_seen = 0
+        self._update_seen = 0
+
+    # -- reference accessors
+    def x(self):
+        return self._x
+
+    def y(self):
+        return self._y
+
+    def theta(self):
+        return self._theta
+
+    def weight(self):
+        return self._weight
+
+    @property
+    def _cov(self):
+        return self._shared.covs()[self._slot]
+
+    def get_latest_pose(self):
+        p = self._shared.poses()[self._slot] if self._shared.ps is not None else (0.0, 0.0, 0.0)
+        return Pose(float(p[0]), float(p[1]), float(p[2]))
+
+    def __str__(self):
+        return "Robot at position: " + str(self.get_latest_pose())
+
+    # -- stage 1, robot.py:45-57
+    def imu_update(self, reading):
+        sh = self._shared
+        if self._motion_seen == sh.motion_rounds:
+            if reading.motion is None:
+                raise RbpfError("this Reading carries no motion family; use the loaders in thesis_b200.loaders")
+            family, par = reading.motion
+            ps = sh.materialise()
+            ps.motion(family, np.asarray(reading.get_data(), dtype=np.float64), reading.dt() / 1e4, par)
+            sh.motion_rounds += 1
+            sh.invalidate()
+            sh.record_history()
+        self._motion_seen += 1
+        return self.get_latest_pose()
+
+    # -- stages 2-4, robot.py:59-115
+    def map_update(self, scan, last_scan=None, adj=False):
+        sh = self._shared
+        if self._update_seen == sh.update_rounds:
+            if scan.ranges() is None:
+                raise RbpfError("map_update needs a Scan built from ranges (Lidar[i])")
+            ps = sh.materialise(len(scan))
+            ps.set_scan(scan.ranges(), scan.angles())
+            ps.scan_match()          # adj (scan-to-previous-scan, hybridmap.py:147-191) is a declared "next" row: scan-to-map is used
+            if sh.rng == "numpy":
+                valid = ps.match_result()["valid"]
+                z = np.zeros((ps.N, ps.K, 3))
+                for i in np.flatnonzero(valid):          # draw order: particle-major, skipped for failed matches
+                    z[i] = np.random.standard_normal((ps.K, 3))
+                ps.weight(z)
+            else:
+                ps.weight(None)
+            ps.integrate(fallback_weights=True)
+            sh.update_rounds += 1
+            sh.invalidate()
+            sh.record_history()
+        self._update_seen += 1
+
+    def copy(self):
+        raise RbpfError("Robot.copy(): duplicates are made on the device by resample() (copy-on-write)")
+
+
+def make_particles(n, rng="numpy", keep_history=True, **set_kwargs):
+    """Replacement for `particles = [Robot(eng) for _ in range(NUM_PARTICLES)]` (main.py:87)."""
+    sh = new_filter(rng=rng, keep_history=keep_history, **set_kwargs)
+    return [Robot("gpu", _shared=sh) for _ in range(n)]
+
+
+def seed_map(particles, scan, times=2):
+    """The map seeding of main.py:89-90: integrate `scan` at every particle's pose."""
+    sh = particles[0]._shared
+    ps = sh.materialise(len(scan))
+    ps.set_scan(scan.ranges(), scan.angles())
+    for _ in range(times):
+        ps.integrate()
+
+
+def resample(particles):
+    """main.resample (main.py:46-79): systematic resampling when max - min > 200.
+    Returns the new particle list (views re-bound to the resampled slots)."""
+    sh = particles[0]._shared
+    ps = sh.materialise()
+    if sh.rng == "numpy":
+        w = sh.weights()
+        # the reference draws its uniform only when the trigger fires (main.py:50,59)
+        u01 = float(np.random.random()) if np.max(w) - np.min(w) > 200 else 0.5
+        did, anc = ps.resample(u01)
+    else:
+        did, anc = ps.resample(None)
+    sh.last_ancestors = anc
+    sh.invalidate()
+    if did:
+        if sh.keep_history:
+            old = [(list(v._x), list(v._y), list(v._theta), list(v._weight)) for v in sh.views]
+            for v in sh.views:
+                hx, hy, ht, hw = old[anc[v._slot]]
+                v._x, v._y, v._theta, v._weight = list(hx), list(hy), list(ht), list(hw) + [1.0]
+        else:
+            for v in sh.views:
+                v._weight = [1.0]
+    return list(sh.views)
