@@ -168,6 +168,27 @@ int32_t rbpf_rot_count(void);
 
 /* Local weights of this rank, contiguous N doubles, to be all-gathered. */
 int rbpf_weights_device_ptr(rbpf_handle h, uint64_t *dev_ptr);
+/* Global systematic resample (main.py:46-67) on the all-gathered weights of all
+ * ranks (n_global doubles, identical on every rank): fills the handle's ancestor
+ * vector, moves nothing.  ancestors_out (nullable host, n_global) synchronises. */
+int rbpf_resample_global(rbpf_handle h, uint64_t weights_all_dev, int32_t n_global, const double *u01,
+                         int32_t *did_resample, int32_t *ancestors_out);
+/* Sender: src_slots[n] = local particles a peer needs (each once).  _count
+ * de-duplicates their sub-tiles and reports how many travel and the packed size;
+ * _pack writes [records | page tables | sub-tile payloads] to dev_buf. */
+int rbpf_migrate_count(rbpf_handle h, const int32_t *src_slots, int32_t n, int32_t *n_subtiles, int64_t *bytes);
+int rbpf_migrate_pack(rbpf_handle h, uint64_t dev_buf);
+int64_t rbpf_migrate_bytes(rbpf_handle h, int32_t n_particles, int32_t n_subtiles);
+/* Local half of the resample: gather local ancestors, fix reference counts
+ * (replaces Robot.copy robot.py:141-149 by page-table sharing).  Call after the
+ * packs and before the unpacks. */
+int rbpf_resample_apply_local(rbpf_handle h);
+/* Receiver: adopt a packed buffer; local slot dst_slots[i] becomes a copy of
+ * received record rec_index[i] (weight 1.0, main.py:77-78). */
+int rbpf_migrate_unpack(rbpf_handle h, uint64_t dev_buf, int32_t n_particles, int32_t n_subtiles,
+                        const int32_t *dst_slots, const int32_t *rec_index, int32_t m);
+/* Make the resampled particle buffers current. */
+int rbpf_resample_commit(rbpf_handle h);
 
 #ifdef __cplusplus
 }

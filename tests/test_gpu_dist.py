@@ -1,0 +1,67 @@
+"""GPU: the sharded resample (global plan + sub-tile migration) emulated with two
+rank slices on ONE device -- buffers are handed over directly instead of through
+NCCL -- must reproduce a single set holding all particles."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from thesis_b200 import dist, particles
+
+    return torch, dist, particles
+
+
+def test_two_rank_emulation_equals_single_set(mods, golden):
+    torch, D, P = mods
+    world, nl, B, K = 2, 6, 180, 30
+    N = world * nl
+    ang = golden["intel_angles"]
+    rng = np.random.default_rng(21)
+    one = P.ParticleSet(N, B, pool_subtiles=3000)
+    ranks = [D.MigratingSet(nl, B, r, world, pool_subtiles=2000) for r in range(world)]
+    par = (0.002, 0.05, 0.01 * np.pi / 180, 0.05)
+    r0 = golden["intel_ranges"][0]
+    for ps in [one] + ranks:
+        for _ in range(2):
+            ps.set_scan(r0, ang)
+            ps.integrate()
+    for step in range(1, 6):
+        u = (rng.normal(0.05, 0.02), rng.normal(0, 0.02), rng.normal(-0.3, 0.05))
+        z = rng.standard_normal((N, K, 3))
+        u01 = float(rng.random())
+        r = golden["intel_ranges"][step]
+        one.motion(1, u, 1.0, par)
+        one.set_scan(r, ang); one.scan_match(); one.weight(z); one.integrate(fallback_weights=True)
+        did1, anc1 = one.resample(u01)
+        for k, ps in enumerate(ranks):
+            ps.motion(1, u, 1.0, par)
+            ps.set_scan(r, ang); ps.scan_match(); ps.weight(z[k * nl:(k + 1) * nl]); ps.integrate(fallback_weights=True)
+        w_all = torch.cat([ps.local_weights_tensor().clone() for ps in ranks])       # the all-gather
+        packed = [ps.pack_outgoing(w_all, u01) for ps in ranks]
+        for k, ps in enumerate(ranks):
+            assert packed[k][0] == did1
+            assert np.array_equal(ps._anc, anc1), "step %d: ancestors differ from the single set" % step
+        for k, ps in enumerate(ranks):
+            incoming = {r_: packed[r_][1][k] for r_ in range(world) if r_ != k}      # the all-to-all
+            ps.adopt_incoming(incoming, packed[k][2])
+        poses = np.concatenate([ps.poses for ps in ranks])
+        assert np.array_equal(poses, one.poses), "step %d" % step
+        assert np.array_equal(np.concatenate([ps.weights for ps in ranks]), one.weights)
+        assert np.array_equal(np.concatenate([ps.covs for ps in ranks]), one.covs)
+    assert sum(ps.migrated_particles for ps in ranks) > 0, "test never exercised a migration"
+    for j in range(N):
+        ps, lj = ranks[j // nl], j % nl
+        assert sorted(ps.list_tiles(lj)) == sorted(one.list_tiles(j))
+        for (cx, cy) in one.list_tiles(j):
+            assert np.array_equal(ps.export_tile(lj, cx, cy), one.export_tile(j, cx, cy)), "particle %d tile %s" % (j, (cx, cy))
+    # pool accounting: nothing leaked on either rank
+    for ps in ranks:
+        st = ps.stats()
+        assert st["pool_in_use"] <= st["total_refs"]

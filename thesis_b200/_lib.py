@@ -65,6 +65,13 @@ SIGNATURES = {
     "rbpf_rot_step": (C.c_double, []),
     "rbpf_rot_count": (C.c_int32, []),
     "rbpf_weights_device_ptr": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
+    "rbpf_resample_global": (C.c_int, [_H, C.c_uint64, C.c_int32, _dp, _ip, _ip]),
+    "rbpf_migrate_count": (C.c_int, [_H, _ip, C.c_int32, _ip, C.POINTER(C.c_int64)]),
+    "rbpf_migrate_pack": (C.c_int, [_H, C.c_uint64]),
+    "rbpf_migrate_bytes": (C.c_int64, [_H, C.c_int32, C.c_int32]),
+    "rbpf_resample_apply_local": (C.c_int, [_H]),
+    "rbpf_migrate_unpack": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int32, _ip, _ip, C.c_int32]),
+    "rbpf_resample_commit": (C.c_int, [_H]),
 }
 
 _LIB = None

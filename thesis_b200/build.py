@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_librbpf.so")
-SOURCES = ["ctx.cu", "k_motion.cu", "k_match.cu", "k_weight.cu", "k_raycast.cu", "k_resample.cu", "k_misc.cu"]
+SOURCES = ["ctx.cu", "k_motion.cu", "k_match.cu", "k_weight.cu", "k_raycast.cu", "k_resample.cu", "k_migrate.cu", "k_misc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -30,6 +30,10 @@ struct rbpf_ctx {
     double *h_scan;                // pinned staging: px, py, dist
     int have_scan;
     // optional per-stage CUDA-event timing of rbpf_step
+    int *d_mg_slots;               // 2*N staging ints (migration)
+    uint32_t *d_mg_mark, *d_mg_list;
+    int *d_mg_count;
+    int mg_n, mg_tiles;
     std::vector<cudaEvent_t> tev;  // (RB_NSTAGES + 1) events per recorded step
     int t_max_steps, t_steps;
 };
@@ -171,6 +175,10 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_tile, RB_DIM * RB_DIM);
     A(h->d_slice, RB_SLICE_W * RB_SLICE_W);
     A(h->d_refstats, 2);
+    A(h->d_mg_slots, 2 * N);
+    A(h->d_mg_mark, d.pool_tiles);
+    A(h->d_mg_list, d.pool_tiles);
+    A(h->d_mg_count, 4);
 #undef A
     if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     if (cudaMallocHost((void **)&h->h_scan, 3 * RB_MAXB * sizeof(double)) != cudaSuccess)
@@ -189,6 +197,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "table upload failed");
+    h->mg_n = h->mg_tiles = 0;
+    cudaMemsetAsync(h->d_mg_mark, 0xFF, sizeof(uint32_t) * (size_t)d.pool_tiles, h->stream);
     rb_launch_init(d, h->stream);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, std::string("init: ") + cudaGetErrorString(e));
@@ -511,4 +521,94 @@ extern "C" int rbpf_weights_device_ptr(rbpf_handle h, uint64_t *dev_ptr)
     if (!h || !dev_ptr) return RBPF_ERR_ARG;
     *dev_ptr = (uint64_t)(uintptr_t)h->d.weight;
     return RBPF_OK;
+}
+
+// Global systematic resample on the all-gathered weights; every rank computes
+// the identical ancestor vector (main.py:46-67).  Does not move any particle.
+extern "C" int rbpf_resample_global(rbpf_handle h, uint64_t weights_all_dev, int32_t n_global, const double *u01,
+                                    int32_t *did_resample, int32_t *ancestors_out)
+{
+    if (!h || !weights_all_dev || n_global != h->d.n_global) { if (h) h->err = "resample_global: bad arguments"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    return resample_common(h, (const double *)(uintptr_t)weights_all_dev, u01, ancestors_out, did_resample);
+}
+
+static int upload_ints(rbpf_ctx *h, int *dst, const int32_t *src, int n)
+{
+    if (n > 0) CK(cudaMemcpyAsync(dst, src, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    return RBPF_OK;
+}
+
+// Sender, step 1: how many distinct sub-tiles go with these local particles.
+extern "C" int rbpf_migrate_count(rbpf_handle h, const int32_t *src_slots, int32_t n, int32_t *n_subtiles, int64_t *bytes)
+{
+    if (!h || n < 0 || n > h->d.N || (n > 0 && !src_slots) || !n_subtiles) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = upload_ints(h, h->d_mg_slots, src_slots, n);
+    if (rc) return rc;
+    rb_launch_migrate_claim(h->d, h->d_mg_slots, n, h->d_mg_mark, h->d_mg_list, h->d_mg_count, h->stream);
+    CK(cudaGetLastError());
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, h->d_mg_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_subtiles = cnt;
+    h->mg_n = n;
+    h->mg_tiles = cnt;
+    if (bytes) *bytes = (int64_t)rb_migrate_bytes(n, cnt, h->d.nsub);
+    return RBPF_OK;
+}
+
+// Sender, step 2: pack what rbpf_migrate_count just claimed into dev_buf.
+extern "C" int rbpf_migrate_pack(rbpf_handle h, uint64_t dev_buf)
+{
+    if (!h || (!dev_buf && h->mg_n > 0)) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    rb_launch_migrate_pack(h->d, h->d_mg_slots, h->mg_n, h->mg_tiles, h->d_mg_mark, h->d_mg_list, h->d_mg_count,
+                           (unsigned char *)(uintptr_t)dev_buf, h->stream);
+    CK(cudaGetLastError());
+    h->mg_n = h->mg_tiles = 0;
+    return RBPF_OK;
+}
+
+// Receiver: adopt n_particles records / n_subtiles payloads from dev_buf; local
+// destination slot dst_slots[i] becomes a copy of received record rec_index[i].
+extern "C" int rbpf_migrate_unpack(rbpf_handle h, uint64_t dev_buf, int32_t n_particles, int32_t n_subtiles,
+                                   const int32_t *dst_slots, const int32_t *rec_index, int32_t m)
+{
+    if (!h || n_particles < 0 || m < 0 || m > h->d.N || (m > 0 && (!dst_slots || !rec_index || !dev_buf))) return RBPF_ERR_ARG;
+    if ((uint32_t)n_subtiles > h->d.pool_tiles) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = upload_ints(h, h->d_mg_slots, dst_slots, m);
+    if (!rc) rc = upload_ints(h, h->d_mg_slots + h->d.N, rec_index, m);
+    if (rc) return rc;
+    rb_launch_migrate_unpack(h->d, (const unsigned char *)(uintptr_t)dev_buf, n_particles, n_subtiles, h->d_mg_slots,
+                             h->d_mg_slots + h->d.N, m, h->d_mg_list, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));                       // the staging arrays are reused by the next peer
+    return RBPF_OK;
+}
+
+// Local half of the resample (gather of local ancestors, reference counts); call
+// after every rbpf_migrate_pack and before any rbpf_migrate_unpack.
+extern "C" int rbpf_resample_apply_local(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    rb_launch_resample_apply(h->d, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+// Make the resampled buffers current (after the last rbpf_migrate_unpack).
+extern "C" int rbpf_resample_commit(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    swap_buffers(h);
+    h->d.step_no++;
+    return RBPF_OK;
+}
+
+extern "C" int64_t rbpf_migrate_bytes(rbpf_handle h, int32_t n_particles, int32_t n_subtiles)
+{
+    return h ? (int64_t)rb_migrate_bytes(n_particles, n_subtiles, h->d.nsub) : 0;
 }

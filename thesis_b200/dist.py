@@ -1,0 +1,198 @@
+"""Particle sharding across the GPUs of one box.
+
+One process per GPU (torchrun), each owning a contiguous slice of the particles,
+its own tile pool and page tables.  Stages 1-4 touch only a rank's own
+particles; the one exchange step is resampling:
+
+  1. all-gather of the weights over NCCL (8 B x N),
+  2. every rank runs the identical global systematic resample
+     (`rbpf_resample_global`, bit-exact ancestors on all ranks),
+  3. survivors whose ancestor lives on another rank migrate: the sender packs
+     state + page table + the de-duplicated sub-tiles (`rbpf_migrate_count/pack`),
+     NCCL all-to-all moves the buffers over NVLink, the receiver adopts them into
+     its pool (`rbpf_migrate_unpack`).
+
+`plan_migration` is pure numpy (same result on every rank, no negotiation) and is
+what the gloo CPU tests exercise; the byte movement is torch.distributed.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .particles import ParticleSet
+
+_ip = C.POINTER(C.c_int32)
+
+
+def owner_of(global_index, n_local):
+    return global_index // n_local
+
+
+def plan_migration(ancestors, n_local, rank, world):
+    """From the global ancestor vector derive, for this rank:
+      send[r]  = sorted unique LOCAL slots whose particle rank r needs,
+      recv[r]  = (dst_slots, rec_index): local destination slots fed by rank r and,
+                 for each, the index into r's send list (== r's send[rank]).
+    Every rank computes both sides from the same vector, so sizes agree."""
+    ancestors = np.asarray(ancestors, dtype=np.int64)
+    send, recv = {}, {}
+    src_rank = ancestors // n_local
+    dst_rank = np.arange(len(ancestors)) // n_local
+    for r in range(world):
+        if r == rank:
+            continue
+        m = (src_rank == rank) & (dst_rank == r)
+        send[r] = np.unique(ancestors[m] - rank * n_local).astype(np.int32)
+        m2 = (src_rank == r) & (dst_rank == rank)
+        dst_slots = (np.flatnonzero(m2) - rank * n_local).astype(np.int32)
+        needed = ancestors[m2] - r * n_local
+        uniq = np.unique(needed)
+        recv[r] = (dst_slots, np.searchsorted(uniq, needed).astype(np.int32), len(uniq))
+    return send, recv
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can view library memory."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class MigratingSet(ParticleSet):
+    """ParticleSet slice of one rank + the two halves of the resample exchange,
+    independent of how the bytes travel (NCCL in ShardedParticleSet, plain device
+    copies in the single-GPU emulation used by the tests)."""
+
+    def __init__(self, n_local, n_beams, rank, world, device=0, **kw):
+        import torch
+
+        self._torch = torch
+        super().__init__(n_local, n_beams, device=device, rank=rank, world=world, **kw)
+        self.n_global = n_local * world
+        self._dev = torch.device("cuda", device)
+        self._w_local = torch.as_tensor(_DevArray(self.weights_device_ptr(), n_local, "<f8"), device=self._dev)
+        self._anc = np.empty(self.n_global, dtype=np.int32)
+        self.migrated_particles = 0
+        self.migrated_bytes = 0
+
+    def local_weights_tensor(self):
+        return self._w_local
+
+    def pack_outgoing(self, weights_all, u01=None):
+        """Global resample on the gathered weights, then pack what leaves this rank.
+        Returns (did_resample, {peer: (buffer, n_particles, n_subtiles)}, recv_plan)."""
+        lib, torch = self._lib, self._torch
+        did = C.c_int32(0)
+        up = None
+        if u01 is not None:
+            u = C.c_double(float(u01))
+            up = C.cast(C.byref(u), C.POINTER(C.c_double))
+        self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, C.byref(did),
+                                          self._anc.ctypes.data_as(_ip)))
+        send, recv = plan_migration(self._anc, self.N, self.rank, self.world)
+        out = {}
+        for r, slots in send.items():
+            nt, nbytes = C.c_int32(0), C.c_int64(0)
+            self._ck(lib.rbpf_migrate_count(self._h, slots.ctypes.data_as(_ip), len(slots), C.byref(nt), C.byref(nbytes)))
+            buf = torch.empty(int(nbytes.value) if len(slots) else 0, dtype=torch.uint8, device=self._dev)
+            self._ck(lib.rbpf_migrate_pack(self._h, buf.data_ptr() if len(slots) else 0))
+            out[r] = (buf, len(slots), int(nt.value))
+            self.migrated_particles += len(slots)
+            self.migrated_bytes += buf.numel()
+        return bool(did.value), out, recv
+
+    def adopt_incoming(self, incoming, recv_plan):
+        """Local gather / refcounts, then adopt {peer: (buffer, n_particles, n_subtiles)}."""
+        lib = self._lib
+        self._ck(lib.rbpf_resample_apply_local(self._h))
+        for r, (buf, n_in, t_in) in incoming.items():
+            dst_slots, rec_idx, n_plan = recv_plan[r]
+            assert n_in == n_plan, "migration plan mismatch between ranks"
+            if n_in:
+                self._ck(lib.rbpf_migrate_unpack(self._h, buf.data_ptr(), n_in, t_in, dst_slots.ctypes.data_as(_ip),
+                                                 rec_idx.ctypes.data_as(_ip), len(dst_slots)))
+        self._ck(lib.rbpf_resample_commit(self._h))
+
+    def recv_bytes(self, n_particles, n_subtiles):
+        return int(self._lib.rbpf_migrate_bytes(self._h, n_particles, n_subtiles))
+
+
+class ShardedParticleSet(MigratingSet):
+    """One rank of a torch.distributed (NCCL) job."""
+
+    def __init__(self, n_local, n_beams, group=None, device=0, **kw):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        super().__init__(n_local, n_beams, dist.get_rank(group), dist.get_world_size(group), device=device, **kw)
+        self._w_all = self._torch.empty(self.n_global, dtype=self._torch.float64, device=self._dev)
+        self._tev = None
+
+    def resample(self, u01=None, want_ancestors=True):
+        torch, dist = self._torch, self._dist
+        dist.all_gather_into_tensor(self._w_all, self._w_local, group=self.group)
+        did, out, recv = self.pack_outgoing(self._w_all, u01)
+        meta = torch.zeros((self.world, 2), dtype=torch.int64)
+        for r, (_, n, nt) in out.items():
+            meta[r, 0], meta[r, 1] = n, nt
+        meta_dev = meta.to(self._dev)
+        meta_in = torch.empty_like(meta_dev)
+        dist.all_to_all_single(meta_in, meta_dev, group=self.group)       # sub-tile counts of what arrives
+        meta_in = meta_in.cpu()
+        incoming, ops = {}, []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            n_in, t_in = int(meta_in[r, 0]), int(meta_in[r, 1])
+            if n_in:
+                buf = torch.empty(self.recv_bytes(n_in, t_in), dtype=torch.uint8, device=self._dev)
+                incoming[r] = (buf, n_in, t_in)
+                ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
+            else:
+                incoming[r] = (None, 0, 0)
+            if out[r][1]:
+                ops.append(dist.P2POp(dist.isend, out[r][0], r, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self.adopt_incoming(incoming, recv)
+        return did, (self._anc.copy() if want_ancestors else None)
+
+    def step(self, ranges, angles):
+        """One lidar event on this rank's slice + the global resample."""
+        ev = self._tev
+        marks = []
+
+        def mark():
+            if ev is not None:
+                e = self._torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+
+        mark(); self.set_scan(ranges, angles)
+        mark(); self.scan_match()
+        mark(); self.weight(None)
+        mark(); self.integrate(fallback_weights=True)
+        mark(); self.resample(None, want_ancestors=False)
+        mark()
+        if ev is not None:
+            ev.append(marks)
+
+    def timing_enable(self, max_steps):
+        self._tev = [] if max_steps > 0 else None
+
+    def timing_read(self):
+        out = {k: 0.0 for k in self.STAGES}
+        steps = self._tev or []
+        self._torch.cuda.synchronize()
+        for m in steps:
+            out["set_scan"] += m[0].elapsed_time(m[1])
+            out["match"] += m[1].elapsed_time(m[2])
+            out["weight"] += m[2].elapsed_time(m[3])
+            out["raycast_cast"] += m[3].elapsed_time(m[4])       # prepare + cast + fallback weights
+            out["resample_plan"] += m[4].elapsed_time(m[5])      # all-gather + plan + migration + apply
+        n = len(steps)
+        if self._tev is not None:
+            self._tev = []
+        return out, n
