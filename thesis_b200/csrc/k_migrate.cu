@@ -19,7 +19,7 @@
 
 #define MG_REC_DOUBLES 13            // pose 3 + cov 9 + exists mask (bit pattern)
 
-__host__ __device__ inline size_t mg_rec_bytes(int nsub) { return (size_t)MG_REC_DOUBLES * 8 + (size_t)nsub * 4; }
+__host__ __device__ inline size_t mg_rec_bytes(int nsub) { return ((size_t)MG_REC_DOUBLES * 8 + (size_t)nsub * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t mg_header_bytes(int n, int nsub) { return (mg_rec_bytes(nsub) * (size_t)n + 255) & ~(size_t)255; }
 
 // pass 1: every allocated page-table entry of the departing particles claims its sub-tile once
