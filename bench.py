@@ -288,7 +288,9 @@ def run_b200(args):
         "config": dict(workload_config(args, world), burnin_scans=args.burnin,
                        ray_cells_per_scan=a_r, pool_subtiles=pool,
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),
-                       pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"]),
+                       pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
+                       match_scoring_passes_per_update=st["match_evals"] / max(1, n_local * (s - 1)),
+                       match_exhaustive_passes_per_update=231),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h)},

@@ -56,6 +56,7 @@
 #define RESAMPLE_TRIGGER 200.0 /* main.py:50 */
 #define ROT_RANGE (M_PI / 6.0) /* hybridmap.py:249 */
 #define MAX_NT 14          /* window clamp 0.7 m (robot.py:64-65) / 0.05 m */
+#define ROT_LINE_HALF 16   /* rotation-variance support: +-16 lattice steps (~4.2 deg) around the best rotation */
 
 /* ------------------------------------------------------------------ map -- */
 
@@ -484,7 +485,7 @@ static int64_t match_key(int score, int i, int j, int k)
  *   gate       matchScanCustom.m:52-57 isValidPose : strictly inside the window
  *              and not the zero correction, else cov = NaN, score = 0 (:26-28).
  *   covariance weights 2^(score - best) over the translation slice at the best
- *              rotation and over the rotation line at the best translation,
+ *              rotation and over the rotation line (+-16 steps) at the best translation,
  *              cross terms zero, plus the lattice quantisation variance.
  *   result     guess + correction, hybridmap.py:253-255.
  * No NDT refinement (matchScanCustom.m:32-50): declared, see DESIGN.md.
@@ -611,7 +612,9 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
                 W0 += w; Wx += w * i; Wy += w * j; Wxx += w * i * i; Wyy += w * j * j; Wxy += w * i * j;
             }
         int64_t T0 = 0, T1 = 0, T2 = 0;
-        for (int k = -nk; k <= nk; k++) {
+        int klo = bk - ROT_LINE_HALF < -nk ? -nk : bk - ROT_LINE_HALF;
+        int khi = bk + ROT_LINE_HALF > nk ? nk : bk + ROT_LINE_HALF;
+        for (int k = klo; k <= khi; k++) {
             int d = bs - vol[((size_t)(k + nk) * W + (bj + MAX_NT)) * W + (bi + MAX_NT)];
             if (d > 40) continue;
             int64_t w = (int64_t)1 << (40 - d);

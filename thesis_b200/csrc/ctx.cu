@@ -511,6 +511,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_failed = s.match_failed;
     out->shared_refs = rs[0];
     out->total_refs = rs[1];
+    out->match_evals = s.match_evals;
     return RBPF_OK;
 }
 

@@ -24,18 +24,34 @@
 //   4. bit-sliced max + tie-break key per lane, warp-shuffle argmax, CTA argmax.
 //   5. covariance from the score slice at the best rotation and the score line
 //      at the best translation (integer moments, weights 2^(score - best)).
+//
+// Branch and bound over rotations (exact): rotations are grouped by MT_GROUP
+// consecutive lattice steps.  A point at range <= 11 m moves at most one cell per
+// rotation step, so scoring the group's middle rotation against the bitmap
+// dilated by MT_GRAD cells bounds the score of every rotation of the group at
+// every translation from above.  Phase A scores every group once (231/8 = 29
+// passes instead of 231), phase B visits groups in decreasing bound and scores a
+// member rotation only while its bound can still beat the best key so far.  The
+// result is identical to the exhaustive search of the oracle.
 #include "common.cuh"
 
-#define MT_WARPS 8
+#define MT_GROUP 8                      // rotations per group
+#define MT_GRAD 5                       // dilation radius: ceil(MT_GROUP/2) cells of motion + 1 cell of rounding
+#define MT_MAXGROUPS 32
+#define MT_ROT_LINE_HALF 16             // rotation-variance support (oracle ROT_LINE_HALF)
+#define MT_WARPS 12
 #define MT_THREADS (MT_WARPS * 32)
 #define MT_PLANES 9                     // bit-sliced counters up to 511 >= RB_MAXB
 
 struct MatchShared {
     double gx, gy, gth, cs0, sn0, fx, fy, rx, ry;
     int M, nx, ny, g0xu, g0yu, x0, y0, t0x, t0y, ok, overflow;
-    unsigned long long warp_key[MT_WARPS];
     unsigned long long best_key;
     long long mom[9];                   // W0 Wx Wy Wxx Wyy Wxy T0 T1 T2
+    int group_ub[MT_MAXGROUPS];         // phase A: upper bound of every rotation group
+    int group_order[MT_MAXGROUPS];      // groups by decreasing bound
+    int next_item;                      // phase B work queue
+    int evals;                          // rotations actually scored (statistics)
 };
 
 __host__ __device__ inline size_t mt_bm_words() { return ((size_t)RB_BM_ROWS * RB_BM_STRIDE + 3) & ~(size_t)3; }  // keeps raw/pts 16-B aligned
@@ -43,7 +59,7 @@ __host__ __device__ inline size_t mt_raw_words() { return (size_t)RB_RAW_ROWS * 
 
 size_t rb_match_smem_bytes()
 {
-    size_t words = mt_bm_words() + mt_raw_words();
+    size_t words = 2 * mt_bm_words() + mt_raw_words();
     words = (words + 1) & ~(size_t)1;
     return words * 4 + 2 * RB_MAXB * sizeof(double) + sizeof(MatchShared);
 }
@@ -158,8 +174,9 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm = smem;
-    uint32_t *raw = bm + mt_bm_words();
-    size_t w_end = (mt_bm_words() + mt_raw_words() + 1) & ~(size_t)1;
+    uint32_t *bmg = bm + mt_bm_words();                                     // bm dilated by MT_GRAD (group bounds)
+    uint32_t *raw = bmg + mt_bm_words();                                    // staging, then per-warp point lists
+    size_t w_end = (2 * mt_bm_words() + mt_raw_words() + 1) & ~(size_t)1;
     double *ccx = reinterpret_cast<double *>(smem + w_end);
     double *ccy = ccx + RB_MAXB;
     MatchShared *sh = reinterpret_cast<MatchShared *>(ccy + RB_MAXB);
@@ -192,6 +209,8 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         sh->M = 0;
         sh->overflow = 0;
         sh->best_key = 0ull;
+        sh->next_item = 0;
+        sh->evals = 0;
 #pragma unroll
         for (int q = 0; q < 9; q++) sh->mom[q] = 0;
     }
@@ -254,21 +273,93 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     }
     __syncthreads();
 
+    // dilation by MT_GRAD for the rotation-group bounds: horizontal pass bm -> raw,
+    // vertical pass raw -> bmg (rows / words outside the window are empty)
+    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
+        const int r = idx / RB_BM_STRIDE, w = idx - r * RB_BM_STRIDE;
+        uint32_t v = 0;
+        if (w < RB_BM_STRIDE - 1) {
+            const uint32_t cur = bm[idx], prev = w > 0 ? bm[idx - 1] : 0u, next = bm[idx + 1];
+            v = cur;
+#pragma unroll
+            for (int d = 1; d <= MT_GRAD; d++) v |= (cur << d) | (cur >> d) | (prev >> (32 - d)) | (next << (32 - d));
+        }
+        raw[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
+        const int r = idx / RB_BM_STRIDE;
+        const int r0 = max(r - MT_GRAD, 0), r1 = min(r + MT_GRAD, RB_BM_ROWS - 1);
+        uint32_t v = 0;
+        for (int rr = r0; rr <= r1; rr++) v |= raw[idx + (rr - r) * RB_BM_STRIDE];
+        bmg[idx] = v;
+    }
+    __syncthreads();
+
     const int M = sh->M, nx = sh->nx, ny = sh->ny;
     const int nrows = 2 * ny + 1, ncols = 2 * nx + 1;
     const uint32_t colmask = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
     uint32_t *pts = raw + warp * RB_MAXB;                                   // raw is dead now: per-warp point lists
     const int lane_off = (lane < nrows ? lane : 0) * RB_BM_STRIDE;
-    unsigned long long best = 0ull;
+    const int nrot = 2 * c.nk + 1, ngroups = (nrot + MT_GROUP - 1) / MT_GROUP;
 
-    // ---- 3. score all rotations ---------------------------------------------
+    // ---- 3a. upper bound of every rotation group --------------------------------
     if (sh->ok) {
-        for (int k = -c.nk + warp; k <= c.nk; k += MT_WARPS) {
+        for (int g = warp; g < ngroups; g += MT_WARPS) {
+            const int kmid = min(g * MT_GROUP + MT_GROUP / 2, nrot - 1) - c.nk;
+            __syncwarp();
+            mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+            __syncwarp();
+            uint32_t pl[MT_PLANES];
+            mt_accumulate(bmg, pts, M, lane_off, pl);
+            int sc = 0;
+            if (lane < nrows) {
+                uint32_t cand = colmask;
+#pragma unroll
+                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+                    uint32_t t = cand & pl[pbit];
+                    if (t) { cand = t; sc |= 1 << pbit; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) sc = max(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+            if (lane == 0) sh->group_ub[g] = sc;
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && sh->ok) {                                              // rank the groups by decreasing bound
+        if (lane < ngroups) {
+            const int mine = sh->group_ub[lane];
+            int rank = 0;
+            for (int g = 0; g < ngroups; g++) {
+                const int o = sh->group_ub[g];
+                rank += (o > mine) || (o == mine && g < lane);
+            }
+            sh->group_order[rank] = lane;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3b. score member rotations while their group's bound can still win -----
+    if (sh->ok) {
+        volatile unsigned long long *vbest = &sh->best_key;
+        for (;;) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&sh->next_item, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= ngroups * MT_GROUP) break;
+            const int g = sh->group_order[item / MT_GROUP];
+            const int ridx = g * MT_GROUP + item % MT_GROUP;
+            if (ridx >= nrot) continue;
+            const int k = ridx - c.nk, ub = sh->group_ub[g];
+            const unsigned long long cur = *vbest;
+            if (ub < (int)(cur >> 32)) break;                               // groups are sorted: nothing left can win
+            if (mt_key(ub, 0, 0, k) < cur) continue;                        // this rotation cannot beat the best key
             __syncwarp();
             mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
             mt_accumulate(bm, pts, M, lane_off, pl);
+            unsigned long long key = 0ull;
             if (lane < nrows) {
                 // bit-sliced max over the ncols translation bits
                 uint32_t cand = colmask;
@@ -284,21 +375,17 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
                 int dn = lowm ? nx - (31 - __clz(lowm)) : 99;
                 int dp = highm ? __ffs(highm) - 1 : 99;
                 int i = dn <= dp ? -dn : dp;
-                unsigned long long key = mt_key(sc, i, lane - ny, k);
-                if (key > best) best = key;
+                key = mt_key(sc, i, lane - ny, k);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                if (other > key) key = other;
+            }
+            if (lane == 0) {
+                atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
+                atomicAdd(&sh->evals, 1);
             }
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        if (other > best) best = other;
-    }
-    if (lane == 0) sh->warp_key[warp] = best;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long b = 0ull;
-        for (int q = 0; q < MT_WARPS; q++) if (sh->warp_key[q] > b) b = sh->warp_key[q];
-        sh->best_key = b;
     }
     __syncthreads();
     int bs, bi, bj, bk;
@@ -340,7 +427,8 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             }
         } else {                                                            // rotation line at the best translation
             long long T0 = 0, T1 = 0, T2 = 0;
-            for (int k = -c.nk + (warp - 1); k <= c.nk; k += MT_WARPS - 1) {
+            const int klo = max(bk - MT_ROT_LINE_HALF, -c.nk), khi = min(bk + MT_ROT_LINE_HALF, c.nk);
+            for (int k = klo + (warp - 1); k <= khi; k += MT_WARPS - 1) {
                 __syncwarp();
                 mt_rasterise(c, sh, ccx, ccy, k, pts, lane, bi, bj, 0, 0);
                 __syncwarp();
@@ -375,6 +463,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         ob[0] = bi; ob[1] = bj; ob[2] = bk; ob[3] = M;
         c.m_valid[p] = valid ? 1 : 0;
         if (sh->overflow) atomicExch(&c.flags->world_overflow, 1);
+        if (!slice_out) atomicAdd(&c.stats->match_evals, (unsigned long long)(sh->evals + ngroups));
         if (!valid) {                                                       // matchScanCustom.m:26-28
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             for (int q = 0; q < 9; q++) oc[q] = nan;
