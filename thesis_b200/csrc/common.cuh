@@ -58,7 +58,6 @@ struct RbCtx {
     int tiles_x, tiles_y, txh, tyh;         // world extent in reference tiles, half extents
     int subs_x, subs_y, nsub;               // sub-tile grid of the world
     int ux_max, uy_max;                     // storage extent in cells
-    int lut_h;                              // half extent (tiles) covered by the write LUT
     uint32_t pool_tiles;
     // tile pool
     int8_t *pool;
@@ -82,7 +81,7 @@ struct RbCtx {
     double *m_pose, *m_cov, *m_score;
     int *m_valid, *m_best;
     // write-path LUT (lattice cell k -> storage coordinate)
-    const uint16_t *lut;
+    const uint32_t *lutx, *luty;            // per axis, packed: off | sub << 8 | tile << 20
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch
     int *ancestors;                         // n_global
@@ -110,14 +109,21 @@ __device__ __forceinline__ void rb_xform(double c, double s, double x, double y,
 // Read path, one axis: HybridMapEntry.is_in_map hybridmap.py:44-45 on the 40 m
 // lattice followed by GridMap.get_cell gridmap.py:120-128.  Returns the tile
 // lattice index in t and the tile-local index in idx.
+//
+// The reference's index expression int(rel/40*800 + 400) needs an IEEE divide.
+// rel*20 + 400 differs from it by < 1e-12, so its truncation is the same unless
+// the value sits within 1e-6 of an integer; only then is the exact expression
+// replayed.  The tile candidate uses a multiply and is fixed up by exact compares.
 __device__ __forceinline__ void rb_read_axis(double g, int &t, int &idx)
 {
-    t = __double2int_rd(g / RB_TILE_LEN + 0.5);
+    t = __double2int_rd(g * 0.025 + 0.5);
     double c = RB_TILE_LEN * (double)t;
     if (g < c - 20.0) { t--; c -= RB_TILE_LEN; }
     else if (g >= c + 20.0) { t++; c += RB_TILE_LEN; }
-    double rel = g - c;
-    idx = rb_trunc(rel / RB_TILE_LEN * 800.0 + 400.0);
+    const double rel = g - c;
+    double v = rel * 20.0 + 400.0;
+    if (fabs(v - rint(v)) < 1e-6) v = rel / RB_TILE_LEN * 800.0 + 400.0;
+    idx = rb_trunc(v);
 }
 
 // GridMap.index_to_distance gridmap.py:333-334 plus the tile centre.
@@ -137,6 +143,19 @@ __device__ __forceinline__ int rb_cell_tenths(const RbCtx &c, int p, int ux, int
     return c.pool[(size_t)t * RB_SUB_BYTES + (uy % RB_SUB) * RB_SUB + (ux % RB_SUB)];
 }
 
+// Read path split for memory-level parallelism: page-table slot and byte offset
+// of the cell under (gx, gy); sub = -1 outside the world.
+__device__ __forceinline__ void rb_locate(const RbCtx &c, double gx, double gy, int &sub, int &off)
+{
+    int tx, ty, ix, iy;
+    rb_read_axis(gx, tx, ix);
+    rb_read_axis(gy, ty, iy);
+    if (tx < -c.txh || tx > c.txh || ty < -c.tyh || ty > c.tyh) { sub = -1; off = 0; return; }
+    const int ux = 800 * (tx + c.txh) + ix, uy = 800 * (ty + c.tyh) + iy;
+    sub = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
+    off = (uy % RB_SUB) * RB_SUB + (ux % RB_SUB);
+}
+
 // HybridMap.get_odds_at hybridmap.py:85-93 in tenths (None -> 0).
 __device__ __forceinline__ int rb_odds_tenths(const RbCtx &c, int p, double gx, double gy)
 {
@@ -153,16 +172,15 @@ __device__ __forceinline__ bool rb_tile_exists(const RbCtx &c, unsigned long lon
     return (mask >> ((ty + c.tyh) * c.tiles_x + (tx + c.txh))) & 1ull;
 }
 
-// Write path, one axis: lattice cell k -> storage coordinate through the LUT
-// built on the host from int((k*0.05 - c)/0.05 + 400.0) (gridmap.py:92-95).
-// Returns -1 outside the world.
-__device__ __forceinline__ int rb_write_axis(const RbCtx &c, int k, int half_tiles)
+// Write path, one axis: lattice cell k -> packed storage location through the
+// LUT built on the host from int((k*0.05 - c)/0.05 + 400.0) (gridmap.py:92-95):
+// bits 0-7 offset in the sub-tile, 8-19 sub-tile index, 20-27 reference-tile
+// index along that axis.  RB_NONE outside the world.
+__device__ __forceinline__ uint32_t rb_write_lut(const uint32_t *__restrict__ lut, int k, int half_tiles)
 {
-    int q = k + 800 * c.lut_h + 400;
-    if (q < 0 || q >= 800 * (2 * c.lut_h + 1)) return -1;
-    int u = (int)__ldg(&c.lut[q]) - 800 * (c.lut_h - half_tiles);
-    if (u < 0 || u >= 800 * (2 * half_tiles + 1)) return -1;
-    return u;
+    const unsigned q = (unsigned)(k + 800 * half_tiles + 400);
+    if (q >= (unsigned)(800 * (2 * half_tiles + 1))) return RB_NONE;
+    return __ldg(&lut[q]);
 }
 
 // Philox4x32-10 (counter-based RNG) for device-side draws.

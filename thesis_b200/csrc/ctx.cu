@@ -21,7 +21,7 @@ struct rbpf_ctx {
     double *d_ranges_unused;
     double *d_px, *d_py, *d_dist;  // scan
     double *d_rot;                 // rotation table
-    uint16_t *d_lut;
+    uint32_t *d_lutx, *d_luty;
     double *d_z;                   // N*K*3 host-supplied normals
     double *d_u01;
     double *d_tile;                // 800*800 export buffer
@@ -68,7 +68,10 @@ extern "C" int32_t rbpf_rot_count(void) { return rot_count_host(); }
 // int((k*0.05 - c)/0.05 + 400.0) of GridMap.set_*_pos (gridmap.py:92-95) for the
 // tile that contains k*0.05 (hybridmap.py:44-45,193-208).  The float64 result is
 // one cell low for some k; negative indices wrap like ndarray[-1].
-static void build_lut(int h, std::vector<uint16_t> &lut)
+// Entries are packed for the ray-cast inner loop:
+//   bits 0-7 cell offset inside the sub-tile, bits 8-19 sub-tile index along the
+//   axis, bits 20-27 reference-tile index along the axis.
+static void build_lut(int h, std::vector<uint32_t> &lut)
 {
     const int n = 800 * (2 * h + 1);
     lut.resize(n);
@@ -87,7 +90,8 @@ static void build_lut(int h, std::vector<uint16_t> &lut)
         int idx = (int)(qd + 400.0);
         if (idx < 0) idx += RB_DIM;
         if (idx >= RB_DIM) idx = RB_DIM - 1;
-        lut[q] = (uint16_t)(800 * (t + h) + idx);
+        const int u = 800 * (t + h) + idx;
+        lut[q] = (uint32_t)(u % RB_SUB) | ((uint32_t)(u / RB_SUB) << 8) | ((uint32_t)(u / RB_DIM) << 20);
     }
 }
 
@@ -145,7 +149,6 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     d.subs_x = d.tiles_x * RB_SUBS_PER_TILE; d.subs_y = d.tiles_y * RB_SUBS_PER_TILE;
     d.nsub = d.subs_x * d.subs_y;
     d.ux_max = d.tiles_x * RB_DIM; d.uy_max = d.tiles_y * RB_DIM;
-    d.lut_h = d.txh > d.tyh ? d.txh : d.tyh;
     d.pool_tiles = cfg->pool_subtiles;
     d.seed = cfg->seed;
     d.step_no = 0;
@@ -166,7 +169,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(d.exists, N); A(d.exists2, N);
     A(h->d_px, RB_MAXB); A(h->d_py, RB_MAXB); A(h->d_dist, RB_MAXB);
     A(h->d_rot, 2 * (2 * d.nk + 1));
-    A(h->d_lut, 800 * (2 * d.lut_h + 1));
+    A(h->d_lutx, 800 * d.tiles_x);
+    A(h->d_luty, 800 * d.tiles_y);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4);
     A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N);
     A(d.stats, 1); A(d.flags, 1);
@@ -185,17 +189,20 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
     d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist;
     d.rot_cs = h->d_rot;
-    d.lut = h->d_lut;
+    d.lutx = h->d_lutx;
+    d.luty = h->d_luty;
 
     std::vector<double> rot(2 * (2 * d.nk + 1));
     for (int k = -d.nk; k <= d.nk; k++) {
         rot[2 * (k + d.nk)] = cos(k * d.rot_step);
         rot[2 * (k + d.nk) + 1] = sin(k * d.rot_step);
     }
-    std::vector<uint16_t> lut;
-    build_lut(d.lut_h, lut);
+    std::vector<uint32_t> lutx, luty;
+    build_lut(d.txh, lutx);
+    build_lut(d.tyh, luty);
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        cudaMemcpy(h->d_lutx, lutx.data(), lutx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_luty, luty.data(), luty.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "table upload failed");
     h->mg_n = h->mg_tiles = 0;
     cudaMemsetAsync(h->d_mg_mark, 0xFF, sizeof(uint32_t) * (size_t)d.pool_tiles, h->stream);

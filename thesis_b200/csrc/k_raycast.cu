@@ -20,13 +20,20 @@
 
 #define RC_WARPS 4
 
+// One beam's ray on the 0.05 m lattice, everything the per-cell closed form needs.
 struct Ray {
-    int ex, ey;      // end cell (lattice)
-    int len;         // number of cells (0 for the reference's empty-list quirk)
+    int ex, ey;      // end cell
+    int len;         // number of cells (0 for the reference's empty-list quirk, hybridmap.py:278-281)
     int occ;         // end cell is an obstacle (range <= 15 m)
 };
 
-// End cell and length of beam j for a particle at (x, y) with start cell (sx, sy).
+struct RayStep {     // derived per-beam constants (uniform across the warp)
+    int steep;       // major axis is y
+    int smaj, smin;  // signed unit steps along the major / minor axis
+    unsigned d2, D, D2;   // 2*minor extent, major extent, 2*major extent
+    float inv_D2;
+};
+
 __device__ __forceinline__ Ray ray_of_beam(const RbCtx &c, int j, double x, double y, double cs_, double sn_, int sx,
                                            int sy)
 {
@@ -53,24 +60,37 @@ __device__ __forceinline__ Ray ray_of_beam(const RbCtx &c, int j, double x, doub
     return r;
 }
 
-// n-th cell of the reference's integer Bresenham, closed form:
-// minor(n) = floor((2 n d + D) / (2 D)) with D = major extent, d = minor extent.
-__device__ __forceinline__ void ray_cell(int sx, int sy, const Ray &r, int n, int &kx, int &ky)
+__device__ __forceinline__ RayStep ray_step(int sx, int sy, const Ray &r)
 {
-    int dx = r.ex - sx, dy = r.ey - sy;
-    int adx = abs(dx), ady = abs(dy);
-    if (adx == 0) { kx = sx; ky = sy + n; return; }
-    if (ady == 0) { kx = sx + n; ky = sy; return; }
-    int xs = dx > 0 ? 1 : -1, ys = dy > 0 ? 1 : -1;
-    if (ady > adx) {
-        unsigned m = (2u * (unsigned)n * (unsigned)adx + (unsigned)ady) / (2u * (unsigned)ady);
-        kx = sx + xs * (int)m;
-        ky = sy + ys * n;
-    } else {
-        unsigned m = (2u * (unsigned)n * (unsigned)ady + (unsigned)adx) / (2u * (unsigned)adx);
-        kx = sx + xs * n;
-        ky = sy + ys * (int)m;
-    }
+    RayStep s;
+    const int dx = r.ex - sx, dy = r.ey - sy;
+    const int adx = abs(dx), ady = abs(dy);
+    // degenerate rays only ever step in the positive direction (range(y0, y1+1))
+    s.steep = ady > adx || adx == 0;
+    const int amaj = s.steep ? ady : adx, amin = s.steep ? adx : ady;
+    const int dmaj = s.steep ? dy : dx, dmin = s.steep ? dx : dy;
+    s.smaj = (adx == 0 || ady == 0) ? 1 : (dmaj > 0 ? 1 : -1);
+    s.smin = dmin > 0 ? 1 : (dmin < 0 ? -1 : 0);
+    s.D = (unsigned)max(amaj, 1);
+    s.D2 = 2u * s.D;
+    s.d2 = 2u * (unsigned)amin;
+    s.inv_D2 = 1.0f / (float)s.D2;
+    return s;
+}
+
+// n-th cell of the reference's integer Bresenham in closed form:
+// minor(n) = floor((2 n d + D) / (2 D)), D = major extent, d = minor extent.
+// The quotient comes from a float reciprocal (operands < 2^19) fixed up exactly.
+__device__ __forceinline__ void ray_cell(int sx, int sy, const RayStep &s, int n, int &kx, int &ky)
+{
+    const unsigned num = (unsigned)n * s.d2 + s.D;
+    unsigned m = __float2uint_rz(__uint2float_rz(num) * s.inv_D2);
+    int rem = (int)(num - m * s.D2);
+    if (rem < 0) { m--; rem += (int)s.D2; }
+    if (rem >= (int)s.D2) m++;
+    const int maj = s.smaj * n, mn = s.smin * (int)m;
+    kx = sx + (s.steep ? mn : maj);
+    ky = sy + (s.steep ? maj : mn);
 }
 
 __device__ __forceinline__ bool particle_frame(const RbCtx &c, int p, double &x, double &y, double &cs_, double &sn_,
@@ -112,22 +132,21 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
     // the sub-tiles of its two end cells and the two mixed corners (a segment
     // spans at most 2x2 sub-tiles because 33 < 160 and the LUT is monotone).
     for (int j = lane; j < c.B; j += 32) {
-        Ray r = ray_of_beam(c, j, x, y, cs_, sn_, sx, sy);
+        const Ray r = ray_of_beam(c, j, x, y, cs_, sn_, sx, sy);
+        const RayStep st = ray_step(sx, sy, r);
         for (int n0 = 0; n0 < r.len; n0 += 32) {
             int n1 = min(n0 + 31, r.len - 1), ax, ay, bx, by;
-            ray_cell(sx, sy, r, n0, ax, ay);
-            ray_cell(sx, sy, r, n1, bx, by);
-            int uax = rb_write_axis(c, ax, c.txh), uay = rb_write_axis(c, ay, c.tyh);
-            int ubx = rb_write_axis(c, bx, c.txh), uby = rb_write_axis(c, by, c.tyh);
-            int sax = uax < 0 ? -1 : uax / RB_SUB, say = uay < 0 ? -1 : uay / RB_SUB;
-            int sbx = ubx < 0 ? -1 : ubx / RB_SUB, sby = uby < 0 ? -1 : uby / RB_SUB;
-            // when one end is outside the world, cells of the segment inside the
-            // world still lie in the row/column of the inside end or up to the
-            // world border; mark the border sub-tile of that axis as well.
-            if (sax < 0) sax = ax < 0 ? 0 : c.subs_x - 1;
-            if (sbx < 0) sbx = bx < 0 ? 0 : c.subs_x - 1;
-            if (say < 0) say = ay < 0 ? 0 : c.subs_y - 1;
-            if (sby < 0) sby = by < 0 ? 0 : c.subs_y - 1;
+            ray_cell(sx, sy, st, n0, ax, ay);
+            ray_cell(sx, sy, st, n1, bx, by);
+            const uint32_t pax = rb_write_lut(c.lutx, ax, c.txh), pay = rb_write_lut(c.luty, ay, c.tyh);
+            const uint32_t pbx = rb_write_lut(c.lutx, bx, c.txh), pby = rb_write_lut(c.luty, by, c.tyh);
+            // when one end is outside the world, the cells of the segment that are
+            // inside still lie between the inside end and the world border: use the
+            // border sub-tile of that axis
+            int sax = pax == RB_NONE ? (ax < 0 ? 0 : c.subs_x - 1) : (int)((pax >> 8) & 0xfff);
+            int sbx = pbx == RB_NONE ? (bx < 0 ? 0 : c.subs_x - 1) : (int)((pbx >> 8) & 0xfff);
+            int say = pay == RB_NONE ? (ay < 0 ? 0 : c.subs_y - 1) : (int)((pay >> 8) & 0xfff);
+            int sby = pby == RB_NONE ? (by < 0 ? 0 : c.subs_y - 1) : (int)((pby >> 8) & 0xfff);
             int s0 = say * c.subs_x + sax, s1 = sby * c.subs_x + sbx, s2 = say * c.subs_x + sbx,
                 s3 = sby * c.subs_x + sax;
             atomicOr(&mask[s0 >> 5], 1u << (s0 & 31));
@@ -207,10 +226,13 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     int sx, sy;
     if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) return;
     const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-    unsigned long long ex_mask = c.exists[p], ex_new = 0ull;
-    unsigned long long dropped = 0;
+    const unsigned long long ex_mask = c.exists[p];
+    unsigned long long ex_new = 0ull;
+    unsigned dropped = 0;
     int cached_sub = -1;
     int8_t *cached_base = nullptr;
+    const uint32_t *__restrict__ lutx = c.lutx, *__restrict__ luty = c.luty;
+    const int txh = c.txh, tyh = c.tyh, subs_x = c.subs_x, tiles_x = c.tiles_x;
 
     for (int j0 = 0; j0 < c.B; j0 += 32) {
         Ray mine;
@@ -223,50 +245,51 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             r.ey = __shfl_sync(0xffffffffu, mine.ey, b);
             r.len = __shfl_sync(0xffffffffu, mine.len, b);
             r.occ = __shfl_sync(0xffffffffu, mine.occ, b);
+            if (r.len == 0) continue;
+            const RayStep st = ray_step(sx, sy, r);
             // reference tile of the end cell, for the "nearby" rule (hybridmap.py:141)
-            int uex = rb_write_axis(c, r.ex, c.txh), uey = rb_write_axis(c, r.ey, c.tyh);
+            const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
+            const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)((pey >> 20) * tiles_x + (pex >> 20));
+            const int n_last = r.len - 1, n_near = r.occ ? r.len - 2 : -1, n_occ = r.occ ? n_last : -1;
             for (int n0 = 0; n0 < r.len; n0 += 32) {
                 const int n = n0 + lane;
-                const bool active = n < r.len;
                 int ops = 0;
                 uint32_t id = 0xFFFFFFFFu;
                 int8_t *addr = nullptr;
-                if (active) {
+                if (n <= n_last) {
                     int kx, ky;
-                    ray_cell(sx, sy, r, n, kx, ky);
-                    int ux = rb_write_axis(c, kx, c.txh), uy = rb_write_axis(c, ky, c.tyh);
-                    if (ux < 0 || uy < 0) {
+                    ray_cell(sx, sy, st, n, kx, ky);
+                    const uint32_t px_ = rb_write_lut(lutx, kx, txh), py_ = rb_write_lut(luty, ky, tyh);
+                    if (px_ == RB_NONE || py_ == RB_NONE) {
                         dropped++;
                     } else {
-                        if (r.occ && n == r.len - 1) ops = 2;                       // hybridmap.py:137-138
-                        else ops = 1;                                               // hybridmap.py:144
-                        if (r.occ && n == r.len - 2 && uex >= 0 && uey >= 0 && ux / RB_DIM == uex / RB_DIM &&
-                            uy / RB_DIM == uey / RB_DIM)
-                            ops |= 4;                                               // hybridmap.py:139-142
-                        int sub = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
+                        const int tile = (int)((py_ >> 20) * tiles_x + (px_ >> 20));
+                        ops = n == n_occ ? 2 : 1;                                   // hybridmap.py:137-138 / :144
+                        if (n == n_near && tile == end_tile) ops |= 4;              // hybridmap.py:139-142
+                        const int sub = (int)((py_ >> 8) & 0xfff) * subs_x + (int)((px_ >> 8) & 0xfff);
                         if (sub != cached_sub) {
-                            uint32_t t = pt[sub];
+                            const uint32_t t = pt[sub];
                             cached_sub = sub;
                             cached_base = t == RB_NONE ? nullptr : c.pool + (size_t)t * RB_SUB_BYTES;
                         }
                         if (cached_base) {
-                            addr = cached_base + (uy % RB_SUB) * RB_SUB + (ux % RB_SUB);
-                            id = (uint32_t)uy * (uint32_t)c.ux_max + (uint32_t)ux;
+                            const uint32_t off = (py_ & 0xff) * RB_SUB + (px_ & 0xff);
+                            addr = cached_base + off;
+                            id = ((uint32_t)sub << 15) | off;                       // nsub <= 1600, off < 25600
                         } else {
                             ops = 0;                                                // cannot happen after prepare
                             atomicExch(&c.flags->world_overflow, 2);
                         }
-                        int tbit = (uy / RB_DIM) * c.tiles_x + ux / RB_DIM;          // HybridMapEntry allocation :125-131
-                        if (!((ex_mask >> tbit) & 1ull)) ex_new |= 1ull << tbit;
+                        if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;    // HybridMapEntry allocation :125-131
                     }
                 }
                 // two consecutive lattice cells can alias to one storage cell
                 // (SURVEY 3.4-2): the earlier lane applies both op sets in order.
-                uint32_t id_next = __shfl_down_sync(0xffffffffu, id, 1);
-                int ops_next = __shfl_down_sync(0xffffffffu, ops, 1);
-                uint32_t id_prev = __shfl_up_sync(0xffffffffu, id, 1);
-                bool dup_of_prev = lane > 0 && id != 0xFFFFFFFFu && id == id_prev;
-                bool absorbs_next = lane < 31 && id != 0xFFFFFFFFu && id == id_next;
+                const uint32_t id_next = __shfl_down_sync(0xffffffffu, id, 1);
+                const uint32_t id_prev = __shfl_up_sync(0xffffffffu, id, 1);
+                const int ops_next = __shfl_down_sync(0xffffffffu, ops, 1);
+                const bool dup_of_prev = lane > 0 && id != 0xFFFFFFFFu && id == id_prev;
+                const bool absorbs_next = lane < 31 && id != 0xFFFFFFFFu && id == id_next;
                 if (ops && !dup_of_prev) {
                     int t = *addr;
                     t = apply_ops(t, ops);
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     }
     if (lane == 0) {
         if (ex_new) c.exists[p] = ex_mask | ex_new;
-        if (dropped) atomicAdd(&c.stats->cells_dropped, dropped);
+        if (dropped) atomicAdd(&c.stats->cells_dropped, (unsigned long long)dropped);
     }
 }
 

@@ -87,13 +87,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32) weight_kernel(RbCtx c, const do
         // observation weight of this sample, robot.py:118-139
         double cs_ = cos(g2), sn_ = sin(g2);
         int S = 0;
-        for (int j = 0; j < c.B; j++) {
-            double d = c.dist[j];
-            if (d < RB_W_MAX_R && d > RB_W_MIN_R) {
-                double gx, gy;
-                rb_xform(cs_, sn_, g0, g1, c.px[j], c.py[j], gx, gy);
-                S += rb_odds_tenths(c, p, gx, gy);
+        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
+        // four beams in flight: locate (ALU) -> page-table entries -> cells
+        for (int j = 0; j < c.B; j += 4) {
+            int sub[4], off[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int jj = j + u;
+                sub[u] = -1; off[u] = 0;
+                if (jj < c.B) {
+                    const double d = c.dist[jj];
+                    if (d < RB_W_MAX_R && d > RB_W_MIN_R) {
+                        double gx, gy;
+                        rb_xform(cs_, sn_, g0, g1, c.px[jj], c.py[jj], gx, gy);
+                        rb_locate(c, gx, gy, sub[u], off[u]);
+                    }
+                }
             }
+            uint32_t t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = sub[u] >= 0 ? pt[sub[u]] : RB_NONE;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (t[u] != RB_NONE) S += c.pool[(size_t)t[u] * RB_SUB_BYTES + off[u]];
         }
         w = ((double)(10 + S) / 10.0) * pr;
     }
