@@ -70,7 +70,9 @@ extern "C" int32_t rbpf_rot_count(void) { return rot_count_host(); }
 // one cell low for some k; negative indices wrap like ndarray[-1].
 // Entries are packed for the ray-cast inner loop:
 //   bits 0-7 cell offset inside the sub-tile, bits 8-19 sub-tile index along the
-//   axis, bits 20-27 reference-tile index along the axis.
+//   axis, bits 20-27 reference-tile index along the axis, bit 28 / 29 = this
+//   lattice cell shares its storage cell with k+1 / k-1 (the aliasing the ray-cast
+//   has to apply in order).
 static void build_lut(int h, std::vector<uint32_t> &lut)
 {
     const int n = 800 * (2 * h + 1);
@@ -93,6 +95,8 @@ static void build_lut(int h, std::vector<uint32_t> &lut)
         const int u = 800 * (t + h) + idx;
         lut[q] = (uint32_t)(u % RB_SUB) | ((uint32_t)(u / RB_SUB) << 8) | ((uint32_t)(u / RB_DIM) << 20);
     }
+    for (int q = 0; q + 1 < n; q++)
+        if ((lut[q] & 0x0FFFFFFFu) == (lut[q + 1] & 0x0FFFFFFFu)) { lut[q] |= 1u << 28; lut[q + 1] |= 1u << 29; }
 }
 
 extern "C" const char *rbpf_last_error(rbpf_handle h) { return h ? h->err.c_str() : "null handle"; }

@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #define RC_WARPS 4
+#define RC_INFLIGHT 4       // chunks of 32 ray cells whose loads are issued together
 
 // One beam's ray on the 0.05 m lattice, everything the per-cell closed form needs.
 struct Ray {
@@ -216,8 +217,17 @@ __device__ __forceinline__ int apply_ops(int t, int ops)
     return t;
 }
 
+// Per-beam constants computed lane-parallel (one beam per lane) and broadcast.
+struct BeamPack {
+    int w0;          // len (bits 0-11) | occ << 12 | steep << 13 | (smaj + 1) << 14 | (smin + 1) << 16
+    int w1;          // D (bits 0-12) | step_q << 13        (D = major extent >= 1)
+    int w2;          // d2 (bits 0-13) | step_e << 14       (d2 = 2 * minor extent)
+    int end_tile;    // reference tile of the end cell (ty * tiles_x + tx) or -1
+};
+
 __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 {
+    const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * RC_WARPS + warp;
     if (p >= c.N) return;
@@ -235,75 +245,121 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     const int txh = c.txh, tyh = c.tyh, subs_x = c.subs_x, tiles_x = c.tiles_x;
 
     for (int j0 = 0; j0 < c.B; j0 += 32) {
-        Ray mine;
-        mine.ex = mine.ey = mine.len = mine.occ = 0;
-        if (j0 + lane < c.B) mine = ray_of_beam(c, j0 + lane, x, y, cs_, sn_, sx, sy);
+        BeamPack mine;
+        mine.w0 = 0; mine.w1 = 1; mine.w2 = 0; mine.end_tile = -1;
+        if (j0 + lane < c.B) {
+            const Ray r = ray_of_beam(c, j0 + lane, x, y, cs_, sn_, sx, sy);
+            const RayStep st = ray_step(sx, sy, r);
+            const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
+            mine.end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(((pey >> 20) & 0xff) * tiles_x + ((pex >> 20) & 0xff));
+            int len = r.len;
+            if (len > 4095 || st.D > 4095u) len = 0;               // cannot happen: rays are clipped at 15 m = 300 cells
+            // lanes advance 32 cells per chunk: minor += step_q (+1 on remainder overflow), e += step_e
+            const unsigned step_q = (32u * st.d2) / st.D2, step_e = 32u * st.d2 - step_q * st.D2;
+            mine.w0 = len | (r.occ << 12) | (st.steep << 13) | ((st.smaj + 1) << 14) | ((st.smin + 1) << 16);
+            mine.w1 = (int)(st.D | (step_q << 13));
+            mine.w2 = (int)(st.d2 | (step_e << 14));
+        }
         const int nb = min(32, c.B - j0);
         for (int b = 0; b < nb; b++) {
-            Ray r;
-            r.ex = __shfl_sync(0xffffffffu, mine.ex, b);
-            r.ey = __shfl_sync(0xffffffffu, mine.ey, b);
-            r.len = __shfl_sync(0xffffffffu, mine.len, b);
-            r.occ = __shfl_sync(0xffffffffu, mine.occ, b);
-            if (r.len == 0) continue;
-            const RayStep st = ray_step(sx, sy, r);
-            // reference tile of the end cell, for the "nearby" rule (hybridmap.py:141)
-            const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
-            const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)((pey >> 20) * tiles_x + (pex >> 20));
-            const int n_last = r.len - 1, n_near = r.occ ? r.len - 2 : -1, n_occ = r.occ ? n_last : -1;
-            for (int n0 = 0; n0 < r.len; n0 += 32) {
-                const int n = n0 + lane;
-                int ops = 0;
-                uint32_t id = 0xFFFFFFFFu;
-                int8_t *addr = nullptr;
-                if (n <= n_last) {
-                    int kx, ky;
-                    ray_cell(sx, sy, st, n, kx, ky);
-                    const uint32_t px_ = rb_write_lut(lutx, kx, txh), py_ = rb_write_lut(luty, ky, tyh);
-                    if (px_ == RB_NONE || py_ == RB_NONE) {
-                        dropped++;
-                    } else {
-                        const int tile = (int)((py_ >> 20) * tiles_x + (px_ >> 20));
-                        ops = n == n_occ ? 2 : 1;                                   // hybridmap.py:137-138 / :144
-                        if (n == n_near && tile == end_tile) ops |= 4;              // hybridmap.py:139-142
-                        const int sub = (int)((py_ >> 8) & 0xfff) * subs_x + (int)((px_ >> 8) & 0xfff);
-                        if (sub != cached_sub) {
-                            const uint32_t t = pt[sub];
-                            cached_sub = sub;
-                            cached_base = t == RB_NONE ? nullptr : c.pool + (size_t)t * RB_SUB_BYTES;
-                        }
-                        if (cached_base) {
-                            const uint32_t off = (py_ & 0xff) * RB_SUB + (px_ & 0xff);
-                            addr = cached_base + off;
-                            id = ((uint32_t)sub << 15) | off;                       // nsub <= 1600, off < 25600
+            const int w0 = __shfl_sync(FULL, mine.w0, b);
+            const int len = w0 & 0xfff;
+            if (len == 0) continue;                                 // hybridmap.py:278-281 empty list
+            const int w1 = __shfl_sync(FULL, mine.w1, b), w2 = __shfl_sync(FULL, mine.w2, b);
+            const int end_tile = __shfl_sync(FULL, mine.end_tile, b);
+            const int occ = (w0 >> 12) & 1, steep = (w0 >> 13) & 1;
+            const int smaj = ((w0 >> 14) & 3) - 1, smin = ((w0 >> 16) & 3) - 1;
+            const int D = w1 & 0x1fff, step_q = w1 >> 13, d2 = w2 & 0x3fff, step_e = w2 >> 14;
+            const int D2 = 2 * D;
+            const int n_occ = occ ? len - 1 : -1, n_near = occ ? len - 2 : -1;
+            const uint32_t *__restrict__ lmaj = steep ? luty : lutx, *__restrict__ lmin = steep ? lutx : luty;
+            const int hmaj = steep ? tyh : txh, hmin = steep ? txh : tyh;
+            // LUT bit that says "this lattice cell shares its storage cell with the
+            // next / previous cell of the ray along that axis" 
+            const int sh_maj_next = smaj > 0 ? 28 : 29, sh_maj_prev = smaj > 0 ? 29 : 28;
+            const int sh_min_next = smin > 0 ? 28 : 29, sh_min_prev = smin > 0 ? 29 : 28;
+            // state of cell n = lane (closed form), then +32 cells per chunk incrementally:
+            // minor(n) = floor((n*d2 + D) / D2), e = remainder
+            int n = lane, e, kmaj, kmin;
+            {
+                const unsigned num = (unsigned)lane * (unsigned)d2 + (unsigned)D;
+                unsigned m = __float2uint_rz(__uint2float_rz(num) * __frcp_rn((float)D2));
+                int rem = (int)(num - m * (unsigned)D2);
+                if (rem < 0) { m--; rem += D2; }
+                if (rem >= D2) { m++; rem -= D2; }
+                e = rem;
+                kmaj = (steep ? sy : sx) + smaj * lane;
+                kmin = (steep ? sx : sy) + smin * (int)m;
+            }
+            // Up to RC_INFLIGHT chunks (32 consecutive cells each) of the ray are in
+            // flight together: cells of one ray are distinct storage cells except for
+            // the aliasing pairs, which the earlier cell's lane applies in order.
+            for (int n0 = 0; n0 < len; n0 += 32 * RC_INFLIGHT) {
+                int ops[RC_INFLIGHT], t[RC_INFLIGHT];
+                int8_t *addr[RC_INFLIGHT];
+#pragma unroll
+                for (int u = 0; u < RC_INFLIGHT; u++) {
+                    ops[u] = 0; addr[u] = nullptr;
+                    if (n0 + 32 * u >= len) continue;               // warp-uniform
+                    if (n < len) {
+                        const uint32_t pmaj = rb_write_lut(lmaj, kmaj, hmaj), pmin = rb_write_lut(lmin, kmin, hmin);
+                        if (pmaj == RB_NONE || pmin == RB_NONE) {
+                            dropped++;
                         } else {
-                            ops = 0;                                                // cannot happen after prepare
-                            atomicExch(&c.flags->world_overflow, 2);
+                            const uint32_t px_ = steep ? pmin : pmaj, py_ = steep ? pmaj : pmin;
+                            const int sub = (int)((py_ >> 8) & 0xfff) * subs_x + (int)((px_ >> 8) & 0xfff);
+                            const int tile = (int)(((py_ >> 20) & 0xff) * tiles_x + ((px_ >> 20) & 0xff));
+                            if (sub != cached_sub) {
+                                const uint32_t tt = pt[sub];
+                                cached_sub = sub;
+                                cached_base = tt == RB_NONE ? nullptr : c.pool + (size_t)tt * RB_SUB_BYTES;
+                                if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;   // HybridMapEntry allocation :125-131
+                                if (!cached_base) atomicExch(&c.flags->world_overflow, 2);  // cannot happen after prepare
+                            }
+                            // does this cell share its storage cell with the previous / next ray cell?
+                            const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                            const bool alias_prev = n >= 1 && ((pmaj >> sh_maj_prev) & 1u) &&
+                                                    (!bump_prev || ((pmin >> sh_min_prev) & 1u));
+                            const bool alias_next = n + 1 < len && ((pmaj >> sh_maj_next) & 1u) &&
+                                                    (!bump_next || ((pmin >> sh_min_next) & 1u));
+                            if (cached_base && !alias_prev) {
+                                int o = n == n_occ ? 2 : 1;                                 // hybridmap.py:137-138 / :144
+                                if (n == n_near && tile == end_tile) o |= 4;                // hybridmap.py:139-142
+                                if (alias_next) {                                           // next cell's ops, applied after ours
+                                    int o2 = n + 1 == n_occ ? 2 : 1;
+                                    if (n + 1 == n_near && tile == end_tile) o2 |= 4;
+                                    o |= o2 << 3;
+                                }
+                                ops[u] = o;
+                                addr[u] = cached_base + (py_ & 0xff) * RB_SUB + (px_ & 0xff);
+                            }
                         }
-                        if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;    // HybridMapEntry allocation :125-131
                     }
+                    // advance this lane by 32 cells
+                    n += 32;
+                    kmaj += 32 * smaj;
+                    e += step_e;
+                    int dq = step_q;
+                    if (e >= D2) { e -= D2; dq++; }
+                    kmin += smin * dq;
                 }
-                // two consecutive lattice cells can alias to one storage cell
-                // (SURVEY 3.4-2): the earlier lane applies both op sets in order.
-                const uint32_t id_next = __shfl_down_sync(0xffffffffu, id, 1);
-                const uint32_t id_prev = __shfl_up_sync(0xffffffffu, id, 1);
-                const int ops_next = __shfl_down_sync(0xffffffffu, ops, 1);
-                const bool dup_of_prev = lane > 0 && id != 0xFFFFFFFFu && id == id_prev;
-                const bool absorbs_next = lane < 31 && id != 0xFFFFFFFFu && id == id_next;
-                if (ops && !dup_of_prev) {
-                    int t = *addr;
-                    t = apply_ops(t, ops);
-                    if (absorbs_next) t = apply_ops(t, ops_next);
-                    *addr = (int8_t)t;
-                }
-                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < RC_INFLIGHT; u++) t[u] = ops[u] ? (int)*addr[u] : 0;
+#pragma unroll
+                for (int u = 0; u < RC_INFLIGHT; u++)
+                    if (ops[u]) {
+                        int v = apply_ops(t[u], ops[u] & 7);
+                        if (ops[u] >> 3) v = apply_ops(v, ops[u] >> 3);
+                        if (v != t[u]) *addr[u] = (int8_t)v;        // saturated cells (most of a built map) are not rewritten
+                    }
+                __syncwarp();                                       // the next beam must see these stores
             }
         }
     }
     // publish newly created reference tiles and dropped-cell count
     for (int o = 16; o > 0; o >>= 1) {
-        ex_new |= __shfl_xor_sync(0xffffffffu, ex_new, o);
-        dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+        ex_new |= __shfl_xor_sync(FULL, ex_new, o);
+        dropped += __shfl_xor_sync(FULL, dropped, o);
     }
     if (lane == 0) {
         if (ex_new) c.exists[p] = ex_mask | ex_new;
