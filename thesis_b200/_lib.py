@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_librbpf.so")
+LIB_PATH = os.environ.get("RBPF_LIB", os.path.join(_HERE, "_librbpf.so"))   # RBPF_LIB: tuning variants built by build.py --variant
 
 RBPF_OK = 0
 RBPF_ERR_ARG, RBPF_ERR_CUDA, RBPF_ERR_POOL, RBPF_ERR_RESAMPLE, RBPF_ERR_WORLD = -1, -2, -3, -4, -5

@@ -29,15 +29,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants, e.g. build(defines=["RC_INFLIGHT=2"], out="_librbpf_if2.so")."""
+    target = os.path.join(HERE, out) if out else OUT
+    if not force and not out and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    cmd = ([NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", target])
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":

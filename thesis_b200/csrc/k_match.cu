@@ -35,11 +35,15 @@
 // result is identical to the exhaustive search of the oracle.
 #include "common.cuh"
 
+#ifndef MT_GROUP
 #define MT_GROUP 8                      // rotations per group
-#define MT_GRAD 5                       // dilation radius: ceil(MT_GROUP/2) cells of motion + 1 cell of rounding
-#define MT_MAXGROUPS 32
+#endif
+#define MT_GRAD (MT_GROUP / 2 + 1)      // dilation radius: MT_GROUP/2 cells of motion + 1 cell of rounding
+#define MT_MAXGROUPS 64
 #define MT_ROT_LINE_HALF 16             // rotation-variance support (oracle ROT_LINE_HALF)
+#ifndef MT_WARPS
 #define MT_WARPS 12
+#endif
 #define MT_THREADS (MT_WARPS * 32)
 #define MT_PLANES 9                     // bit-sliced counters up to 511 >= RB_MAXB
 
@@ -327,14 +331,14 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     }
     __syncthreads();
     if (warp == 0 && sh->ok) {                                              // rank the groups by decreasing bound
-        if (lane < ngroups) {
-            const int mine = sh->group_ub[lane];
+        for (int me = lane; me < ngroups; me += 32) {
+            const int mine = sh->group_ub[me];
             int rank = 0;
             for (int g = 0; g < ngroups; g++) {
                 const int o = sh->group_ub[g];
-                rank += (o > mine) || (o == mine && g < lane);
+                rank += (o > mine) || (o == mine && g < me);
             }
-            sh->group_order[rank] = lane;
+            sh->group_order[rank] = me;
         }
     }
     __syncthreads();
