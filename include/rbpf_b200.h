@@ -101,6 +101,11 @@ int rbpf_motion(rbpf_handle h, int32_t family, const double *u, double dt, const
  * HybridMap.get_scan_match (hybridmap.py:210-261) + eng.matchScanCustom
  * (matchScanCustom.m:1-58).  Results stay on the device (see getters). */
 int rbpf_scan_match(rbpf_handle h);
+/* Scan-to-previous-scan variant used on "adj" frames (main.py:156-159):
+ * HybridMap.get_scan_adj (hybridmap.py:147-191).  last_scan_xy = n_points global
+ * endpoints (x, y interleaved, host) of the previous scan, shared by all
+ * particles (main.py:168). */
+int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, int32_t n_points);
 
 /* Replaces the sampling/weighting half of Robot.map_update (robot.py:73-114):
  * proposal samples, _generate_sample_weight (robot.py:118-139), moments, weight

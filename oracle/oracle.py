@@ -59,6 +59,9 @@ def lib():
         L.orc_pose_range.argtypes = [_dp, _dp, _dp]
         L.orc_match.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double,
                                 _dp, _dp, _dp, _ip, _ip]
+        L.orc_match_adj.argtypes = [_dp, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double,
+                                    _dp, _dp, _dp, _ip, _ip]
+        L.orc_filter_map_update_adj.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int]
         L.orc_match_curr.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, _dp]
         L.orc_motion.argtypes = [C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.orc_resample.argtypes = [_dp, C.c_int, C.c_double, _ip]
@@ -169,6 +172,22 @@ class Map:
         return dict(valid=bool(valid), pose=pose, cov=cov.reshape(3, 3), score=score.value,
                     M=int(dbg[0]), best=(int(dbg[1]), int(dbg[2]), int(dbg[3])), nx=int(dbg[4]),
                     ny=int(dbg[5]), slice=sl.reshape(SLICE_W, SLICE_W))
+
+
+def match_adj(guess, scan, prev_xy, rx, ry):
+    """Scan-to-previous-scan matcher (hybridmap.py:147-191); prev_xy = [n, 2] global endpoints."""
+    prev = np.ascontiguousarray(prev_xy, dtype=np.float64)
+    px, py = np.ascontiguousarray(prev[:, 0]), np.ascontiguousarray(prev[:, 1])
+    pose = np.empty(3)
+    cov = np.empty(9)
+    score = C.c_double()
+    dbg = np.zeros(6, dtype=np.int32)
+    sl = np.zeros(SLICE_W * SLICE_W, dtype=np.int32)
+    valid = lib().orc_match_adj(_d(guess)[1], _d(scan.px)[1], _d(scan.py)[1], scan.B, _d(px)[1], _d(py)[1], len(px),
+                                rx, ry, _d(pose)[1], _d(cov)[1], C.byref(score), _i(dbg), _i(sl))
+    return dict(valid=bool(valid), pose=pose, cov=cov.reshape(3, 3), score=score.value, M=int(dbg[0]),
+                best=(int(dbg[1]), int(dbg[2]), int(dbg[3])), nx=int(dbg[4]), ny=int(dbg[5]),
+                slice=sl.reshape(SLICE_W, SLICE_W))
 
 
 def transform(pose, scan):
@@ -283,10 +302,15 @@ class Filter:
     def integrate(self):
         lib().orc_filter_integrate(self._h)
 
-    def map_update(self, z):
+    def map_update(self, z, prev_xy=None):
         z, zp = _d(z)
         assert z.size == self.N * self.K * 3
-        lib().orc_filter_map_update(self._h, zp)
+        if prev_xy is None:
+            lib().orc_filter_map_update(self._h, zp)
+        else:
+            prev = np.ascontiguousarray(prev_xy, dtype=np.float64)
+            px, py = np.ascontiguousarray(prev[:, 0]), np.ascontiguousarray(prev[:, 1])
+            lib().orc_filter_map_update_adj(self._h, zp, _d(px)[1], _d(py)[1], len(px))
 
     def resample(self, u01):
         anc = np.empty(self.N, dtype=np.int32)

@@ -525,12 +525,14 @@ int orc_match_curr(const orc_map *m, const double *guess, const double *px, cons
     return M;
 }
 
-int orc_match(const orc_map *m, const double *guess, const double *px, const double *py,
-              const double *dist, int B, double rx, double ry,
-              double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
+/* Shared search core.  Occupancy comes either from the particle's map (m != NULL,
+ * scan-to-map, hybridmap.py:210-261) or from the previous scan's endpoints
+ * rasterised on the same lattice (ref_x/ref_y, n_ref; scan-to-scan,
+ * hybridmap.py:147-191). */
+static int match_core(const orc_map *m, const double *ref_x, const double *ref_y, int n_ref,
+                      const double *guess, double *cx, double *cy, int M, double rx, double ry,
+                      double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
 {
-    double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
-    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
     /* cell of the guess position and the guess's offset inside it */
     int t0x = (int)floor(guess[0] / TILE_LEN + 0.5), t0y = (int)floor(guess[1] / TILE_LEN + 0.5);
     if (guess[0] < t0x * TILE_LEN - 20.0) t0x--; else if (guess[0] >= t0x * TILE_LEN + 20.0) t0x++;
@@ -548,10 +550,22 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
      * lands inside it (|c| < 11 m = 220 cells, +1 rounding, +14 shift) */
     enum { R = 240, S = 2 * R + 1 };
     unsigned char *win = (unsigned char *)malloc((size_t)S * S);
-    unsigned char *raw = (unsigned char *)malloc((size_t)(S + 2) * (S + 2));
-    for (int b = -R - 1; b <= R + 1; b++)
-        for (int a = -R - 1; a <= R + 1; a++)
-            raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+    unsigned char *raw = (unsigned char *)calloc((size_t)(S + 2) * (S + 2), 1);
+    if (m) {
+        for (int b = -R - 1; b <= R + 1; b++)
+            for (int a = -R - 1; a <= R + 1; a++)
+                raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+    } else {
+        /* previous-scan endpoints relative to the guess, |r| < 11 (hybridmap.py:170-171),
+         * rasterised like the curr points at rotation 0 */
+        for (int q = 0; q < n_ref; q++) {
+            double qx = ref_x[q] - guess[0], qy = ref_y[q] - guess[1];
+            if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;
+            int a = (int)floor((qx + fx) * 20.0), b = (int)floor((qy + fy) * 20.0);
+            if (abs(a) > R || abs(b) > R) continue;
+            raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = 1;
+        }
+    }
     /* 3x3 proximity kernel: a lookup cell counts when it or one of its 8
      * neighbours is occupied (stands in for the smoothed grid matchScansGrid
      * rasterises from the reference points) */
@@ -629,8 +643,42 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
         out_cov[8] = ((double)T2 / (double)T0 - mt * mt) * qt + qt / 12.0;
         *out_score = (double)bs;
     }
-    free(cx); free(cy); free(vol); free(bx); free(by);
+    free(vol); free(bx); free(by);
     return valid;
+}
+
+int orc_match(const orc_map *m, const double *guess, const double *px, const double *py,
+              const double *dist, int B, double rx, double ry,
+              double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
+{
+    double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
+    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
+    int v = match_core(m, NULL, NULL, 0, guess, cx, cy, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    free(cx); free(cy);
+    return v;
+}
+
+/* Scan-to-previous-scan variant, HybridMap.get_scan_adj hybridmap.py:147-191:
+ * curr = every beam endpoint at the guess minus the guess position (not snapped,
+ * no range gate), ref = previous scan's global endpoints minus the guess
+ * position, both kept when |.| < 11.0 (:171-172); same search contract. */
+int orc_match_adj(const double *guess, const double *px, const double *py, int B,
+                  const double *prev_x, const double *prev_y, int n_prev, double rx, double ry,
+                  double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
+{
+    double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
+    double c0 = cos(guess[2]), s0 = sin(guess[2]);
+    int M = 0;
+    for (int j = 0; j < B; j++) {
+        double gx, gy;
+        xform(c0, s0, guess[0], guess[1], px[j], py[j], &gx, &gy);
+        double qx = gx - guess[0], qy = gy - guess[1];
+        if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;
+        cx[M] = qx; cy[M] = qy; M++;
+    }
+    int v = match_core(NULL, prev_x, prev_y, n_prev, guess, cx, cy, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    free(cx); free(cy);
+    return v;
 }
 
 /* -------------------------------------------------------------- motion -- */
@@ -785,13 +833,15 @@ void orc_filter_integrate(orc_filter *f)
 }
 
 /* One particle of Robot.map_update robot.py:59-115 (scan-to-map branch), z = K*3 normals. */
-static void particle_map_update(orc_filter *f, int i, const double *z)
+static void particle_map_update(orc_filter *f, int i, const double *z, const double *prev_x, const double *prev_y,
+                                int n_prev)
 {
     double *pose = f->pose + 3 * i, *cov = f->cov + 9 * i;
     orc_map *m = f->map[i];
     double rx, ry, mp[3], mc[9], sc;
     orc_pose_range(cov, &rx, &ry);
-    int valid = orc_match(m, pose, f->px, f->py, f->dist, f->B, rx, ry, mp, mc, &sc, NULL, NULL);
+    int valid = prev_x ? orc_match_adj(pose, f->px, f->py, f->B, prev_x, prev_y, n_prev, rx, ry, mp, mc, &sc, NULL, NULL)  /* robot.py:66-67 */
+                       : orc_match(m, pose, f->px, f->py, f->dist, f->B, rx, ry, mp, mc, &sc, NULL, NULL);             /* robot.py:68-69 */
     f->valid[i] = valid;
     if (!valid) {                                                          /* :73-78 */
         double one = 1.0, w;
@@ -818,7 +868,15 @@ static void particle_map_update(orc_filter *f, int i, const double *z)
 void orc_filter_map_update(orc_filter *f, const double *z)
 {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i);
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, NULL, NULL, 0);
+}
+
+/* [p.map_update(scan, last_scan, True) for p in particles] main.py:159 : every
+ * particle matches against the same previous scan (global endpoints, main.py:168). */
+void orc_filter_map_update_adj(orc_filter *f, const double *z, const double *prev_x, const double *prev_y, int n_prev)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, prev_x, prev_y, n_prev);
 }
 
 /* particles = resample(particles) main.py:160 with Robot.copy robot.py:141-149. */

@@ -24,9 +24,14 @@ class _Engine:
         self.guess = None
         self.scan = None
         self.prange = None
+        self.prev_xy = None            # set on adj frames (hybridmap.py:147-191)
 
     def matchScanCustom(self, curr, ref, guess0, res, prange, nargout=3):
-        r = self.shadow.match(self.guess, self.scan, float(prange[0]), float(prange[1]))
+        if self.prev_xy is not None:
+            r = O.match_adj(self.guess, self.scan, self.prev_xy, float(prange[0]), float(prange[1]))
+            assert r["M"] == len(curr), "oracle and reference disagree on valid_curr_points"
+        else:
+            r = self.shadow.match(self.guess, self.scan, float(prange[0]), float(prange[1]))
         self.last = r
         corr = r["pose"] - self.guess
         return [list(corr)], r["cov"].tolist(), r["score"]
@@ -47,12 +52,13 @@ def make_ref_particles(n):
 
 
 def ref_map_update(robot, scan, last_scan, adj):
-    """robot.map_update with the seams patched (always scan-to-map, like the GPU path)."""
+    """robot.map_update with the MATLAB and multivariate_normal seams patched."""
     import models
 
     eng = robot._eng
     eng.guess = np.array([robot._x[-1], robot._y[-1], robot._theta[-1]], dtype=np.float64)
     eng.scan = O.Scan(scan.ranges(), scan.angles())
+    eng.prev_xy = np.column_stack((last_scan.x(), last_scan.y())) if adj else None
     orig = np.random.multivariate_normal
 
     def mvn(mean, cov, K):
@@ -62,7 +68,7 @@ def ref_map_update(robot, scan, last_scan, adj):
     np.random.multivariate_normal = mvn
     try:
         with contextlib.redirect_stdout(io.StringIO()):
-            robot.map_update(scan, last_scan, False)
+            robot.map_update(scan, last_scan, bool(adj))
     finally:
         np.random.multivariate_normal = orig
     robot._cov = np.array(robot._cov, dtype=np.float64)
@@ -158,12 +164,14 @@ class OracleParticles:
                 # the reference draws normals only for particles whose match is valid, in particle
                 # order; the oracle filter decides validity inside map_update, so pre-compute it
                 s = O.Scan(scan.ranges(), scan.angles())
+                prev = np.column_stack((last_scan.x(), last_scan.y())) if adj else None
                 z = np.zeros((f.N, f.K, 3))
                 for i in range(f.N):
                     rx, ry = O.pose_range(f.cov[i])
-                    if f.map(i).match(f.pose[i], s, rx, ry)["valid"]:
+                    r = O.match_adj(f.pose[i], s, prev, rx, ry) if adj else f.map(i).match(f.pose[i], s, rx, ry)
+                    if r["valid"]:
                         z[i] = np.random.standard_normal((f.K, 3))
-                f.map_update(z)
+                f.map_update(z, prev)
                 o.urounds += 1
             self.useen += 1
 

@@ -445,3 +445,36 @@ def test_fused_step_runs_and_conserves_pool(PS, golden):
     assert st["pool_in_use"] <= st["pool_subtiles"] and st["cells_dropped"] == 0
     assert np.isfinite(ps.poses).all() and np.isfinite(ps.weights).all()
     assert st["total_refs"] >= st["pool_in_use"] > 0
+
+
+def test_match_adj_against_oracle(PS, golden):
+    """Scan-to-previous-scan variant (hybridmap.py:147-191): same argmax, score,
+    validity, covariance as the oracle for every particle; unsnapped curr points,
+    occupancy = the previous scan rasterised on the lattice."""
+    N = 10
+    rng = np.random.default_rng(8)
+    ps = PS(N, 180, pool_subtiles=64)
+    prev_pose = np.array([0.5, 0.1, 0.2])
+    gx, gy = O.transform(prev_pose, oscan(golden, 3))
+    prev_xy = np.column_stack((gx, gy))
+    base = np.array([0.55, 0.12, -0.25])
+    poses = base + rng.normal(0, [0.1, 0.1, 0.05], (N, 3))
+    covs = np.zeros((N, 3, 3))
+    covs[:, 0, 0] = covs[:, 1, 1] = rng.uniform(0, 0.01, N) ** 2
+    covs[0] = np.diag([1.0, 1.0, 1.0])
+    ps.poses = poses
+    ps.covs = covs
+    s = oscan(golden, 4)
+    ps.set_scan(*scan_of(golden, 4))
+    ps.scan_match(prev_xy)
+    res = ps.match_result()
+    for i in range(N):
+        rx, ry = O.pose_range(covs[i])
+        o = O.match_adj(poses[i], s, prev_xy, rx, ry)
+        b = res["best"][i]
+        assert (int(b[0]), int(b[1]), int(b[2])) == o["best"], "particle %d" % i
+        assert int(b[3]) == o["M"] and bool(res["valid"][i]) == o["valid"] and res["score"][i] == o["score"]
+        assert np.array_equal(res["pose"][i], o["pose"])
+        if o["valid"]:
+            assert np.array_equal(res["cov"][i], o["cov"])
+    assert res["valid"].any()

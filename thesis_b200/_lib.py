@@ -44,6 +44,7 @@ SIGNATURES = {
     "rbpf_set_scan": (C.c_int, [_H, _dp, _dp, C.c_int32]),
     "rbpf_motion": (C.c_int, [_H, C.c_int32, _dp, C.c_double, _dp]),
     "rbpf_scan_match": (C.c_int, [_H]),
+    "rbpf_scan_match_adj": (C.c_int, [_H, _dp, C.c_int32]),
     "rbpf_weight": (C.c_int, [_H, _dp]),
     "rbpf_integrate": (C.c_int, [_H, C.c_int32]),
     "rbpf_resample": (C.c_int, [_H, _dp, _ip, _ip]),

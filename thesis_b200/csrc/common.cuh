@@ -80,6 +80,9 @@ struct RbCtx {
     double rot_step;
     double *m_pose, *m_cov, *m_score;
     int *m_valid, *m_best;
+    // scan-to-previous-scan matching (hybridmap.py:147-191): global endpoints of the previous scan
+    const double *prev_x, *prev_y;
+    int n_prev;
     // write-path LUT (lattice cell k -> storage coordinate)
     const uint32_t *lutx, *luty;            // per axis, packed: off | sub << 8 | tile << 20
     // resample
@@ -207,7 +210,7 @@ __device__ __forceinline__ double rb_u01(uint32_t hi, uint32_t lo)   // (0,1), 5
 
 // ---- launchers (one per kernel file) ----
 void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, const double *par, cudaStream_t s);
-void rb_launch_match(const RbCtx &c, cudaStream_t s);
+void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s);
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s);
 void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s);
 void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);

@@ -22,6 +22,8 @@ struct rbpf_ctx {
     double *d_px, *d_py, *d_dist;  // scan
     double *d_rot;                 // rotation table
     uint32_t *d_lutx, *d_luty;
+    double *d_prev;                // 2 * RB_MAXB: previous scan endpoints (x then y)
+    double *h_prev;                // pinned staging
     double *d_z;                   // N*K*3 host-supplied normals
     double *d_u01;
     double *d_tile;                // 800*800 export buffer
@@ -181,6 +183,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_z, N * d.K * 3);
     A(h->d_u01, 2);
     A(h->d_tile, RB_DIM * RB_DIM);
+    A(h->d_prev, 2 * RB_MAXB);
     A(h->d_slice, RB_SLICE_W * RB_SLICE_W);
     A(h->d_refstats, 2);
     A(h->d_mg_slots, 2 * N);
@@ -189,8 +192,10 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_mg_count, 4);
 #undef A
     if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    if (cudaMallocHost((void **)&h->h_scan, 3 * RB_MAXB * sizeof(double)) != cudaSuccess)
+    if (cudaMallocHost((void **)&h->h_scan, 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
+    h->h_prev = h->h_scan + 3 * RB_MAXB;
+    d.prev_x = h->d_prev; d.prev_y = h->d_prev + RB_MAXB; d.n_prev = 0;
     d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist;
     d.rot_cs = h->d_rot;
     d.lutx = h->d_lutx;
@@ -268,7 +273,23 @@ extern "C" int rbpf_scan_match(rbpf_handle h)
 {
     if (!h || !h->have_scan) { if (h) h->err = "scan_match: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
-    rb_launch_match(h->d, h->stream);
+    rb_launch_match(h->d, 0, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, int32_t n_points)
+{
+    if (!h || !h->have_scan || !last_scan_xy || n_points < 0 || n_points > RB_MAXB) {
+        if (h) h->err = "scan_match_adj: bad arguments";
+        return RBPF_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));                        // pinned staging reuse
+    for (int q = 0; q < n_points; q++) { h->h_prev[q] = last_scan_xy[2 * q]; h->h_prev[RB_MAXB + q] = last_scan_xy[2 * q + 1]; }
+    CK(cudaMemcpyAsync(h->d_prev, h->h_prev, 2 * RB_MAXB * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->d.n_prev = n_points;
+    rb_launch_match(h->d, 1, h->stream);
     CK(cudaGetLastError());
     return RBPF_OK;
 }
@@ -357,7 +378,7 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     int rc = rbpf_set_scan(h, ranges, angles, n_beams);
     if (rc) return rc;
     MARK(1);
-    rb_launch_match(h->d, h->stream);
+    rb_launch_match(h->d, 0, h->stream);
     MARK(2);
     rb_launch_weight(h->d, nullptr, 0, h->stream);
     MARK(3);

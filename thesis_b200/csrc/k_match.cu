@@ -174,7 +174,10 @@ __device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, co
     }
 }
 
-__global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out)
+// adj = 0: scan-to-map (HybridMap.get_scan_match hybridmap.py:210-261)
+// adj = 1: scan-to-previous-scan (HybridMap.get_scan_adj hybridmap.py:147-191): curr points are
+//          the unsnapped endpoints, occupancy is the previous scan rasterised on the lattice.
+__global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out, int adj)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm = smem;
@@ -224,9 +227,17 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     const unsigned long long exists = c.exists[p];
     for (int j = tid; j < c.B; j += MT_THREADS) {
         double d = c.dist[j];
-        if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) continue;
         double gx, gy;
         rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, c.px[j], c.py[j], gx, gy);
+        if (adj) {                                                         // hybridmap.py:165-172
+            const double ax = gx - sh->gx, ay = gy - sh->gy;
+            if (!(sqrt(ax * ax + ay * ay) < RB_MATCH_MAX_R)) continue;
+            const int slot = atomicAdd(&sh->M, 1);
+            ccx[slot] = ax;
+            ccy[slot] = ay;
+            continue;
+        }
+        if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) continue;
         int tx, ty, ix, iy;
         rb_read_axis(gx, tx, ix);
         rb_read_axis(gy, ty, iy);
@@ -239,7 +250,19 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     }
 
     // ---- 2. occupancy bitmap around the guess cell ---------------------------
-    {
+    if (adj) {
+        // previous scan rasterised relative to the guess cell, like curr points at rotation 0
+        for (int idx = tid; idx < RB_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
+        __syncthreads();
+        const int xb = sh->g0xu - sh->x0 + 32, yb = RB_WIN_R + 1;
+        for (int q = tid; q < c.n_prev; q += MT_THREADS) {
+            const double qx = c.prev_x[q] - sh->gx, qy = c.prev_y[q] - sh->gy;
+            if (!(sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R)) continue;     // hybridmap.py:171
+            const int a = __double2int_rd((qx + sh->fx) * 20.0) + xb, b = __double2int_rd((qy + sh->fy) * 20.0) + yb;
+            if (a < 0 || a >= 32 * RB_RAW_STRIDE || b < 0 || b >= RB_RAW_ROWS) continue;
+            atomicOr(&raw[b * RB_RAW_STRIDE + (a >> 5)], 1u << (a & 31));
+        }
+    } else {
         const int x0 = sh->x0, y0 = sh->y0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
         for (int idx = tid; idx < RB_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) {
@@ -497,10 +520,10 @@ static void match_set_attr()
     }
 }
 
-void rb_launch_match(const RbCtx &c, cudaStream_t s)
+void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)
 {
     match_set_attr();
-    match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr);
+    match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr, adj);
 }
 
 // Debug/test entry: re-run the matcher for one particle and dump the score slice
@@ -509,5 +532,5 @@ void rb_launch_match(const RbCtx &c, cudaStream_t s)
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s)
 {
     match_set_attr();
-    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev);
+    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev, 0);
 }

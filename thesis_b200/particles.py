@@ -85,8 +85,13 @@ class ParticleSet:
         p4[: len(par)] = par
         self._ck(self._lib.rbpf_motion(self._h, int(family), _d(u4)[1], float(dt), _d(p4)[1]))
 
-    def scan_match(self):
-        self._ck(self._lib.rbpf_scan_match(self._h))
+    def scan_match(self, last_scan_xy=None):
+        """Scan-to-map, or scan-to-previous-scan when last_scan_xy ([n, 2] global endpoints) is given."""
+        if last_scan_xy is None:
+            self._ck(self._lib.rbpf_scan_match(self._h))
+        else:
+            xy, p = _d(last_scan_xy)
+            self._ck(self._lib.rbpf_scan_match_adj(self._h, p, xy.shape[0]))
 
     def weight(self, z=None):
         if z is None:
@@ -393,7 +398,10 @@ class Robot:
                 raise RbpfError("map_update needs a Scan built from ranges (Lidar[i])")
             ps = sh.materialise(len(scan))
             ps.set_scan(scan.ranges(), scan.angles())
-            ps.scan_match()          # adj (scan-to-previous-scan, hybridmap.py:147-191) is a declared "next" row: scan-to-map is used
+            if adj:                  # robot.py:66-67 -> HybridMap.get_scan_adj hybridmap.py:147-191
+                ps.scan_match(np.column_stack((last_scan.x(), last_scan.y())))
+            else:                    # robot.py:68-69 -> HybridMap.get_scan_match hybridmap.py:210-261
+                ps.scan_match()
             if sh.rng == "numpy":
                 valid = ps.match_result()["valid"]
                 z = np.zeros((ps.N, ps.K, 3))
