@@ -31,6 +31,10 @@ UNIT = "updates/s"
 # compulsory cells of the matcher footprint for a 180-degree sweep,
 # (240/360) * pi * 11.7^2 / 0.0025 cells, 1 byte each (int8 tenths)
 MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
+# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch over 8,192 particles
+# (profiles/r1_full_8192p_final_raw.csv), per update; below the algorithmic figure because
+# particles that share sub-tiles after a resample hit in L2
+MATCH_DRAM_BYTES_PER_UPDATE_NCU = 165.5e6 / 8192
 
 
 def parse():
@@ -42,8 +46,8 @@ def parse():
     ap.add_argument("--particles", type=int, default=65536, help="total over all GPUs")
     ap.add_argument("--beams", type=int, default=360)
     ap.add_argument("--burnin", type=int, default=30, help="untimed scans before warm-up (particle divergence)")
-    ap.add_argument("--cpu-particles", type=int, default=0, help="CPU baseline sample (0 = 2 per core)")
-    ap.add_argument("--cpu-scans", type=int, default=3)
+    ap.add_argument("--cpu-particles", type=int, default=0, help="CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -94,7 +98,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(work, n_particles, n_scans, beams):
+def cpu_baseline(work, n_particles, max_seconds, beams):
     """The oracle (C port of the reference path, OpenMP over particles) on a
     bounded sample of the same workload.  Returns (updates/s, description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -102,7 +106,7 @@ def cpu_baseline(work, n_particles, n_scans, beams):
 
     cores = os.cpu_count() or 1
     if n_particles <= 0:
-        n_particles = 2 * cores
+        n_particles = 4 * cores
     f = O.Filter(n_particles, beams, 30)
     rng = np.random.default_rng(5)
     f.set_scan(work.ranges[0], work.angles)
@@ -114,11 +118,15 @@ def cpu_baseline(work, n_particles, n_scans, beams):
     f.map_update(rng.standard_normal((n_particles, 30, 3)))
     f.resample(float(rng.random()))
     t0 = time.perf_counter()
-    for s in range(2, 2 + n_scans):
+    n_scans = 0
+    for s in range(2, len(work.ranges)):
         f.motion(1, work.odom[s - 1], work.dt, work.par)
         f.set_scan(work.ranges[s], work.angles)
         f.map_update(rng.standard_normal((n_particles, 30, 3)))
         f.resample(float(rng.random()))
+        n_scans += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
     dt = time.perf_counter() - t0
     val = n_particles * n_scans / dt
     desc = "%d particles x %d scans of the same workload (%d beams), %.1f s" % (n_particles, n_scans, beams, dt)
@@ -135,7 +143,7 @@ def run_reference(args):
     from thesis_b200 import synth
 
     cores = os.cpu_count() or 1
-    n_cpu = args.cpu_particles if args.cpu_particles > 0 else 2 * cores
+    n_cpu = args.cpu_particles if args.cpu_particles > 0 else 8 * cores
     n_scans_total = 2 + args.warmup + args.steps
     work = synth.Workload(n_scans_total + 1, args.beams)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -294,16 +302,17 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(args.steps * 11),
+        "gpu_launches": int(args.steps * (11 if world == 1 else 19)),
         "roofline": {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": MATCH_DRAM_BYTES_PER_UPDATE_NCU * n_local,
+                     "traffic_source": "ncu --set full on an 8,192-particle launch, scaled per update", "peak_source": peak_src,
                      "algorithmic_bytes_per_update": MATCH_BYTES_PER_UPDATE, "updates_per_launch": n_local,
                      "launch_ms": match_ms,
                      "note": "the correlative search is shared-memory-lookup bound, not HBM bound; see DESIGN.md"},
         "stage_ms_per_step": {k: v / max(nst, 1) for k, v in stage_ms.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_scans, args.beams)
+        val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     print(json.dumps(line))
     if world > 1:
