@@ -209,6 +209,7 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from thesis_b200.dist import ShardedParticleSet
     n_local = args.particles // world

@@ -31,23 +31,34 @@ def owner_of(global_index, n_local):
 def plan_migration(ancestors, n_local, rank, world):
     """From the global ancestor vector derive, for this rank:
       send[r]  = sorted unique LOCAL slots whose particle rank r needs,
-      recv[r]  = (dst_slots, rec_index): local destination slots fed by rank r and,
-                 for each, the index into r's send list (== r's send[rank]).
-    Every rank computes both sides from the same vector, so sizes agree."""
-    ancestors = np.asarray(ancestors, dtype=np.int64)
-    send, recv = {}, {}
-    src_rank = ancestors // n_local
-    dst_rank = np.arange(len(ancestors)) // n_local
-    for r in range(world):
+      recv[r]  = (dst_slots, rec_index, n_records): local destination slots fed by
+                 rank r and, for each, the index into r's send list (== r's send[rank]).
+    Every rank computes both sides from the same vector, so sizes agree.  The
+    ancestor vector is non-decreasing (systematic resampling), so the slots fed by
+    this rank's particles form one contiguous interval: O(n_local) work."""
+    anc = np.asarray(ancestors, dtype=np.int64)
+    lo_id, hi_id = rank * n_local, (rank + 1) * n_local
+    empty = np.zeros(0, dtype=np.int32)
+    send = {r: empty for r in range(world) if r != rank}
+    recv = {r: (empty, empty, 0) for r in range(world) if r != rank}
+    # what leaves: global slots j whose ancestor is one of my particles and that live elsewhere
+    j0, j1 = np.searchsorted(anc, lo_id, "left"), np.searchsorted(anc, hi_id, "left")
+    if j1 > j0:
+        js = np.arange(j0, j1)
+        dst = js // n_local
+        for r in np.unique(dst):
+            if r != rank:
+                send[int(r)] = np.unique(anc[js[dst == r]] - lo_id).astype(np.int32)
+    # what arrives: my slots whose ancestor lives elsewhere
+    mine = anc[lo_id:hi_id]
+    src = mine // n_local
+    for r in np.unique(src):
         if r == rank:
             continue
-        m = (src_rank == rank) & (dst_rank == r)
-        send[r] = np.unique(ancestors[m] - rank * n_local).astype(np.int32)
-        m2 = (src_rank == r) & (dst_rank == rank)
-        dst_slots = (np.flatnonzero(m2) - rank * n_local).astype(np.int32)
-        needed = ancestors[m2] - r * n_local
+        m = src == r
+        needed = mine[m] - int(r) * n_local
         uniq = np.unique(needed)
-        recv[r] = (dst_slots, np.searchsorted(uniq, needed).astype(np.int32), len(uniq))
+        recv[int(r)] = (np.flatnonzero(m).astype(np.int32), np.searchsorted(uniq, needed).astype(np.int32), len(uniq))
     return send, recv
 
 
@@ -92,6 +103,9 @@ class MigratingSet(ParticleSet):
         send, recv = plan_migration(self._anc, self.N, self.rank, self.world)
         out = {}
         for r, slots in send.items():
+            if len(slots) == 0:                               # nothing for this peer: no device round trip
+                out[r] = (None, 0, 0)
+                continue
             nt, nbytes = C.c_int32(0), C.c_int64(0)
             self._ck(lib.rbpf_migrate_count(self._h, slots.ctypes.data_as(_ip), len(slots), C.byref(nt), C.byref(nbytes)))
             buf = torch.empty(int(nbytes.value) if len(slots) else 0, dtype=torch.uint8, device=self._dev)
