@@ -190,6 +190,7 @@ def workload_config(args, world):
         "workload": "configs[4]: synthetic 200 m x 200 m world, %d particles x %d-beam sweeps" % (args.particles, args.beams),
         "particles_total": args.particles, "particles_per_gpu": args.particles // world, "beams": args.beams,
         "samples_per_particle": 30, "cell_m": 0.05, "parallelism": "particles sharded x%d" % world,
+        "cell_dtype": "int8 log-odds tenths", "state_dtype": "f64 poses / covariances / weights",
         "l2_policy": "per-step working set (page tables + touched sub-tiles of all particles) exceeds the 126 MB L2; no flush",
     }
 
@@ -275,6 +276,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
     st = ps.stats()
+    if getattr(ps, "_prof", None):
+        print("rank %d resample phases (ms/step): %s  migrated particles/step %.1f, MB/step %.2f" % (
+            rank, {k: round(1e3 * v / ps._prof["n"], 3) for k, v in ps._prof.items() if k != "n"},
+            ps.migrated_particles / max(ps._prof["n"], 1), ps.migrated_bytes / 1e6 / max(ps._prof["n"], 1)), file=sys.stderr)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -293,7 +298,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u8 cells / f64 poses", "data": "synthetic",
+        "vs_baseline": None, "dtype": "i8", "data": "synthetic",
         "config": dict(workload_config(args, world), burnin_scans=args.burnin,
                        ray_cells_per_scan=a_r, pool_subtiles=pool,
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),

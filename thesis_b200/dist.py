@@ -16,6 +16,7 @@ particles; the one exchange step is resampling:
 what the gloo CPU tests exercise; the byte movement is torch.distributed.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -85,6 +86,16 @@ class MigratingSet(ParticleSet):
         self._anc = np.empty(self.n_global, dtype=np.int32)
         self.migrated_particles = 0
         self.migrated_bytes = 0
+        self._arena = {}                  # (kind, peer) -> persistent uint8 buffer, grown geometrically
+
+    def _buffer(self, kind, peer, nbytes):
+        """Persistent staging buffer: sizes change every step and a fresh torch.empty
+        of tens of MB can fall through to cudaMalloc (milliseconds)."""
+        buf = self._arena.get((kind, peer))
+        if buf is None or buf.numel() < nbytes:
+            buf = self._torch.empty(max(int(nbytes * 1.5), 1 << 20), dtype=self._torch.uint8, device=self._dev)
+            self._arena[(kind, peer)] = buf
+        return buf[:nbytes]
 
     def local_weights_tensor(self):
         return self._w_local
@@ -108,8 +119,8 @@ class MigratingSet(ParticleSet):
                 continue
             nt, nbytes = C.c_int32(0), C.c_int64(0)
             self._ck(lib.rbpf_migrate_count(self._h, slots.ctypes.data_as(_ip), len(slots), C.byref(nt), C.byref(nbytes)))
-            buf = torch.empty(int(nbytes.value) if len(slots) else 0, dtype=torch.uint8, device=self._dev)
-            self._ck(lib.rbpf_migrate_pack(self._h, buf.data_ptr() if len(slots) else 0))
+            buf = self._buffer("send", r, int(nbytes.value))
+            self._ck(lib.rbpf_migrate_pack(self._h, buf.data_ptr()))
             out[r] = (buf, len(slots), int(nt.value))
             self.migrated_particles += len(slots)
             self.migrated_bytes += buf.numel()
@@ -142,11 +153,22 @@ class ShardedParticleSet(MigratingSet):
         super().__init__(n_local, n_beams, dist.get_rank(group), dist.get_world_size(group), device=device, **kw)
         self._w_all = self._torch.empty(self.n_global, dtype=self._torch.float64, device=self._dev)
         self._tev = None
+        self._prof = {} if os.environ.get("RBPF_DIST_PROFILE") else None   # host-side phase timers (adds syncs)
 
     def resample(self, u01=None, want_ancestors=True):
+        import time
+
         torch, dist = self._torch, self._dist
+        prof = self._prof
+        t0 = time.perf_counter()
         dist.all_gather_into_tensor(self._w_all, self._w_local, group=self.group)
+        if prof is not None:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
         did, out, recv = self.pack_outgoing(self._w_all, u01)
+        if prof is not None:
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
         meta = torch.zeros((self.world, 2), dtype=torch.int64)
         for r, (_, n, nt) in out.items():
             meta[r, 0], meta[r, 1] = n, nt
@@ -160,7 +182,7 @@ class ShardedParticleSet(MigratingSet):
                 continue
             n_in, t_in = int(meta_in[r, 0]), int(meta_in[r, 1])
             if n_in:
-                buf = torch.empty(self.recv_bytes(n_in, t_in), dtype=torch.uint8, device=self._dev)
+                buf = self._buffer("recv", r, self.recv_bytes(n_in, t_in))
                 incoming[r] = (buf, n_in, t_in)
                 ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
             else:
@@ -170,7 +192,16 @@ class ShardedParticleSet(MigratingSet):
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if prof is not None:
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
         self.adopt_incoming(incoming, recv)
+        if prof is not None:
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            for k, v in (("allgather", t1 - t0), ("plan+pack", t2 - t1), ("exchange", t3 - t2), ("adopt", t4 - t3)):
+                prof[k] = prof.get(k, 0.0) + v
+            prof["n"] = prof.get("n", 0) + 1
         return did, (self._anc.copy() if want_ancestors else None)
 
     def step(self, ranges, angles):
@@ -195,6 +226,9 @@ class ShardedParticleSet(MigratingSet):
 
     def timing_enable(self, max_steps):
         self._tev = [] if max_steps > 0 else None
+        if self._prof is not None and max_steps > 0:
+            self._prof.clear()
+            self.migrated_particles = self.migrated_bytes = 0
 
     def timing_read(self):
         out = {k: 0.0 for k in self.STAGES}
