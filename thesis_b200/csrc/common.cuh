@@ -24,8 +24,24 @@
 #define RB_NT_MAX 14            // 0.7 m window clamp (robot.py:64-65) in cells
 
 // ---- device layout ----
-#define RB_SUB 160                          // cells per sub-tile side (divides 800; rows are 5 sectors)
+#define RB_SUB 160                          // cells per sub-tile side (divides 800)
 #define RB_SUB_BYTES (RB_SUB * RB_SUB)      // int8 tenths
+// Cells of a sub-tile are stored in blocks of 8 (x) by 4 (y) = one 32-byte sector,
+// 20 blocks per block row: a ray of 32 consecutive cells touches ~5 (along x) to
+// ~9 (along y) sectors instead of 1 to 32 with plain rows.
+#define RB_BLK_X 8
+#define RB_BLK_Y 4
+#define RB_BLKS_PER_ROW (RB_SUB / RB_BLK_X)  // 20
+// the two per-axis parts of a cell's byte offset add up to the offset
+#define RB_OFF_X(x) ((((x) >> 3) << 5) + ((x) & 7))
+#define RB_OFF_Y(y) (((y) >> 2) * (RB_BLKS_PER_ROW * 32) + (((y) & 3) << 3))
+// packed write-LUT entry: bits 0-14 offset part, 15-23 sub-tile index along the axis,
+// 24-29 reference-tile index along the axis, bit 30 / 31 = shares its storage cell with k+1 / k-1
+#define RB_LUT_OFF(p) ((p) & 0x7fffu)
+#define RB_LUT_SUB(p) (((p) >> 15) & 0x1ffu)
+#define RB_LUT_TILE(p) (((p) >> 24) & 0x3fu)
+#define RB_LUT_NEXT_BIT 30
+#define RB_LUT_PREV_BIT 31
 #define RB_SUBS_PER_TILE (RB_DIM / RB_SUB)  // 5
 #define RB_NONE 0xFFFFFFFFu                 // unallocated page-table entry (reads as log-odds 0)
 #define RB_MAXB 384                         // max beams per sweep
@@ -84,7 +100,7 @@ struct RbCtx {
     const double *prev_x, *prev_y;
     int n_prev;
     // write-path LUT (lattice cell k -> storage coordinate)
-    const uint32_t *lutx, *luty;            // per axis, packed: off | sub << 8 | tile << 20
+    const uint32_t *lutx, *luty;            // per axis, packed (RB_LUT_*)
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch
     int *ancestors;                         // n_global
@@ -143,7 +159,7 @@ __device__ __forceinline__ int rb_cell_tenths(const RbCtx &c, int p, int ux, int
     int sub = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
     uint32_t t = c.pt[(size_t)p * c.nsub + sub];
     if (t == RB_NONE) return 0;
-    return c.pool[(size_t)t * RB_SUB_BYTES + (uy % RB_SUB) * RB_SUB + (ux % RB_SUB)];
+    return c.pool[(size_t)t * RB_SUB_BYTES + RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB)];
 }
 
 // Read path split for memory-level parallelism: page-table slot and byte offset
@@ -156,7 +172,7 @@ __device__ __forceinline__ void rb_locate(const RbCtx &c, double gx, double gy, 
     if (tx < -c.txh || tx > c.txh || ty < -c.tyh || ty > c.tyh) { sub = -1; off = 0; return; }
     const int ux = 800 * (tx + c.txh) + ix, uy = 800 * (ty + c.tyh) + iy;
     sub = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
-    off = (uy % RB_SUB) * RB_SUB + (ux % RB_SUB);
+    off = RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB);
 }
 
 // HybridMap.get_odds_at hybridmap.py:85-93 in tenths (None -> 0).
@@ -176,9 +192,8 @@ __device__ __forceinline__ bool rb_tile_exists(const RbCtx &c, unsigned long lon
 }
 
 // Write path, one axis: lattice cell k -> packed storage location through the
-// LUT built on the host from int((k*0.05 - c)/0.05 + 400.0) (gridmap.py:92-95):
-// bits 0-7 offset in the sub-tile, 8-19 sub-tile index, 20-27 reference-tile
-// index along that axis.  RB_NONE outside the world.
+// LUT built on the host from int((k*0.05 - c)/0.05 + 400.0) (gridmap.py:92-95),
+// packed as RB_LUT_*.  RB_NONE outside the world.
 __device__ __forceinline__ uint32_t rb_write_lut(const uint32_t *__restrict__ lut, int k, int half_tiles)
 {
     const unsigned q = (unsigned)(k + 800 * half_tiles + 400);

@@ -71,11 +71,12 @@ extern "C" int32_t rbpf_rot_count(void) { return rot_count_host(); }
 // tile that contains k*0.05 (hybridmap.py:44-45,193-208).  The float64 result is
 // one cell low for some k; negative indices wrap like ndarray[-1].
 // Entries are packed for the ray-cast inner loop:
-//   bits 0-7 cell offset inside the sub-tile, bits 8-19 sub-tile index along the
-//   axis, bits 20-27 reference-tile index along the axis, bit 28 / 29 = this
-//   lattice cell shares its storage cell with k+1 / k-1 (the aliasing the ray-cast
-//   has to apply in order).
-static void build_lut(int h, std::vector<uint32_t> &lut)
+//   RB_LUT_OFF = this axis' part of the byte offset inside the sub-tile (blocked
+//   layout, RB_OFF_X / RB_OFF_Y), RB_LUT_SUB = sub-tile index along the axis,
+//   RB_LUT_TILE = reference-tile index along the axis, bits 30 / 31 = this lattice
+//   cell shares its storage cell with k+1 / k-1 (the aliasing the ray-cast has to
+//   apply in order).
+static void build_lut(int h, std::vector<uint32_t> &lut, bool y_axis)
 {
     const int n = 800 * (2 * h + 1);
     lut.resize(n);
@@ -95,10 +96,14 @@ static void build_lut(int h, std::vector<uint32_t> &lut)
         if (idx < 0) idx += RB_DIM;
         if (idx >= RB_DIM) idx = RB_DIM - 1;
         const int u = 800 * (t + h) + idx;
-        lut[q] = (uint32_t)(u % RB_SUB) | ((uint32_t)(u / RB_SUB) << 8) | ((uint32_t)(u / RB_DIM) << 20);
+        const int o = u % RB_SUB;
+        lut[q] = (uint32_t)(y_axis ? RB_OFF_Y(o) : RB_OFF_X(o)) | ((uint32_t)(u / RB_SUB) << 15) | ((uint32_t)(u / RB_DIM) << 24);
     }
     for (int q = 0; q + 1 < n; q++)
-        if ((lut[q] & 0x0FFFFFFFu) == (lut[q + 1] & 0x0FFFFFFFu)) { lut[q] |= 1u << 28; lut[q + 1] |= 1u << 29; }
+        if ((lut[q] & 0x3FFFFFFFu) == (lut[q + 1] & 0x3FFFFFFFu)) {
+            lut[q] |= 1u << RB_LUT_NEXT_BIT;
+            lut[q + 1] |= 1u << RB_LUT_PREV_BIT;
+        }
 }
 
 extern "C" const char *rbpf_last_error(rbpf_handle h) { return h ? h->err.c_str() : "null handle"; }
@@ -207,8 +212,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         rot[2 * (k + d.nk) + 1] = sin(k * d.rot_step);
     }
     std::vector<uint32_t> lutx, luty;
-    build_lut(d.txh, lutx);
-    build_lut(d.tyh, luty);
+    build_lut(d.txh, lutx, false);
+    build_lut(d.tyh, luty, true);
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_lutx, lutx.data(), lutx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_luty, luty.data(), luty.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)

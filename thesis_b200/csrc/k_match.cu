@@ -265,16 +265,23 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     } else {
         const int x0 = sh->x0, y0 = sh->y0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-        for (int idx = tid; idx < RB_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) {
-            const int rr = idx / RB_RAW_STRIDE, rw = idx - rr * RB_RAW_STRIDE;
+        // four consecutive lanes take the same word of four consecutive rows, so that
+        // together they consume whole 8x4-cell sectors
+        for (int it = tid; it < ((RB_RAW_ROWS + 3) / 4) * RB_RAW_STRIDE * 4; it += MT_THREADS) {
+            const int grp = it / (RB_RAW_STRIDE * 4), within = it - grp * (RB_RAW_STRIDE * 4);
+            const int rw = within >> 2, rr = 4 * grp + (within & 3);
+            if (rr >= RB_RAW_ROWS) continue;
+            const int idx = rr * RB_RAW_STRIDE + rw;
             const int uy = y0 - 1 + rr, ux = x0 - 32 + 32 * rw;
             uint32_t word = 0;
             if (uy >= 0 && uy < c.uy_max && ux >= 0 && ux < c.ux_max) {
                 const uint32_t t = pt[(uy / RB_SUB) * c.subs_x + ux / RB_SUB];
                 if (t != RB_NONE) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES +
-                                                                       (uy % RB_SUB) * RB_SUB + (ux % RB_SUB));
-                    const uint4 a = src[0], b = src[1];
+                    // 32 cells of one row = the same 8-byte row slice of four consecutive 8x4 blocks
+                    const uint2 *src = reinterpret_cast<const uint2 *>(c.pool + (size_t)t * RB_SUB_BYTES +
+                                                                       RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB));
+                    const uint2 q0 = src[0], q1 = src[4], q2 = src[8], q3 = src[12];
+                    const uint4 a = make_uint4(q0.x, q0.y, q1.x, q1.y), b = make_uint4(q2.x, q2.y, q3.x, q3.y);
                     word = mt_pack4(a.x) | (mt_pack4(a.y) << 4) | (mt_pack4(a.z) << 8) | (mt_pack4(a.w) << 12) |
                            (mt_pack4(b.x) << 16) | (mt_pack4(b.y) << 20) | (mt_pack4(b.z) << 24) |
                            (mt_pack4(b.w) << 28);

@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
             // when one end is outside the world, the cells of the segment that are
             // inside still lie between the inside end and the world border: use the
             // border sub-tile of that axis
-            int sax = pax == RB_NONE ? (ax < 0 ? 0 : c.subs_x - 1) : (int)((pax >> 8) & 0xfff);
-            int sbx = pbx == RB_NONE ? (bx < 0 ? 0 : c.subs_x - 1) : (int)((pbx >> 8) & 0xfff);
-            int say = pay == RB_NONE ? (ay < 0 ? 0 : c.subs_y - 1) : (int)((pay >> 8) & 0xfff);
-            int sby = pby == RB_NONE ? (by < 0 ? 0 : c.subs_y - 1) : (int)((pby >> 8) & 0xfff);
+            int sax = pax == RB_NONE ? (ax < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(pax);
+            int sbx = pbx == RB_NONE ? (bx < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(pbx);
+            int say = pay == RB_NONE ? (ay < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(pay);
+            int sby = pby == RB_NONE ? (by < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(pby);
             int s0 = say * c.subs_x + sax, s1 = sby * c.subs_x + sbx, s2 = say * c.subs_x + sbx,
                 s3 = sby * c.subs_x + sax;
             atomicOr(&mask[s0 >> 5], 1u << (s0 & 31));
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             const Ray r = ray_of_beam(c, j0 + lane, x, y, cs_, sn_, sx, sy);
             const RayStep st = ray_step(sx, sy, r);
             const uint32_t pex = RC_LUT(lutx, r.ex, txh), pey = RC_LUT(luty, r.ey, tyh);
-            mine.end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(((pey >> 20) & 0xff) * tiles_x + ((pex >> 20) & 0xff));
+            mine.end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(RB_LUT_TILE(pey) * tiles_x + RB_LUT_TILE(pex));
             int len = r.len;
             if (len > 4095 || st.D > 4095u) len = 0;               // cannot happen: rays are clipped at 15 m = 300 cells
             // lanes advance 32 cells per chunk: minor += step_q (+1 on remainder overflow), e += step_e
@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             const int hmaj = steep ? tyh : txh, hmin = steep ? txh : tyh;
             // LUT bit that says "this lattice cell shares its storage cell with the
             // next / previous cell of the ray along that axis" 
-            const int sh_maj_next = smaj > 0 ? 28 : 29, sh_maj_prev = smaj > 0 ? 29 : 28;
-            const int sh_min_next = smin > 0 ? 28 : 29, sh_min_prev = smin > 0 ? 29 : 28;
+            const int sh_maj_next = smaj > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT, sh_maj_prev = smaj > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT;
+            const int sh_min_next = smin > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT, sh_min_prev = smin > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT;
             // state of cell n = lane (closed form), then +32 cells per chunk incrementally:
             // minor(n) = floor((n*d2 + D) / D2), e = remainder
             int n = lane, e, kmaj, kmin;
@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                             dropped++;
                         } else {
                             const uint32_t px_ = steep ? pmin : pmaj, py_ = steep ? pmaj : pmin;
-                            const int sub = (int)((py_ >> 8) & 0xfff) * subs_x + (int)((px_ >> 8) & 0xfff);
-                            const int tile = (int)(((py_ >> 20) & 0xff) * tiles_x + ((px_ >> 20) & 0xff));
+                            const int sub = (int)RB_LUT_SUB(py_) * subs_x + (int)RB_LUT_SUB(px_);
+                            const int tile = (int)(RB_LUT_TILE(py_) * tiles_x + RB_LUT_TILE(px_));
                             if (sub != cached_sub) {
                                 const uint32_t tt = pt[sub];
                                 cached_sub = sub;
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                                     o |= o2 << 3;
                                 }
                                 ops[u] = o;
-                                addr[u] = cached_base + (py_ & 0xff) * RB_SUB + (px_ & 0xff);
+                                addr[u] = cached_base + RB_LUT_OFF(py_) + RB_LUT_OFF(px_);   // blocked layout: the two axis parts add up
                             }
                         }
                     }
