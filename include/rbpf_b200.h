@@ -79,6 +79,7 @@ typedef struct {
     uint64_t match_failed;    /* particle-scans whose match failed the isValidPose gate (cumulative) */
     uint64_t shared_refs;     /* page-table entries whose sub-tile is shared by >1 particle (snapshot) */
     uint64_t total_refs;      /* allocated page-table entries over all particles (snapshot) */
+    uint64_t refcount_sum;    /* sum of sub-tile reference counts (snapshot; must equal total_refs) */
     uint64_t match_evals;     /* bitmap scoring passes of the matcher (group bounds + member rotations; exhaustive = 231 per match) */
 } rbpf_stats_t;
 

@@ -190,7 +190,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_tile, RB_DIM * RB_DIM);
     A(h->d_prev, 2 * RB_MAXB);
     A(h->d_slice, RB_SLICE_W * RB_SLICE_W);
-    A(h->d_refstats, 2);
+    A(h->d_refstats, 4);
     A(h->d_mg_slots, 2 * N);
     A(h->d_mg_mark, d.pool_tiles);
     A(h->d_mg_list, d.pool_tiles);
@@ -533,7 +533,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     CK(cudaSetDevice(h->cfg.device));
     RbStats s;
     int fc = 0;
-    unsigned long long rs[2];
+    unsigned long long rs[3];
     rb_launch_refstats(h->d, h->d_refstats, h->stream);
     CK(cudaMemcpyAsync(&s, h->d.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&fc, h->d.free_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -548,6 +548,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_failed = s.match_failed;
     out->shared_refs = rs[0];
     out->total_refs = rs[1];
+    out->refcount_sum = rs[2];
     out->match_evals = s.match_evals;
     return RBPF_OK;
 }

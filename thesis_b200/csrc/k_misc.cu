@@ -46,7 +46,8 @@ void rb_launch_export_tile(const RbCtx &c, int particle, int tx, int ty, double 
     export_tile_kernel<<<(RB_DIM * RB_DIM + 255) / 256, 256, 0, s>>>(c, particle, tx, ty, out_dev);
 }
 
-// out[0] = page-table entries whose sub-tile is shared, out[1] = allocated entries.
+// out[0] = page-table entries whose sub-tile is shared, out[1] = allocated entries,
+// out[2] = sum of all reference counts (== out[1] when the pool accounting is intact).
 __global__ void refstats_kernel(RbCtx c, unsigned long long *out)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -61,11 +62,14 @@ __global__ void refstats_kernel(RbCtx c, unsigned long long *out)
         shared += __shfl_xor_sync(0xffffffffu, shared, o);
         total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], shared); atomicAdd(&out[1], total); }
+    unsigned long long rsum = 0;
+    for (size_t i = tid; i < c.pool_tiles; i += stride) rsum += c.refcnt[i];
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], shared); atomicAdd(&out[1], total); atomicAdd(&out[2], rsum); }
 }
 
 void rb_launch_refstats(const RbCtx &c, unsigned long long *out2_dev, cudaStream_t s)
 {
-    cudaMemsetAsync(out2_dev, 0, 2 * sizeof(unsigned long long), s);
+    cudaMemsetAsync(out2_dev, 0, 3 * sizeof(unsigned long long), s);
     refstats_kernel<<<512, 256, 0, s>>>(c, out2_dev);
 }

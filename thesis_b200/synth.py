@@ -122,3 +122,30 @@ class Workload:
     def ray_cells(self, i):
         """A_r of SURVEY 8d for scan i: cells written by the ray-cast."""
         return float(np.sum(np.minimum(self.ranges[i], 15.0) / CELL))
+
+
+def write_carmen_log(path, work, t0=100.0, dt=0.5, odom_per_scan=4):
+    """Write the workload as a CARMEN log (ODOM / FLASER lines) so that the
+    reference-style loaders (thesis_b200.loaders) and the headless main.py loop can
+    be exercised on logs that are not in the reference tree (aces.txt, fr.log, ...
+    are missing there, SURVEY 8c "data gaps").  Odometry = ground truth + the
+    workload's noise, interpolated odom_per_scan times between sweeps."""
+    odo = np.vstack(([0.0, 0.0, 0.0], np.cumsum(work.odom, axis=0)))
+    lines = []
+    for i in range(len(work.ranges)):
+        ts = t0 + i * dt
+        if i > 0:
+            for k in range(1, odom_per_scan + 1):
+                a = k / odom_per_scan
+                p = odo[i - 1] * (1 - a) + odo[i] * a
+                tk = t0 + (i - 1) * dt + a * dt - 1e-3
+                lines.append("ODOM %.6f %.6f %.6f 0 0 0 %.6f synth %.6f" % (p[0], p[1], p[2], tk, tk))
+        else:
+            lines.append("ODOM 0 0 0 0 0 0 %.6f synth %.6f" % (ts - 1e-3, ts - 1e-3))
+        r = " ".join("%.3f" % v for v in work.ranges[i])
+        p = odo[i]
+        lines.append("FLASER %d %s %.6f %.6f %.6f %.6f %.6f %.6f %.6f synth %.6f" % (
+            work.ranges.shape[1], r, p[0], p[1], p[2], p[0], p[1], p[2], ts, ts))
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return path
