@@ -561,7 +561,7 @@ static int match_core(const orc_map *m, const double *ref_x, const double *ref_y
         for (int q = 0; q < n_ref; q++) {
             double qx = ref_x[q] - guess[0], qy = ref_y[q] - guess[1];
             if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;
-            int a = (int)floor((qx + fx) * 20.0), b = (int)floor((qy + fy) * 20.0);
+            int a = (int)floor((qx + fx) * 20.0 + 0.5), b = (int)floor((qy + fy) * 20.0 + 0.5);
             if (abs(a) > R || abs(b) > R) continue;
             raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = 1;
         }
@@ -586,8 +586,11 @@ static int match_core(const orc_map *m, const double *ref_x, const double *ref_y
         for (int q = 0; q < M; q++) {
             double rxq = (ck * cx[q] - sk * cy[q]) + fx;
             double ryq = (sk * cx[q] + ck * cy[q]) + fy;
-            bx[q] = (int)floor(rxq * 20.0);      /* cell offsets from the guess cell */
-            by[q] = (int)floor(ryq * 20.0);
+            /* nearest lattice point: the curr points are cell corners (hybridmap.py:226-228), so at
+             * rotation 0 rxq*20 is an integer up to rounding noise -- flooring it would make the
+             * result depend on the last ulp of the guess */
+            bx[q] = (int)floor(rxq * 20.0 + 0.5);      /* cell offsets from the guess cell */
+            by[q] = (int)floor(ryq * 20.0 + 0.5);
             if (abs(bx[q]) + nx > R || abs(by[q]) + ny > R) { fprintf(stderr, "orc_match: window overflow\n"); abort(); }
         }
         for (int q = 0; q < M; q++)

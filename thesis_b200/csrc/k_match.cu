@@ -164,7 +164,7 @@ __device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, co
     for (int q = lane; q < M; q += 32) {
         double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
         double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
-        int ox = __double2int_rd(rxq * 20.0), oy = __double2int_rd(ryq * 20.0);
+        int ox = __double2int_rd(rxq * 20.0 + 0.5), oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
         int bx = ox + xoff, by = oy + yoff;
         if (bx < 0 || bx + span_i >= 32 * (RB_BM_STRIDE - 1) || by < 0 || by + span_j >= RB_BM_ROWS) {
             sh->overflow = 1;                                              // cannot happen for |c| < 11 m
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         for (int q = tid; q < c.n_prev; q += MT_THREADS) {
             const double qx = c.prev_x[q] - sh->gx, qy = c.prev_y[q] - sh->gy;
             if (!(sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R)) continue;     // hybridmap.py:171
-            const int a = __double2int_rd((qx + sh->fx) * 20.0) + xb, b = __double2int_rd((qy + sh->fy) * 20.0) + yb;
+            const int a = __double2int_rd((qx + sh->fx) * 20.0 + 0.5) + xb, b = __double2int_rd((qy + sh->fy) * 20.0 + 0.5) + yb;
             if (a < 0 || a >= 32 * RB_RAW_STRIDE || b < 0 || b >= RB_RAW_ROWS) continue;
             atomicOr(&raw[b * RB_RAW_STRIDE + (a >> 5)], 1u << (a & 31));
         }
