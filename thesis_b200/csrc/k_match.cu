@@ -107,14 +107,34 @@ __device__ __forceinline__ uint32_t mt_pack4(uint32_t bytes)
 
 // Accumulate the hit masks of all points of one rotation into bit-sliced
 // counters.  pts[q] = (word address << 5) | bit shift for row shift 0.
-__device__ __forceinline__ void mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
-                                              int lane_off, uint32_t pl[MT_PLANES])
+//
+// ABORT: every 64 points the best partial count of the warp is compared with
+// the best complete score found so far (best_key, shared): when even hitting all
+// remaining points cannot reach it, the pass is abandoned (returns false).  The
+// bound is admissible, so the search result is unchanged.
+template <bool ABORT>
+__device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
+                                              int lane_off, uint32_t pl[MT_PLANES], uint32_t rowmask = 0u,
+                                              const volatile unsigned long long *best_key = nullptr)
 {
     uint32_t ones = 0, twos = 0, fours = 0;
 #pragma unroll
     for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
     int q = 0;
     for (; q + 8 <= M; q += 8) {
+        if (ABORT && q && (q & 63) == 0) {
+            // bit-sliced max of the partial counts of this lane's row
+            uint32_t cand = rowmask;
+            int sc = 0;
+#pragma unroll
+            for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+                const uint32_t plane = pbit >= 3 ? pl[pbit] : (pbit == 2 ? fours : (pbit == 1 ? twos : ones));
+                const uint32_t t = cand & plane;
+                if (t) { cand = t; sc |= 1 << pbit; }
+            }
+            const int wmax = __reduce_max_sync(0xffffffffu, rowmask ? sc : 0);
+            if (wmax + (M - q) < (int)(*best_key >> 32)) return false;
+        }
         uint32_t h[8];
         const uint4 pa = *reinterpret_cast<const uint4 *>(pts + q);
         const uint4 pb = *reinterpret_cast<const uint4 *>(pts + q + 4);
@@ -144,6 +164,7 @@ __device__ __forceinline__ void mt_accumulate(const uint32_t *__restrict__ bm, c
 #pragma unroll
         for (int p = 0; p < MT_PLANES; p++) { uint32_t t = pl[p] & carry; pl[p] ^= carry; carry = t; }
     }
+    return true;
 }
 
 __device__ __forceinline__ int mt_decode(const uint32_t pl[MT_PLANES], int bit)
@@ -152,6 +173,25 @@ __device__ __forceinline__ int mt_decode(const uint32_t pl[MT_PLANES], int bit)
 #pragma unroll
     for (int p = 0; p < MT_PLANES; p++) s |= (int)((pl[p] >> bit) & 1u) << p;
     return s;
+}
+
+// Best key of one lane's row: bit-sliced max over the translation bits, then the
+// column closest to the window centre (negative side first), oracle match_key order.
+__device__ __forceinline__ unsigned long long mt_lane_key(const uint32_t pl[MT_PLANES], uint32_t colmask, int nx, int j, int k)
+{
+    uint32_t cand = colmask;
+    int sc = 0;
+#pragma unroll
+    for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+        uint32_t t = cand & pl[pbit];
+        if (t) { cand = t; sc |= 1 << pbit; }
+    }
+    uint32_t lowm = cand & ((2u << nx) - 1u);                                // bits 0..nx   (i <= 0)
+    uint32_t highm = cand >> nx;                                             // bit d = i = +d
+    int dn = lowm ? nx - (31 - __clz(lowm)) : 99;
+    int dp = highm ? __ffs(highm) - 1 : 99;
+    int i = dn <= dp ? -dn : dp;
+    return mt_key(sc, i, j, k);
 }
 
 // Rasterise the curr points for rotation k into packed bitmap addresses.
@@ -337,6 +377,28 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     const int lane_off = (lane < nrows ? lane : 0) * RB_BM_STRIDE;
     const int nrot = 2 * c.nk + 1, ngroups = (nrot + MT_GROUP - 1) / MT_GROUP;
 
+    // ---- 3a0. seed the best key with the MT_WARPS rotations around the guess ------
+    // (odometry is usually close: a strong bound lets the group passes below give up early)
+    const int seed_lo = -(MT_WARPS / 2), seed_hi = seed_lo + MT_WARPS - 1;
+    if (sh->ok && seed_lo + warp >= -c.nk && seed_lo + warp <= c.nk) {
+        const int k = seed_lo + warp;
+        mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+        __syncwarp();
+        uint32_t pl[MT_PLANES];
+        mt_accumulate<false>(bm, pts, M, lane_off, pl);
+        unsigned long long key = 0ull;
+        if (lane < nrows) key = mt_lane_key(pl, colmask, nx, lane - ny, k);
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            if (other > key) key = other;
+        }
+        if (lane == 0) {
+            atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
+            atomicAdd(&sh->evals, 1);
+        }
+    }
+    __syncthreads();
+
     // ---- 3a. upper bound of every rotation group --------------------------------
     if (sh->ok) {
         for (int g = warp; g < ngroups; g += MT_WARPS) {
@@ -345,7 +407,11 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
-            mt_accumulate(bmg, pts, M, lane_off, pl);
+            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key);
+            if (!done) {                                                    // even the bound cannot reach the seeded best
+                if (lane == 0) sh->group_ub[g] = -1;
+                continue;
+            }
             int sc = 0;
             if (lane < nrows) {
                 uint32_t cand = colmask;
@@ -385,6 +451,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             const int ridx = g * MT_GROUP + item % MT_GROUP;
             if (ridx >= nrot) continue;
             const int k = ridx - c.nk, ub = sh->group_ub[g];
+            if (k >= seed_lo && k <= seed_hi) continue;                     // scored as a seed
             const unsigned long long cur = *vbest;
             if (ub < (int)(cur >> 32)) break;                               // groups are sorted: nothing left can win
             if (mt_key(ub, 0, 0, k) < cur) continue;                        // this rotation cannot beat the best key
@@ -392,33 +459,16 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
-            mt_accumulate(bm, pts, M, lane_off, pl);
+            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest);
+            if (lane == 0) atomicAdd(&sh->evals, 1);
+            if (!done) continue;                                            // cannot reach the best score any more
             unsigned long long key = 0ull;
-            if (lane < nrows) {
-                // bit-sliced max over the ncols translation bits
-                uint32_t cand = colmask;
-                int sc = 0;
-#pragma unroll
-                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
-                    uint32_t t = cand & pl[pbit];
-                    if (t) { cand = t; sc |= 1 << pbit; }
-                }
-                // closest to the window centre, negative side first
-                uint32_t lowm = cand & ((2u << nx) - 1u);                    // bits 0..nx   (i <= 0)
-                uint32_t highm = cand >> nx;                                 // bit d = i = +d
-                int dn = lowm ? nx - (31 - __clz(lowm)) : 99;
-                int dp = highm ? __ffs(highm) - 1 : 99;
-                int i = dn <= dp ? -dn : dp;
-                key = mt_key(sc, i, lane - ny, k);
-            }
+            if (lane < nrows) key = mt_lane_key(pl, colmask, nx, lane - ny, k);
             for (int o = 16; o > 0; o >>= 1) {
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 if (other > key) key = other;
             }
-            if (lane == 0) {
-                atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
-                atomicAdd(&sh->evals, 1);
-            }
+            if (lane == 0) atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
         }
     }
     __syncthreads();
@@ -436,7 +486,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             mt_rasterise(c, sh, ccx, ccy, bk, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
-            mt_accumulate(bm, pts, M, lane_off, pl);
+            mt_accumulate<false>(bm, pts, M, lane_off, pl);
             long long W0 = 0, Wx = 0, Wy = 0, Wxx = 0, Wyy = 0, Wxy = 0;
             if (lane < nrows) {
                 const int j = lane - ny;
