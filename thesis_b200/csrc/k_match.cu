@@ -44,6 +44,9 @@
 #ifndef MT_WARPS
 #define MT_WARPS 12
 #endif
+#ifndef MT_ABORT_EVERY
+#define MT_ABORT_EVERY 64              // points between two abort checks of a scoring pass (power of two, multiple of 8)
+#endif
 #define MT_THREADS (MT_WARPS * 32)
 #define MT_PLANES 9                     // bit-sliced counters up to 511 >= RB_MAXB
 
@@ -122,7 +125,7 @@ __device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, c
     for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
     int q = 0;
     for (; q + 8 <= M; q += 8) {
-        if (ABORT && q && (q & 63) == 0) {
+        if (ABORT && q && (q & (MT_ABORT_EVERY - 1)) == 0) {
             // bit-sliced max of the partial counts of this lane's row
             uint32_t cand = rowmask;
             int sc = 0;
