@@ -115,7 +115,9 @@ class Workload:
             self.ranges[i] = np.clip(r, 0.0, MAX_RANGE)
         # world-frame velocity odometry with dt = 1 s (additive-velocity family)
         d = np.diff(self.truth, axis=0)
-        self.odom = d + rng.normal(0, [0.01, 0.01, 0.005], d.shape)
+        # noise well above the matcher lattice (0.05 m, 0.26 deg) so that the zero correction --
+        # which isValidPose rejects (matchScanCustom.m:55) -- is rarely the best match
+        self.odom = d + rng.normal(0, [0.03, 0.03, 0.02], d.shape)
         self.dt = 1.0
         self.par = VEL_PAR
 
