@@ -304,7 +304,8 @@ def run_b200(args):
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),
                        pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
                        match_scoring_passes_per_update=st["match_evals"] / max(1, n_local * (s - 1)),
-                       match_exhaustive_passes_per_update=231),
+                       match_exhaustive_passes_per_update=231,
+                       match_full_pass_equivalents_per_update=st["match_visits"] / max(1, st["match_points"])),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h)},

@@ -80,6 +80,8 @@ typedef struct {
     uint64_t shared_refs;     /* page-table entries whose sub-tile is shared by >1 particle (snapshot) */
     uint64_t total_refs;      /* allocated page-table entries over all particles (snapshot) */
     uint64_t refcount_sum;    /* sum of sub-tile reference counts (snapshot; must equal total_refs) */
+    uint64_t match_visits;    /* points visited by those passes (an aborted pass visits fewer than its points) */
+    uint64_t match_points;    /* matcher points summed over all matches (exhaustive search = 231 * match_points visits) */
     uint64_t match_evals;     /* bitmap scoring passes of the matcher (group bounds + member rotations; exhaustive = 231 per match) */
 } rbpf_stats_t;
 

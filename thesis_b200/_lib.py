@@ -28,7 +28,8 @@ class RbpfStats(C.Structure):
         ("pool_subtiles", C.c_uint32), ("pool_in_use", C.c_uint32), ("cow_copies", C.c_uint64),
         ("fresh_allocs", C.c_uint64), ("cells_dropped", C.c_uint64), ("resamples", C.c_uint64),
         ("match_failed", C.c_uint64), ("shared_refs", C.c_uint64), ("total_refs", C.c_uint64),
-        ("refcount_sum", C.c_uint64), ("match_evals", C.c_uint64),
+        ("refcount_sum", C.c_uint64), ("match_visits", C.c_uint64), ("match_points", C.c_uint64),
+        ("match_evals", C.c_uint64),
     ]
 
 

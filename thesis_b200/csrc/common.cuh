@@ -56,7 +56,7 @@
 #define RB_SLICE_W (2 * RB_NT_MAX + 1)      // 29
 
 struct RbStats {                            // device-side counters
-    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals;
+    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points;
 };
 
 struct RbFlags {                            // device-side status words

@@ -550,6 +550,8 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->total_refs = rs[1];
     out->refcount_sum = rs[2];
     out->match_evals = s.match_evals;
+    out->match_visits = s.match_visits;
+    out->match_points = s.match_points;
     return RBPF_OK;
 }
 

@@ -58,7 +58,8 @@ struct MatchShared {
     int group_ub[MT_MAXGROUPS];         // phase A: upper bound of every rotation group
     int group_order[MT_MAXGROUPS];      // groups by decreasing bound
     int next_item;                      // phase B work queue
-    int evals;                          // rotations actually scored (statistics)
+    int evals;                          // scoring passes started (statistics)
+    int visits;                         // points visited by those passes (an aborted pass visits fewer than M)
 };
 
 __host__ __device__ inline size_t mt_bm_words() { return ((size_t)RB_BM_ROWS * RB_BM_STRIDE + 3) & ~(size_t)3; }  // keeps raw/pts 16-B aligned
@@ -118,7 +119,8 @@ __device__ __forceinline__ uint32_t mt_pack4(uint32_t bytes)
 template <bool ABORT>
 __device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
                                               int lane_off, uint32_t pl[MT_PLANES], uint32_t rowmask = 0u,
-                                              const volatile unsigned long long *best_key = nullptr)
+                                              const volatile unsigned long long *best_key = nullptr,
+                                              int *visited = nullptr)
 {
     uint32_t ones = 0, twos = 0, fours = 0;
 #pragma unroll
@@ -136,7 +138,10 @@ __device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, c
                 if (t) { cand = t; sc |= 1 << pbit; }
             }
             const int wmax = __reduce_max_sync(0xffffffffu, rowmask ? sc : 0);
-            if (wmax + (M - q) < (int)(*best_key >> 32)) return false;
+            if (wmax + (M - q) < (int)(*best_key >> 32)) {
+                if (visited) *visited += q;
+                return false;
+            }
         }
         uint32_t h[8];
         const uint4 pa = *reinterpret_cast<const uint4 *>(pts + q);
@@ -167,6 +172,7 @@ __device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, c
 #pragma unroll
         for (int p = 0; p < MT_PLANES; p++) { uint32_t t = pl[p] & carry; pl[p] ^= carry; carry = t; }
     }
+    if (visited) *visited += M;
     return true;
 }
 
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         sh->best_key = 0ull;
         sh->next_item = 0;
         sh->evals = 0;
+        sh->visits = 0;
 #pragma unroll
         for (int q = 0; q < 9; q++) sh->mom[q] = 0;
     }
@@ -383,12 +390,13 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     // ---- 3a0. seed the best key with the MT_WARPS rotations around the guess ------
     // (odometry is usually close: a strong bound lets the group passes below give up early)
     const int seed_lo = -(MT_WARPS / 2), seed_hi = seed_lo + MT_WARPS - 1;
+    int visited = 0;                                                        // per warp (all lanes count alike)
     if (sh->ok && seed_lo + warp >= -c.nk && seed_lo + warp <= c.nk) {
         const int k = seed_lo + warp;
         mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
         __syncwarp();
         uint32_t pl[MT_PLANES];
-        mt_accumulate<false>(bm, pts, M, lane_off, pl);
+        mt_accumulate<false>(bm, pts, M, lane_off, pl, 0u, nullptr, &visited);
         unsigned long long key = 0ull;
         if (lane < nrows) key = mt_lane_key(pl, colmask, nx, lane - ny, k);
         for (int o = 16; o > 0; o >>= 1) {
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key);
+            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key, &visited);
             if (!done) {                                                    // even the bound cannot reach the seeded best
                 if (lane == 0) sh->group_ub[g] = -1;
                 continue;
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
             __syncwarp();
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest);
+            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest, &visited);
             if (lane == 0) atomicAdd(&sh->evals, 1);
             if (!done) continue;                                            // cannot reach the best score any more
             unsigned long long key = 0ull;
@@ -475,6 +483,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         }
     }
     __syncthreads();
+    if (lane == 0 && visited) atomicAdd(&sh->visits, visited);
     int bs, bi, bj, bk;
     mt_key_decode(sh->best_key, bs, bi, bj, bk);
     if (!sh->ok) { bs = 0; bi = bj = bk = 0; }
@@ -550,7 +559,11 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         ob[0] = bi; ob[1] = bj; ob[2] = bk; ob[3] = M;
         c.m_valid[p] = valid ? 1 : 0;
         if (sh->overflow) atomicExch(&c.flags->world_overflow, 1);
-        if (!slice_out) atomicAdd(&c.stats->match_evals, (unsigned long long)(sh->evals + ngroups));
+        if (!slice_out) {
+            atomicAdd(&c.stats->match_evals, (unsigned long long)(sh->evals + ngroups));
+            atomicAdd(&c.stats->match_visits, (unsigned long long)sh->visits);
+            atomicAdd(&c.stats->match_points, (unsigned long long)M);
+        }
         if (!valid) {                                                       // matchScanCustom.m:26-28
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             for (int q = 0; q < 9; q++) oc[q] = nan;
