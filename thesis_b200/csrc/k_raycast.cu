@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             if (len > 4095 || st.D > 4095u) len = 0;               // cannot happen: rays are clipped at 15 m = 300 cells
             // lanes advance 32 cells per chunk: minor += step_q (+1 on remainder overflow), e += step_e
             const unsigned step_q = (32u * st.d2) / st.D2, step_e = 32u * st.d2 - step_q * st.D2;
-            mine.w0 = len | (r.occ << 12) | (st.steep << 13) | ((st.smaj + 1) << 14) | ((st.smin + 1) << 16);
+            // start and end cell inside the world => every cell of the ray is (bounding box)
+            const int inside = pex != RB_NONE && pey != RB_NONE && RC_LUT(lutx, sx, txh) != RB_NONE && RC_LUT(luty, sy, tyh) != RB_NONE;
+            mine.w0 = len | (r.occ << 12) | (st.steep << 13) | ((st.smaj + 1) << 14) | ((st.smin + 1) << 16) | (inside << 18);
             mine.w1 = (int)(st.D | (step_q << 13));
             mine.w2 = (int)(st.d2 | (step_e << 14));
         }
@@ -320,7 +322,62 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             // Up to RC_INFLIGHT chunks (32 consecutive cells each) of the ray are in
             // flight together: cells of one ray are distinct storage cells except for
             // the aliasing pairs, which the earlier cell's lane applies in order.
-            for (int n0 = 0; n0 < len; n0 += 32 * RC_INFLIGHT) {
+            int n0 = 0;
+            // Fast path: chunks whose 32 cells all have n <= len - 4 are plain "empty"
+            // updates (-0.3, floor -3.0) whose successor is one too; no lane is idle, no
+            // end/nearby handling, no world-border checks.
+            if ((w0 >> 18) & 1) {
+                const uint32_t *__restrict__ fmaj = lmaj + (800 * hmaj + 400), *__restrict__ fmin = lmin + (800 * hmin + 400);
+                while (n0 + 32 <= len - 3) {
+                    const int nch = min(RC_INFLIGHT, (len - 3 - n0) >> 5);
+                    int8_t *addr[RC_INFLIGHT];
+                    int dec[RC_INFLIGHT], t[RC_INFLIGHT];
+#pragma unroll
+                    for (int u = 0; u < RC_INFLIGHT; u++) {
+                        addr[u] = nullptr; dec[u] = 0;
+                        if (u >= nch) continue;                          // warp-uniform
+                        const uint32_t pmaj = __ldg(&fmaj[kmaj]), pmin = __ldg(&fmin[kmin]);
+                        const uint32_t px_ = steep ? pmin : pmaj, py_ = steep ? pmaj : pmin;
+                        const int sub = (int)RB_LUT_SUB(py_) * subs_x + (int)RB_LUT_SUB(px_);
+                        if (sub != cached_sub) {
+                            const uint32_t tt = pt[sub];
+                            cached_sub = sub;
+                            cached_base = tt == RB_NONE ? nullptr : c.pool + (size_t)tt * RB_SUB_BYTES;
+                            const int tile = (int)(RB_LUT_TILE(py_) * tiles_x + RB_LUT_TILE(px_));
+                            if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;
+                            if (!cached_base) atomicExch(&c.flags->world_overflow, 2);
+                        }
+                        int d_ = RB_T_EMP;
+                        bool skip = false;
+                        if (pmaj >> RB_LUT_NEXT_BIT) {                      // rare: an aliasing pair along the major axis
+                            const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                            skip = n >= 1 && ((pmaj >> sh_maj_prev) & 1u) && (!bump_prev || ((pmin >> sh_min_prev) & 1u));
+                            if (((pmaj >> sh_maj_next) & 1u) && (!bump_next || ((pmin >> sh_min_next) & 1u))) d_ = 2 * RB_T_EMP;
+                        }
+                        if (cached_base && !skip) {
+                            addr[u] = cached_base + RB_LUT_OFF(py_) + RB_LUT_OFF(px_);
+                            dec[u] = d_;
+                        }
+                        n += 32;
+                        kmaj += 32 * smaj;
+                        e += step_e;
+                        int dq = step_q;
+                        if (e >= D2) { e -= D2; dq++; }
+                        kmin += smin * dq;
+                    }
+#pragma unroll
+                    for (int u = 0; u < RC_INFLIGHT; u++) t[u] = addr[u] ? (int)*addr[u] : 0;
+#pragma unroll
+                    for (int u = 0; u < RC_INFLIGHT; u++)
+                        if (addr[u]) {
+                            const int v = max(t[u] - dec[u], -RB_T_MAX);
+                            if (v != t[u]) *addr[u] = (int8_t)v;
+                        }
+                    __syncwarp();
+                    n0 += 32 * nch;
+                }
+            }
+            for (; n0 < len; n0 += 32 * RC_INFLIGHT) {
                 int ops[RC_INFLIGHT], t[RC_INFLIGHT];
                 int8_t *addr[RC_INFLIGHT];
 #pragma unroll
