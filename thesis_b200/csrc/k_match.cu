@@ -44,6 +44,9 @@
 #ifndef MT_WARPS
 #define MT_WARPS 12
 #endif
+#ifndef MT_SEEDS
+#define MT_SEEDS 8                      // rotations around the guess scored first (by as many warps)
+#endif
 #ifndef MT_ABORT_EVERY
 #define MT_ABORT_EVERY 64              // points between two abort checks of a scoring pass (power of two, multiple of 8)
 #endif
@@ -57,6 +60,7 @@ struct MatchShared {
     long long mom[9];                   // W0 Wx Wy Wxx Wyy Wxy T0 T1 T2
     int group_ub[MT_MAXGROUPS];         // phase A: upper bound of every rotation group
     int group_order[MT_MAXGROUPS];      // groups by decreasing bound
+    int next_group;                     // phase A work queue
     int next_item;                      // phase B work queue
     int evals;                          // scoring passes started (statistics)
     int visits;                         // points visited by those passes (an aborted pass visits fewer than M)
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         sh->overflow = 0;
         sh->best_key = 0ull;
         sh->next_item = 0;
+        sh->next_group = 0;
         sh->evals = 0;
         sh->visits = 0;
 #pragma unroll
@@ -387,11 +392,12 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     const int lane_off = (lane < nrows ? lane : 0) * RB_BM_STRIDE;
     const int nrot = 2 * c.nk + 1, ngroups = (nrot + MT_GROUP - 1) / MT_GROUP;
 
-    // ---- 3a0. seed the best key with the MT_WARPS rotations around the guess ------
-    // (odometry is usually close: a strong bound lets the group passes below give up early)
-    const int seed_lo = -(MT_WARPS / 2), seed_hi = seed_lo + MT_WARPS - 1;
+    // ---- 3a0. seed the best key with MT_SEEDS rotations around the guess ---------
+    // (odometry is usually close: a strong bound lets the group passes below give up
+    // early).  The other warps start on the group bounds right away.
+    const int seed_lo = -(MT_SEEDS / 2), seed_hi = seed_lo + MT_SEEDS - 1;
     int visited = 0;                                                        // per warp (all lanes count alike)
-    if (sh->ok && seed_lo + warp >= -c.nk && seed_lo + warp <= c.nk) {
+    if (sh->ok && warp < MT_SEEDS && seed_lo + warp >= -c.nk && seed_lo + warp <= c.nk) {
         const int k = seed_lo + warp;
         mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
         __syncwarp();
@@ -408,11 +414,14 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             atomicAdd(&sh->evals, 1);
         }
     }
-    __syncthreads();
 
-    // ---- 3a. upper bound of every rotation group --------------------------------
+    // ---- 3a. upper bound of every rotation group (shared queue) -------------------
     if (sh->ok) {
-        for (int g = warp; g < ngroups; g += MT_WARPS) {
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&sh->next_group, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= ngroups) break;
             const int kmid = min(g * MT_GROUP + MT_GROUP / 2, nrot - 1) - c.nk;
             __syncwarp();
             mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
