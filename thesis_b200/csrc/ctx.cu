@@ -29,7 +29,9 @@ struct rbpf_ctx {
     double *d_tile;                // 800*800 export buffer
     int *d_slice;                  // 29*29 debug slice
     unsigned long long *d_refstats;
-    double *h_scan;                // pinned staging: px, py, dist
+    double *h_scan;                // pinned staging: 2 slots x (px, py, dist | prev x, prev y), used alternately
+    cudaEvent_t stage_ev[2];       // "the copies out of slot i have completed"
+    int stage_slot;
     int have_scan;
     // optional per-stage CUDA-event timing of rbpf_step
     int *d_mg_slots;               // 2*N staging ints (migration)
@@ -115,6 +117,7 @@ extern "C" int rbpf_destroy(rbpf_handle h)
     cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(h->stage_ev[i]);
     if (h->h_scan) cudaFreeHost(h->h_scan);
     delete h;
     return RBPF_OK;
@@ -197,9 +200,13 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_mg_count, 4);
 #undef A
     if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    if (cudaMallocHost((void **)&h->h_scan, 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
+    if (cudaMallocHost((void **)&h->h_scan, 2 * 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
-    h->h_prev = h->h_scan + 3 * RB_MAXB;
+    h->h_prev = nullptr;
+    h->stage_slot = 0;
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(RBPF_ERR_CUDA, "cudaEventCreate failed");
     d.prev_x = h->d_prev; d.prev_y = h->d_prev + RB_MAXB; d.n_prev = 0;
     d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist;
     d.rot_cs = h->d_rot;
@@ -251,8 +258,10 @@ extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *
     if (!h || !ranges || !angles || n_beams < 1 || n_beams > RB_MAXB) { if (h) h->err = "set_scan: bad arguments"; return RBPF_ERR_ARG; }
     h->d.B = n_beams;                                            // loaders differ in beam count; buffers hold RB_MAXB
     CK(cudaSetDevice(h->cfg.device));
-    CK(cudaStreamSynchronize(h->stream));                        // the pinned staging buffer may still be in flight
-    double *px = h->h_scan, *py = px + RB_MAXB, *dist = py + RB_MAXB;
+    // two pinned slots used alternately: only wait for the copies issued two calls ago
+    h->stage_slot ^= 1;
+    CK(cudaEventSynchronize(h->stage_ev[h->stage_slot]));
+    double *px = h->h_scan + (size_t)h->stage_slot * 5 * RB_MAXB, *py = px + RB_MAXB, *dist = py + RB_MAXB;
     for (int j = 0; j < n_beams; j++) {                          // Scan.__init__ lidar.py:76-80 (host libm, like the reference)
         px[j] = ranges[j] * cos(angles[j]);
         py[j] = ranges[j] * sin(angles[j]);
@@ -261,6 +270,7 @@ extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *
     CK(cudaMemcpyAsync(h->d_px, px, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_py, py, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_dist, dist, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->stage_ev[h->stage_slot], h->stream));
     h->have_scan = 1;
     return RBPF_OK;
 }
@@ -290,9 +300,12 @@ extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, in
         return RBPF_ERR_ARG;
     }
     CK(cudaSetDevice(h->cfg.device));
-    CK(cudaStreamSynchronize(h->stream));                        // pinned staging reuse
-    for (int q = 0; q < n_points; q++) { h->h_prev[q] = last_scan_xy[2 * q]; h->h_prev[RB_MAXB + q] = last_scan_xy[2 * q + 1]; }
-    CK(cudaMemcpyAsync(h->d_prev, h->h_prev, 2 * RB_MAXB * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // shares the slot of the preceding rbpf_set_scan (its event is re-recorded after this copy)
+    CK(cudaEventSynchronize(h->stage_ev[h->stage_slot]));
+    double *hp = h->h_scan + (size_t)h->stage_slot * 5 * RB_MAXB + 3 * RB_MAXB;
+    for (int q = 0; q < n_points; q++) { hp[q] = last_scan_xy[2 * q]; hp[RB_MAXB + q] = last_scan_xy[2 * q + 1]; }
+    CK(cudaMemcpyAsync(h->d_prev, hp, 2 * RB_MAXB * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->stage_ev[h->stage_slot], h->stream));
     h->d.n_prev = n_points;
     rb_launch_match(h->d, 1, h->stream);
     CK(cudaGetLastError());
