@@ -87,12 +87,13 @@ def main():
         if os.path.exists(f):
             md += ["## `ncu --set full` (%s), one launch per kernel: `%s`" % (tag, os.path.basename(f)), ""] + full(f) + [""]
     md += ["## Reading", "",
-           "* `match_kernel`: ~70 % of issue slots busy, DRAM < 1 %: bound by instruction issue (LOP3 carry-save adders, LDS,",
-           "  address arithmetic) of the bit-parallel scoring passes; the levers are fewer passes (branch and bound: 231 -> ~59)",
-           "  and fewer instructions per pass.",
-           "* `raycast_cast_kernel`: ~15 sectors per store request, ~6 per load request -- byte read-modify-writes along rays;",
-           "  bound by the L1/L2 sector traffic of those scattered accesses.  Skipping the store when the clamped value is",
-           "  unchanged (saturated cells) took it from 27.6 to 18.9 ms at 65,536 particles.",
+           "* `match_kernel`: ~70 % of issue slots busy, DRAM a few %: bound by instruction issue (LOP3 carry-save adders, LDS,",
+           "  address arithmetic) of the bit-parallel scoring passes; the levers were fewer passes (exact branch and bound over",
+           "  rotation groups, seeding with the rotations around the guess, admissible early abort: 231 -> ~34 full-pass",
+           "  equivalents per update) and fewer instructions per pass.",
+           "* `raycast_cast_kernel`: byte read-modify-writes along rays.  Baseline: ~15 sectors per store request, bound by L1/L2",
+           "  sector traffic; not storing unchanged (saturated) cells, the 8x4-cell sector blocks and the interior fast path",
+           "  took it from 29.4 to ~15 ms at 65,536 particles; now ~80 % of issue slots busy, about half of them per-beam set-up.",
            "* `raycast_prepare_kernel`: copy-on-write sub-tile copies, DRAM-bound as intended.",
            "* `weight_kernel`: latency-bound lookups, one warp per particle, 4 lookups in flight per lane."]
     open(os.path.join(P, "README.md"), "w").write("\n".join(md) + "\n")
