@@ -210,8 +210,19 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the first communicator is created:
+        # keep stdout to the one JSON line by pointing fd 1 at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         from thesis_b200.dist import ShardedParticleSet
     n_local = args.particles // world
     n_scans = 1 + args.burnin + args.warmup + 2 * args.steps + 2
