@@ -104,7 +104,7 @@ def cpu_baseline(work, n_particles, max_seconds, beams):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
     if n_particles <= 0:
         n_particles = 4 * cores
     f = O.Filter(n_particles, beams, 30)
@@ -142,12 +142,13 @@ def run_reference(args):
         return
     from thesis_b200 import synth
 
-    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+
+    cores = O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
     n_cpu = args.cpu_particles if args.cpu_particles > 0 else 8 * cores
     n_scans_total = 2 + args.warmup + args.steps
     work = synth.Workload(n_scans_total + 1, args.beams)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
 
     f = O.Filter(n_cpu, args.beams, 30)
     rng = np.random.default_rng(5)

@@ -190,6 +190,11 @@ def match_adj(guess, scan, prev_xy, rx, ry):
                 slice=sl.reshape(SLICE_W, SLICE_W))
 
 
+def set_threads(n=0):
+    """OpenMP threads used by Filter (n <= 0: query only)."""
+    return lib().orc_set_threads(int(n))
+
+
 def transform(pose, scan):
     gx = np.empty(scan.B)
     gy = np.empty(scan.B)

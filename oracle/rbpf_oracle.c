@@ -774,6 +774,22 @@ int orc_resample(const double *weights, int N, double u01, int *anc)
 
 /* -------------------------------------------------------- whole filter -- */
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* Number of OpenMP threads of the particle loops below (torchrun exports
+ * OMP_NUM_THREADS=1, which would silently make the CPU baseline single-threaded).
+ * n <= 0 only queries.  Returns the thread count in effect. */
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 typedef struct {
     int N, B, K;
     double *pose;      /* N*3 */
