@@ -1,0 +1,74 @@
+"""GPU: error conventions of the C ABI (include/rbpf_b200.h) -- status codes, not
+crashes; a failed match is a flag, not an error (matchScanCustom.m:26-28)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from thesis_b200 import particles
+
+    return particles
+
+
+def test_pool_exhaustion_is_reported_not_fatal(P, golden):
+    ps = P.ParticleSet(64, 180, pool_subtiles=40)            # far too small for 64 diverging particles
+    r, a = golden["intel_ranges"][0], golden["intel_angles"]
+    ps.poses = np.random.default_rng(0).uniform(-30, 30, (64, 3))
+    ps.set_scan(r, a)
+    ps.integrate()
+    with pytest.raises(P.RbpfError, match="pool"):
+        ps.synchronize()
+    st = ps.stats()
+    assert st["pool_in_use"] <= st["pool_subtiles"]
+
+
+def test_rays_leaving_the_world_are_dropped_and_counted(P, golden):
+    ps = P.ParticleSet(2, 180, world_tiles=(1, 1), pool_subtiles=200)     # 40 m x 40 m world
+    ps.poses = (18.0, 0.0, 0.0)                                          # 2 m from the border, looking out
+    ps.set_scan(np.full(180, 9.0), golden["intel_angles"])
+    ps.integrate()
+    ps.synchronize()
+    st = ps.stats()
+    assert st["cells_dropped"] > 0
+    assert ps.list_tiles(0) == [(0, 0)]
+
+
+def test_bad_arguments(P, golden):
+    with pytest.raises(P.RbpfError):
+        P.ParticleSet(4, 180, world_tiles=(4, 4))                         # even tile counts are rejected
+    with pytest.raises(P.RbpfError):
+        P.ParticleSet(4, 1000)                                            # more beams than RB_MAXB
+    ps = P.ParticleSet(4, 180, pool_subtiles=64)
+    with pytest.raises(P.RbpfError):
+        ps.scan_match()                                                   # no scan set
+    with pytest.raises(ValueError):
+        ps.set_scan(golden["intel_ranges"][0], golden["intel_angles"])
+        ps.weight(np.zeros(7))                                            # wrong number of normals
+    assert ps.export_tile(0, 40, 0) is None                               # tile does not exist: None like HybridMap
+    with pytest.raises(P.RbpfError):
+        ps.export_tile(0, 41, 0)                                          # not a tile centre
+
+
+def test_resample_assertion_maps_to_python_assertion(P):
+    """main.py:66-67: AssertionError("Incorrect number of resampled weights.") -- reachable with NaN weights."""
+    ps = P.ParticleSet(16, 180, world_tiles=(1, 1), pool_subtiles=64)
+    w = np.linspace(0.0, 1000.0, 16)
+    w[3] = np.nan
+    ps.weights = w
+    poses = np.arange(48, dtype=float).reshape(16, 3)
+    ps.poses = poses
+    try:
+        did, anc = ps.resample(0.5)
+    except AssertionError as e:
+        assert "Incorrect number of resampled weights" in str(e)
+        assert np.array_equal(ps.poses, poses)                            # particles unchanged
+    else:
+        # NaN compares false everywhere: max - min > 200 may not fire; then nothing must have changed
+        assert np.array_equal(ps.poses, poses if not did else poses[anc])
