@@ -165,6 +165,16 @@ int rbpf_export_tile(rbpf_handle h, int32_t particle, int32_t cx, int32_t cy, do
 /* Centres of the particle's existing tiles: out_xy[2*max_tiles]; returns count in *n. */
 int rbpf_list_tiles(rbpf_handle h, int32_t particle, int32_t *out_xy, int32_t max_tiles, int32_t *n);
 
+/* HybridMap.get_occupied_points (hybridmap.py:303-313; main.py:171,176 plots it):
+ * cells with log-odds > 1.0 of one particle, thresholded and compacted on the
+ * device, in the reference's cell units.  out_xy may be NULL (count only). */
+int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out_xy, int64_t max_points, int64_t *n);
+/* Checkpoint / resume of the whole particle set (the reference shelves particle 0
+ * only, main.py:183-210): state, page tables and every sub-tile in use.  The
+ * reading handle must have the same configuration. */
+int rbpf_checkpoint_write(rbpf_handle h, const char *path);
+int rbpf_checkpoint_read(rbpf_handle h, const char *path);
+
 int rbpf_stats(rbpf_handle h, rbpf_stats_t *out);
 int rbpf_synchronize(rbpf_handle h);
 

@@ -63,6 +63,9 @@ SIGNATURES = {
     "rbpf_get_match_slice": (C.c_int, [_H, C.c_int32, _ip]),
     "rbpf_export_tile": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, _dp, _ip]),
     "rbpf_list_tiles": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip]),
+    "rbpf_occupied_points": (C.c_int, [_H, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_int64)]),
+    "rbpf_checkpoint_write": (C.c_int, [_H, C.c_char_p]),
+    "rbpf_checkpoint_read": (C.c_int, [_H, C.c_char_p]),
     "rbpf_stats": (C.c_int, [_H, C.POINTER(RbpfStats)]),
     "rbpf_synchronize": (C.c_int, [_H]),
     "rbpf_rot_step": (C.c_double, []),

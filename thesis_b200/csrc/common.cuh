@@ -236,6 +236,8 @@ void rb_launch_export_tile(const RbCtx &c, int particle, int tx, int ty, double 
 void rb_launch_init(const RbCtx &c, cudaStream_t s);
 void rb_launch_refstats(const RbCtx &c, unsigned long long *out2_dev, cudaStream_t s);
 size_t rb_match_smem_bytes();
+void rb_launch_occupied_points(const RbCtx &c, int particle, double *out_dev, unsigned long long cap,
+                               unsigned long long *count_dev, cudaStream_t s);
 void rb_launch_migrate_claim(const RbCtx &c, const int *slots_dev, int n, uint32_t *mark, uint32_t *list, int *count,
                              cudaStream_t s);
 void rb_launch_migrate_pack(const RbCtx &c, const int *slots_dev, int n, int n_tiles, uint32_t *mark, uint32_t *list,

@@ -193,7 +193,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_tile, RB_DIM * RB_DIM);
     A(h->d_prev, 2 * RB_MAXB);
     A(h->d_slice, RB_SLICE_W * RB_SLICE_W);
-    A(h->d_refstats, 4);
+    A(h->d_refstats, 8);
     A(h->d_mg_slots, 2 * N);
     A(h->d_mg_mark, d.pool_tiles);
     A(h->d_mg_list, d.pool_tiles);
@@ -665,4 +665,130 @@ extern "C" int rbpf_resample_commit(rbpf_handle h)
 extern "C" int64_t rbpf_migrate_bytes(rbpf_handle h, int32_t n_particles, int32_t n_subtiles)
 {
     return h ? (int64_t)rb_migrate_bytes(n_particles, n_subtiles, h->d.nsub) : 0;
+}
+
+// HybridMap.get_occupied_points (hybridmap.py:303-313) on the device: threshold and
+// compact the particle's sub-tiles.  out_xy may be NULL (count only); at most
+// max_points pairs are written, *n receives the total number of occupied cells.
+extern "C" int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out_xy, int64_t max_points, int64_t *n)
+{
+    if (!h || !n || particle < 0 || particle >= h->d.N || max_points < 0) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    double *dev = nullptr;
+    if (out_xy && max_points > 0) CK(cudaMalloc((void **)&dev, sizeof(double) * 2 * (size_t)max_points));
+    rb_launch_occupied_points(h->d, particle, dev, (unsigned long long)max_points, h->d_refstats + 3, h->stream);
+    unsigned long long cnt = 0;
+    cudaError_t e = cudaMemcpyAsync(&cnt, h->d_refstats + 3, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && dev) {
+        const unsigned long long m = cnt < (unsigned long long)max_points ? cnt : (unsigned long long)max_points;
+        e = cudaMemcpy(out_xy, dev, sizeof(double) * 2 * (size_t)m, cudaMemcpyDeviceToHost);
+    }
+    if (dev) cudaFree(dev);
+    if (e != cudaSuccess) { h->err = std::string("occupied_points: ") + cudaGetErrorString(e); return RBPF_ERR_CUDA; }
+    *n = (int64_t)cnt;
+    return RBPF_OK;
+}
+
+// ---- checkpoint / resume of the whole particle set --------------------------------
+// The reference pickles particle 0 only every 50 frames (main.py:183-210); here the
+// complete set is written: state, page tables, reference counts and every sub-tile
+// in use (sparse, by pool index), through a pinned bounce buffer.
+struct CkptHeader {
+    char magic[8];
+    int32_t N, nsub, tiles_x, tiles_y, rank, world;
+    uint32_t pool_tiles, in_use;
+    uint64_t step_no;
+};
+
+static const size_t CKPT_CH = 32u << 20;
+static void *g_ckpt_host = nullptr;             // pinned bounce buffer, allocated on first use
+
+static int ckpt_io(rbpf_ctx *h, FILE *f, void *dev, size_t bytes, bool write)
+{
+    const size_t CH = CKPT_CH;
+    if (!g_ckpt_host) CK(cudaMallocHost(&g_ckpt_host, CH));
+    void *host = g_ckpt_host;
+    int rc = RBPF_OK;
+    for (size_t off = 0; off < bytes && rc == RBPF_OK; off += CH) {
+        const size_t n = bytes - off < CH ? bytes - off : CH;
+        if (write) {
+            if (cudaMemcpy(host, (char *)dev + off, n, cudaMemcpyDeviceToHost) != cudaSuccess || fwrite(host, 1, n, f) != n) rc = RBPF_ERR_CUDA;
+        } else {
+            if (fread(host, 1, n, f) != n || cudaMemcpy((char *)dev + off, host, n, cudaMemcpyHostToDevice) != cudaSuccess) rc = RBPF_ERR_CUDA;
+        }
+    }
+    if (rc) h->err = write ? "checkpoint: write failed" : "checkpoint: read failed (truncated file?)";
+    return rc;
+}
+
+extern "C" int rbpf_checkpoint_write(rbpf_handle h, const char *path)
+{
+    if (!h || !path) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const RbCtx &d = h->d;
+    std::vector<uint32_t> rc(d.pool_tiles);
+    CK(cudaMemcpy(rc.data(), d.refcnt, sizeof(uint32_t) * d.pool_tiles, cudaMemcpyDeviceToHost));
+    CkptHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "RBPFCK01", 8);
+    hd.N = d.N; hd.nsub = d.nsub; hd.tiles_x = d.tiles_x; hd.tiles_y = d.tiles_y; hd.rank = d.rank; hd.world = d.world;
+    hd.pool_tiles = d.pool_tiles; hd.step_no = d.step_no;
+    for (uint32_t t = 0; t < d.pool_tiles; t++) hd.in_use += rc[t] > 0;
+    FILE *f = fopen(path, "wb");
+    if (!f) { h->err = std::string("checkpoint: cannot open ") + path; return RBPF_ERR_ARG; }
+    int r = fwrite(&hd, sizeof(hd), 1, f) == 1 ? RBPF_OK : RBPF_ERR_CUDA;
+    const size_t N = d.N;
+    if (!r) r = ckpt_io(h, f, d.pose, sizeof(double) * 3 * N, true);
+    if (!r) r = ckpt_io(h, f, d.cov, sizeof(double) * 9 * N, true);
+    if (!r) r = ckpt_io(h, f, d.weight, sizeof(double) * N, true);
+    if (!r) r = ckpt_io(h, f, d.exists, sizeof(unsigned long long) * N, true);
+    if (!r) r = ckpt_io(h, f, d.pt, sizeof(uint32_t) * N * d.nsub, true);
+    if (!r) r = fwrite(rc.data(), sizeof(uint32_t), d.pool_tiles, f) == d.pool_tiles ? RBPF_OK : RBPF_ERR_CUDA;
+    for (uint32_t t = 0; t < d.pool_tiles && !r; t++)
+        if (rc[t] > 0) r = ckpt_io(h, f, d.pool + (size_t)t * RB_SUB_BYTES, RB_SUB_BYTES, true);
+    fclose(f);
+    return r;
+}
+
+extern "C" int rbpf_checkpoint_read(rbpf_handle h, const char *path)
+{
+    if (!h || !path) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    RbCtx &d = h->d;
+    FILE *f = fopen(path, "rb");
+    if (!f) { h->err = std::string("checkpoint: cannot open ") + path; return RBPF_ERR_ARG; }
+    CkptHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "RBPFCK01", 8) != 0 || hd.N != d.N || hd.nsub != d.nsub ||
+        hd.tiles_x != d.tiles_x || hd.tiles_y != d.tiles_y || hd.pool_tiles != d.pool_tiles) {
+        fclose(f);
+        h->err = "checkpoint: header does not match this handle's configuration";
+        return RBPF_ERR_ARG;
+    }
+    const size_t N = d.N;
+    std::vector<uint32_t> rc(d.pool_tiles);
+    int r = ckpt_io(h, f, d.pose, sizeof(double) * 3 * N, false);
+    if (!r) r = ckpt_io(h, f, d.cov, sizeof(double) * 9 * N, false);
+    if (!r) r = ckpt_io(h, f, d.weight, sizeof(double) * N, false);
+    if (!r) r = ckpt_io(h, f, d.exists, sizeof(unsigned long long) * N, false);
+    if (!r) r = ckpt_io(h, f, d.pt, sizeof(uint32_t) * N * d.nsub, false);
+    if (!r) r = fread(rc.data(), sizeof(uint32_t), d.pool_tiles, f) == d.pool_tiles ? RBPF_OK : RBPF_ERR_CUDA;
+    std::vector<uint32_t> freel;
+    for (uint32_t t = 0; t < d.pool_tiles && !r; t++) {
+        if (rc[t] > 0) r = ckpt_io(h, f, d.pool + (size_t)t * RB_SUB_BYTES, RB_SUB_BYTES, false);
+        else freel.push_back(t);
+    }
+    fclose(f);
+    if (r) return r;
+    // free list: pop order ascending like a fresh handle
+    std::vector<uint32_t> fl(d.pool_tiles, 0u);
+    for (size_t i = 0; i < freel.size(); i++) fl[i] = freel[freel.size() - 1 - i];
+    const int fc = (int)freel.size();
+    CK(cudaMemcpy(d.refcnt, rc.data(), sizeof(uint32_t) * d.pool_tiles, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.free_list, fl.data(), sizeof(uint32_t) * d.pool_tiles, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.free_count, &fc, sizeof(int), cudaMemcpyHostToDevice));
+    d.step_no = hd.step_no;
+    return RBPF_OK;
 }

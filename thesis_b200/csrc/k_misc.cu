@@ -73,3 +73,34 @@ void rb_launch_refstats(const RbCtx &c, unsigned long long *out2_dev, cudaStream
     cudaMemsetAsync(out2_dev, 0, 3 * sizeof(unsigned long long), s);
     refstats_kernel<<<512, 256, 0, s>>>(c, out2_dev);
 }
+
+// Occupied cells (log-odds > 1.0) of one particle as the reference's plotting feed
+// HybridMap.get_occupied_points (hybridmap.py:303-313): coordinates in cell units,
+// ((i - 400) * 0.05 + centre) / 0.05.  One CTA per sub-tile; unordered append.
+__global__ void __launch_bounds__(256) occupied_points_kernel(RbCtx c, int p, double *__restrict__ out_xy,
+                                                            unsigned long long cap, unsigned long long *count)
+{
+    const int sub = blockIdx.x;
+    const uint32_t t = c.pt[(size_t)p * c.nsub + sub];
+    if (t == RB_NONE) return;
+    const int sx = sub % c.subs_x, sy = sub / c.subs_x;
+    const int8_t *tile = c.pool + (size_t)t * RB_SUB_BYTES;
+    for (int idx = threadIdx.x; idx < RB_SUB_BYTES; idx += blockDim.x) {
+        const int x = idx % RB_SUB, y = idx / RB_SUB;
+        if (tile[RB_OFF_Y(y) + RB_OFF_X(x)] <= RB_T_OCC_THRESH) continue;
+        const unsigned long long slot = atomicAdd(count, 1ull);
+        if (!out_xy || slot >= cap) continue;
+        const int ux = sx * RB_SUB + x, uy = sy * RB_SUB + y;
+        const int tx = ux / RB_DIM - c.txh, ty = uy / RB_DIM - c.tyh;
+        const int ix = ux % RB_DIM, iy = uy % RB_DIM;
+        out_xy[2 * slot] = (((double)ix - 400.0) * RB_CS + 40.0 * tx) / RB_CS;
+        out_xy[2 * slot + 1] = (((double)iy - 400.0) * RB_CS + 40.0 * ty) / RB_CS;
+    }
+}
+
+void rb_launch_occupied_points(const RbCtx &c, int particle, double *out_dev, unsigned long long cap,
+                               unsigned long long *count_dev, cudaStream_t s)
+{
+    cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), s);
+    occupied_points_kernel<<<c.nsub, 256, 0, s>>>(c, particle, out_dev, cap, count_dev);
+}
