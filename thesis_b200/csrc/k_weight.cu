@@ -12,7 +12,12 @@
 // in the reference's sequential order so that results are run-to-run identical.
 #include "common.cuh"
 
+#ifndef WT_WARPS
 #define WT_WARPS 4
+#endif
+#ifndef WT_INFLIGHT
+#define WT_INFLIGHT 4                   // beam lookups in flight per lane
+#endif
 
 // fallback_phase == 0: particles with a valid match (robot.py:80-114)
 // fallback_phase == 1: particles whose match failed, after the map update
@@ -88,11 +93,11 @@ __global__ void __launch_bounds__(WT_WARPS * 32) weight_kernel(RbCtx c, const do
         double cs_ = cos(g2), sn_ = sin(g2);
         int S = 0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-        // four beams in flight: locate (ALU) -> page-table entries -> cells
-        for (int j = 0; j < c.B; j += 4) {
-            int sub[4], off[4];
+        // WT_INFLIGHT beams in flight: locate (ALU) -> page-table entries -> cells
+        for (int j = 0; j < c.B; j += WT_INFLIGHT) {
+            int sub[WT_INFLIGHT], off[WT_INFLIGHT];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < WT_INFLIGHT; u++) {
                 const int jj = j + u;
                 sub[u] = -1; off[u] = 0;
                 if (jj < c.B) {
@@ -104,11 +109,11 @@ __global__ void __launch_bounds__(WT_WARPS * 32) weight_kernel(RbCtx c, const do
                     }
                 }
             }
-            uint32_t t[4];
+            uint32_t t[WT_INFLIGHT];
 #pragma unroll
-            for (int u = 0; u < 4; u++) t[u] = sub[u] >= 0 ? pt[sub[u]] : RB_NONE;
+            for (int u = 0; u < WT_INFLIGHT; u++) t[u] = sub[u] >= 0 ? pt[sub[u]] : RB_NONE;
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < WT_INFLIGHT; u++)
                 if (t[u] != RB_NONE) S += c.pool[(size_t)t[u] * RB_SUB_BYTES + off[u]];
         }
         w = ((double)(10 + S) / 10.0) * pr;
