@@ -79,3 +79,43 @@ def test_device_rng_mode_runs(gpu, golden):
     ps = parts[0]._shared.ps
     ps.synchronize()
     assert np.isfinite(ps.poses).all() and ps.stats()["cells_dropped"] == 0
+
+
+def test_long_run_gpu_vs_oracle_all_excerpt_frames(gpu):
+    """All 45 sweeps of the Intel excerpt, 48 particles, main.py's map/adj alternation:
+    the GPU views and the oracle, driven by the same loop and the same NumPy draws,
+    must pick the same ancestors at every resample and stay within tolerance."""
+    import ref_adapter as RA
+    from thesis_b200 import harness, sensors
+
+    n = 48
+    np.random.seed(7)
+    ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
+    op = RA.OracleParticles(n, 180)
+    oposes = []
+    harness.run_log(op.views, ld, im, op.resample, seed_fn=op.seed,
+                    on_frame=lambda f, ps: oposes.append([list(p.get_latest_pose().as_tuple()) for p in ps]))
+    np.random.seed(7)
+    ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
+    gpu.new_filter(rng="numpy", keep_history=False, pool_subtiles=20000)
+    parts = [gpu.Robot("eng") for _ in range(n)]
+    anc, gposes = [], []
+
+    def resample(ps):
+        out = gpu.resample(ps)
+        anc.append(ps[0]._shared.last_ancestors.copy())
+        return out
+
+    parts, log = harness.run_log(parts, ld, im, resample, seed_fn=gpu.seed_map,
+                                 on_frame=lambda f, ps: gposes.append(ps[0]._shared.poses().copy()))
+    assert len(log) == 45 and len(anc) == len(op.ancestors) >= 40
+    for k, (a, b) in enumerate(zip(anc, op.ancestors)):
+        assert np.array_equal(a, b), "resample %d" % k
+    assert np.allclose(np.array(gposes), np.array(oposes), rtol=0, atol=1e-8)
+    ps = parts[0]._shared.ps
+    assert np.allclose(ps.weights, op.f.weight, rtol=1e-8)
+    for i in (0, 23, 47):
+        ot = op.f.map(i).tiles()
+        assert sorted(ps.list_tiles(i)) == sorted(ot.keys())
+        for c, ref in ot.items():
+            assert np.array_equal(np.rint(ps.export_tile(i, *c) * 10), np.rint(ref * 10))
