@@ -24,7 +24,8 @@
 #ifndef RC_INFLIGHT
 #define RC_INFLIGHT 4
 #endif
-// RC_INFLIGHT: chunks of 32 ray cells whose loads are issued together
+// RC_INFLIGHT: chunks of 32 ray cells whose loads are issued together (fast path)
+#define RC_INFLIGHT_G 2   // same for the general path, which only sees the tail of a ray
 
 // One beam's ray on the 0.05 m lattice, everything the per-cell closed form needs.
 struct Ray {
@@ -228,6 +229,7 @@ struct BeamPack {
     int w1;          // D (bits 0-12) | step_q << 13        (D = major extent >= 1)
     int w2;          // d2 (bits 0-13) | step_e << 14       (d2 = 2 * minor extent)
     int end_tile;    // reference tile of the end cell (ty * tiles_x + tx) or -1
+    unsigned magic;  // ceil(2^32 / D2): floor(num / D2) == umulhi(num, magic) for num * D2 < 2^32
 };
 
 // Same lookup from a table staged in shared memory (plain load).
@@ -269,10 +271,21 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     const uint32_t *lutx = LUT_SMEM ? lut_s : c.lutx, *luty = LUT_SMEM ? lut_s + 800 * c.tiles_x : c.luty;
 #define RC_LUT(l, k, h) (LUT_SMEM ? rb_write_lut_s(l, k, h) : rb_write_lut(l, k, h))
     const int txh = c.txh, tyh = c.tyh, subs_x = c.subs_x, tiles_x = c.tiles_x;
+    // every ray starts in the robot's cell: its sub-tile is the page-table hit of each beam's first cells
+    int sub0 = -1;
+    int8_t *base0 = nullptr;
+    {
+        const uint32_t p0x = RC_LUT(lutx, sx, txh), p0y = RC_LUT(luty, sy, tyh);
+        if (p0x != RB_NONE && p0y != RB_NONE) {
+            sub0 = (int)RB_LUT_SUB(p0y) * subs_x + (int)RB_LUT_SUB(p0x);
+            const uint32_t t0 = pt[sub0];
+            if (t0 == RB_NONE) sub0 = -1; else base0 = c.pool + (size_t)t0 * RB_SUB_BYTES;
+        }
+    }
 
     for (int j0 = 0; j0 < c.B; j0 += 32) {
         BeamPack mine;
-        mine.w0 = 0; mine.w1 = 1; mine.w2 = 0; mine.end_tile = -1;
+        mine.w0 = 0; mine.w1 = 1; mine.w2 = 0; mine.end_tile = -1; mine.magic = 0u;
         if (j0 + lane < c.B) {
             const Ray r = ray_of_beam(c, j0 + lane, x, y, cs_, sn_, sx, sy);
             const RayStep st = ray_step(sx, sy, r);
@@ -285,6 +298,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             // start and end cell inside the world => every cell of the ray is (bounding box)
             const int inside = pex != RB_NONE && pey != RB_NONE && RC_LUT(lutx, sx, txh) != RB_NONE && RC_LUT(luty, sy, tyh) != RB_NONE;
             mine.w0 = len | (r.occ << 12) | (st.steep << 13) | ((st.smaj + 1) << 14) | ((st.smin + 1) << 16) | (inside << 18);
+            mine.magic = (unsigned)((0x100000000ull + st.D2 - 1) / st.D2);
             mine.w1 = (int)(st.D | (step_q << 13));
             mine.w2 = (int)(st.d2 | (step_e << 14));
         }
@@ -295,27 +309,30 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
             if (len == 0) continue;                                 // hybridmap.py:278-281 empty list
             const int w1 = __shfl_sync(FULL, mine.w1, b), w2 = __shfl_sync(FULL, mine.w2, b);
             const int end_tile = __shfl_sync(FULL, mine.end_tile, b);
+            const unsigned magic = __shfl_sync(FULL, mine.magic, b);
             const int occ = (w0 >> 12) & 1, steep = (w0 >> 13) & 1;
             const int smaj = ((w0 >> 14) & 3) - 1, smin = ((w0 >> 16) & 3) - 1;
             const int D = w1 & 0x1fff, step_q = w1 >> 13, d2 = w2 & 0x3fff, step_e = w2 >> 14;
             const int D2 = 2 * D;
             const int n_occ = occ ? len - 1 : -1, n_near = occ ? len - 2 : -1;
+            cached_sub = sub0;
+            cached_base = base0;
             const uint32_t *lmaj = steep ? luty : lutx, *lmin = steep ? lutx : luty;
             const int hmaj = steep ? tyh : txh, hmin = steep ? txh : tyh;
             // LUT bit that says "this lattice cell shares its storage cell with the
             // next / previous cell of the ray along that axis" 
-            const int sh_maj_next = smaj > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT, sh_maj_prev = smaj > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT;
-            const int sh_min_next = smin > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT, sh_min_prev = smin > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT;
+#define SH_MAJ_NEXT (smaj > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT)
+#define SH_MAJ_PREV (smaj > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT)
+#define SH_MIN_NEXT (smin > 0 ? RB_LUT_NEXT_BIT : RB_LUT_PREV_BIT)
+#define SH_MIN_PREV (smin > 0 ? RB_LUT_PREV_BIT : RB_LUT_NEXT_BIT)
             // state of cell n = lane (closed form), then +32 cells per chunk incrementally:
             // minor(n) = floor((n*d2 + D) / D2), e = remainder
             int n = lane, e, kmaj, kmin;
             {
+                // num <= 31 * 2D + D and D2 <= 8190, so num * D2 < 2^32 and the magic quotient is exact
                 const unsigned num = (unsigned)lane * (unsigned)d2 + (unsigned)D;
-                unsigned m = __float2uint_rz(__uint2float_rz(num) * __frcp_rn((float)D2));
-                int rem = (int)(num - m * (unsigned)D2);
-                if (rem < 0) { m--; rem += D2; }
-                if (rem >= D2) { m++; rem -= D2; }
-                e = rem;
+                const unsigned m = __umulhi(num, magic);
+                e = (int)(num - m * (unsigned)D2);
                 kmaj = (steep ? sy : sx) + smaj * lane;
                 kmin = (steep ? sx : sy) + smin * (int)m;
             }
@@ -351,8 +368,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                         bool skip = false;
                         if (pmaj >> RB_LUT_NEXT_BIT) {                      // rare: an aliasing pair along the major axis
                             const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
-                            skip = n >= 1 && ((pmaj >> sh_maj_prev) & 1u) && (!bump_prev || ((pmin >> sh_min_prev) & 1u));
-                            if (((pmaj >> sh_maj_next) & 1u) && (!bump_next || ((pmin >> sh_min_next) & 1u))) d_ = 2 * RB_T_EMP;
+                            skip = n >= 1 && ((pmaj >> SH_MAJ_PREV) & 1u) && (!bump_prev || ((pmin >> SH_MIN_PREV) & 1u));
+                            if (((pmaj >> SH_MAJ_NEXT) & 1u) && (!bump_next || ((pmin >> SH_MIN_NEXT) & 1u))) d_ = 2 * RB_T_EMP;
                         }
                         if (cached_base && !skip) {
                             addr[u] = cached_base + RB_LUT_OFF(py_) + RB_LUT_OFF(px_);
@@ -377,11 +394,13 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                     n0 += 32 * nch;
                 }
             }
-            for (; n0 < len; n0 += 32 * RC_INFLIGHT) {
-                int ops[RC_INFLIGHT], t[RC_INFLIGHT];
-                int8_t *addr[RC_INFLIGHT];
+            // general path: the last <= 34 cells of the ray (end / nearby handling, idle lanes)
+            // and rays that leave the world
+            for (; n0 < len; n0 += 32 * RC_INFLIGHT_G) {
+                int ops[RC_INFLIGHT_G], t[RC_INFLIGHT_G];
+                int8_t *addr[RC_INFLIGHT_G];
 #pragma unroll
-                for (int u = 0; u < RC_INFLIGHT; u++) {
+                for (int u = 0; u < RC_INFLIGHT_G; u++) {
                     ops[u] = 0; addr[u] = nullptr;
                     if (n0 + 32 * u >= len) continue;               // warp-uniform
                     if (n < len) {
@@ -400,11 +419,12 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                                 if (!cached_base) atomicExch(&c.flags->world_overflow, 2);  // cannot happen after prepare
                             }
                             // does this cell share its storage cell with the previous / next ray cell?
-                            const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
-                            const bool alias_prev = n >= 1 && ((pmaj >> sh_maj_prev) & 1u) &&
-                                                    (!bump_prev || ((pmin >> sh_min_prev) & 1u));
-                            const bool alias_next = n + 1 < len && ((pmaj >> sh_maj_next) & 1u) &&
-                                                    (!bump_next || ((pmin >> sh_min_next) & 1u));
+                            bool alias_prev = false, alias_next = false;
+                            if (pmaj >> RB_LUT_NEXT_BIT) {                  // rare: an aliasing pair along the major axis
+                                const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                                alias_prev = n >= 1 && ((pmaj >> SH_MAJ_PREV) & 1u) && (!bump_prev || ((pmin >> SH_MIN_PREV) & 1u));
+                                alias_next = n + 1 < len && ((pmaj >> SH_MAJ_NEXT) & 1u) && (!bump_next || ((pmin >> SH_MIN_NEXT) & 1u));
+                            }
                             if (cached_base && !alias_prev) {
                                 int o = n == n_occ ? 2 : 1;                                 // hybridmap.py:137-138 / :144
                                 if (n == n_near && tile == end_tile) o |= 4;                // hybridmap.py:139-142
@@ -427,9 +447,9 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
                     kmin += smin * dq;
                 }
 #pragma unroll
-                for (int u = 0; u < RC_INFLIGHT; u++) t[u] = ops[u] ? (int)*addr[u] : 0;
+                for (int u = 0; u < RC_INFLIGHT_G; u++) t[u] = ops[u] ? (int)*addr[u] : 0;
 #pragma unroll
-                for (int u = 0; u < RC_INFLIGHT; u++)
+                for (int u = 0; u < RC_INFLIGHT_G; u++)
                     if (ops[u]) {
                         int v = apply_ops(t[u], ops[u] & 7);
                         if (ops[u] >> 3) v = apply_ops(v, ops[u] >> 3);
