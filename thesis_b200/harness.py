@@ -27,6 +27,17 @@ def dedup_times(seq):
     return seq
 
 
+def _fan(particles, call):
+    """main.py:144,157-159 fan a call over the particle list.  The device-backed views of
+    thesis_b200.particles run the batched kernels for every particle on the first call of a
+    round, so one call is enough there (65,536 Python calls per stage would cost more than
+    the kernels)."""
+    if getattr(particles[0], "_shared", None) is not None:
+        call(particles[0])
+    else:
+        [call(p) for p in particles]
+
+
 def run_log(particles, lidar_data, imu_data, resample_fn, seed_fn=None, max_frames=None, frame0=0,
             on_frame=None):
     """Drive `particles` through the log.  Returns (particles, log) where log is a
@@ -48,7 +59,7 @@ def run_log(particles, lidar_data, imu_data, resample_fn, seed_fn=None, max_fram
         if reading.timestamp() == t:                              # main.py:139-145
             imu_idx = min(imu_idx + 1, len(imu_data) - 1)
             reading.set_dt(reading.timestamp() - prev_timestamp)
-            [p.imu_update(reading) for p in particles]
+            _fan(particles, lambda p: p.imu_update(reading))
             prev_timestamp = reading.timestamp()
         if lidar_data.timestamp_for_idx(lidar_idx) == t:          # main.py:147-180
             scan = lidar_data[lidar_idx]
@@ -59,7 +70,7 @@ def run_log(particles, lidar_data, imu_data, resample_fn, seed_fn=None, max_fram
             updated = False
             if update_count < MAX_UPDATE_COUNT or dist >= DIST_THRESHOLD or rot >= ROT_THRESHOLD:
                 adj = not (frame % 5 < 2)                         # main.py:156-159
-                [p.map_update(scan, last_scan, adj) for p in particles]
+                _fan(particles, lambda p: p.map_update(scan, last_scan, adj))
                 particles = resample_fn(particles)
                 if dist >= DIST_THRESHOLD or rot >= ROT_THRESHOLD:
                     update_count = 0

@@ -361,18 +361,24 @@ class Robot:
         self._motion_seen = 0
         self._update_seen = 0
 
-    # -- reference accessors
+    # -- reference accessors (histories; with keep_history=False only the latest value is kept,
+    #    read lazily from the device so that resample() costs no per-view Python work)
+    def _latest(self, k):
+        return [float(self._shared.poses()[self._slot, k])] if self._shared.ps is not None else [0.0]
+
     def x(self):
-        return self._x
+        return self._x if self._shared.keep_history else self._latest(0)
 
     def y(self):
-        return self._y
+        return self._y if self._shared.keep_history else self._latest(1)
 
     def theta(self):
-        return self._theta
+        return self._theta if self._shared.keep_history else self._latest(2)
 
     def weight(self):
-        return self._weight
+        if self._shared.keep_history or self._shared.ps is None:
+            return self._weight
+        return [float(self._shared.weights()[self._slot])]
 
     @property
     def _cov(self):
@@ -465,7 +471,4 @@ def resample(particles):
             for v in sh.views:
                 hx, hy, ht, hw = old[anc[v._slot]]
                 v._x, v._y, v._theta, v._weight = list(hx), list(hy), list(ht), list(hw) + [1.0]
-        else:
-            for v in sh.views:
-                v._weight = [1.0]
-    return list(sh.views)
+    return sh.views if not sh.keep_history else list(sh.views)
