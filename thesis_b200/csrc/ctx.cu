@@ -18,7 +18,6 @@ struct rbpf_ctx {
     cudaStream_t stream;
     std::string err;
     std::vector<void *> allocs;
-    double *d_ranges_unused;
     double *d_px, *d_py, *d_dist;  // scan
     double *d_rot;                 // rotation table
     uint32_t *d_lutx, *d_luty;

@@ -29,10 +29,13 @@
 // consecutive lattice steps.  A point at range <= 11 m moves at most one cell per
 // rotation step, so scoring the group's middle rotation against the bitmap
 // dilated by MT_GRAD cells bounds the score of every rotation of the group at
-// every translation from above.  Phase A scores every group once (231/8 = 29
-// passes instead of 231), phase B visits groups in decreasing bound and scores a
-// member rotation only while its bound can still beat the best key so far.  The
-// result is identical to the exhaustive search of the oracle.
+// every translation from above.  The rotations around the guess are scored first
+// (seeds), phase A then scores every group once (231/8 = 29 passes instead of
+// 231), phase B visits groups in decreasing bound and scores a member rotation
+// only while its bound can still beat the best key so far.  Every pass gives up
+// as soon as its best partial count plus the points still to come cannot reach
+// the best complete score (admissible).  The result is identical to the
+// exhaustive search of the oracle; ~34 full-pass equivalents instead of 231.
 #include "common.cuh"
 
 #ifndef MT_GROUP

@@ -11,11 +11,15 @@
 //                    turns out to be the last holder.  No cell is modified here,
 //                    so sharers can copy while the future owner waits.
 //   raycast_cast     replays the reference's update order exactly: beams in
-//                    order, lanes across the cells of one ray (closed-form
-//                    Bresenham), saturating int8 read-modify-write.  The
-//                    reference's clamps make the result order-dependent
+//                    order, lanes across 32 consecutive cells of one ray
+//                    (closed-form Bresenham for the first cell of a lane, then
+//                    +32 cells incrementally), saturating int8 read-modify-write.
+//                    The reference's clamps make the result order-dependent
 //                    (SURVEY 3.4-4), hence no atomics and no beam parallelism
-//                    inside a particle.
+//                    inside a particle.  Per-beam constants are computed
+//                    lane-parallel (one beam per lane) and broadcast; chunks whose
+//                    cells are all plain "empty" updates take a fast path; a cell
+//                    whose clamped value does not change is not stored back.
 #include "common.cuh"
 
 #ifndef RC_WARPS
