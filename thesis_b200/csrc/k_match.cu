@@ -595,14 +595,12 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     }
 }
 
-static bool g_match_attr_set = false;
-
+// The opt-in to > 48 KB of dynamic shared memory is per device: set it on every
+// launch (a host-side call of about a microsecond) rather than caching a flag that
+// would be wrong for a second device in the same process.
 static void match_set_attr()
 {
-    if (!g_match_attr_set) {
-        cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb_match_smem_bytes());
-        g_match_attr_set = true;
-    }
+    cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb_match_smem_bytes());
 }
 
 void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)

@@ -485,11 +485,7 @@ void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
 #ifdef RC_SMEM_LUT   // measured slower on B200 (5.55 vs 4.02 ms at 16,384 particles): staging 32 KB per CTA costs more than the L1 hits it saves
     const size_t lut_bytes = sizeof(uint32_t) * 800 * (size_t)(c.tiles_x + c.tiles_y);
     if (lut_bytes <= 64 * 1024) {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(raycast_cast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            attr = true;
-        }
+        cudaFuncSetAttribute(raycast_cast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         raycast_cast_kernel<true><<<blocks, RC_WARPS * 32, lut_bytes, s>>>(c);
         return;
     }
