@@ -315,7 +315,8 @@ def run_b200(args):
                        ray_cells_per_scan=a_r, pool_subtiles=pool,
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),
                        pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
-                       match_scoring_passes_per_update=st["match_evals"] / max(1, n_local * (s - 1)),
+                       match_searches_run_fraction=st["match_runs"] / max(1, n_local * (s - 1)),
+                       match_scoring_passes_per_update=st["match_evals"] / max(1, st["match_runs"]),
                        match_exhaustive_passes_per_update=231,
                        match_full_pass_equivalents_per_update=st["match_visits"] / max(1, st["match_points"])),
         "clocks": clocks,

@@ -82,6 +82,8 @@ typedef struct {
     uint64_t refcount_sum;    /* sum of sub-tile reference counts (snapshot; must equal total_refs) */
     uint64_t match_visits;    /* points visited by those passes (an aborted pass visits fewer than its points) */
     uint64_t match_points;    /* matcher points summed over all matches (exhaustive search = 231 * match_points visits) */
+    uint64_t match_runs;      /* matcher searches actually run: duplicates of the last resample are bit-identical
+                                 until the next weight stage and take their representative's result */
     uint64_t match_evals;     /* bitmap scoring passes of the matcher (group bounds + member rotations; exhaustive = 231 per match) */
 } rbpf_stats_t;
 

@@ -29,6 +29,7 @@ class RbpfStats(C.Structure):
         ("fresh_allocs", C.c_uint64), ("cells_dropped", C.c_uint64), ("resamples", C.c_uint64),
         ("match_failed", C.c_uint64), ("shared_refs", C.c_uint64), ("total_refs", C.c_uint64),
         ("refcount_sum", C.c_uint64), ("match_visits", C.c_uint64), ("match_points", C.c_uint64),
+        ("match_runs", C.c_uint64),
         ("match_evals", C.c_uint64),
     ]
 

@@ -56,7 +56,7 @@
 #define RB_SLICE_W (2 * RB_NT_MAX + 1)      // 29
 
 struct RbStats {                            // device-side counters
-    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points;
+    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points, match_runs;
 };
 
 struct RbFlags {                            // device-side status words
@@ -105,6 +105,11 @@ struct RbCtx {
     double *w_all;                          // n_global adjusted weights / cumsum scratch
     int *ancestors;                         // n_global
     int *mult;                              // N  local descendants of each old local particle
+    // Duplicates made by the last resample are bit-identical (pose, covariance, shared
+    // page table) until the next weight stage: dup_of[j] = first local slot with the same
+    // ancestor.  The matcher runs once per representative and its result is copied.
+    int *dup_of;                            // N
+    int use_dup;                            // host-set: dup_of is valid for this launch
     RbStats *stats;
     RbFlags *flags;
     unsigned long long seed;

@@ -185,7 +185,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4);
-    A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N);
+    A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);
     A(h->d_z, N * d.K * 3);
     A(h->d_u01, 2);
@@ -313,6 +313,7 @@ extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, in
 
 extern "C" int rbpf_weight(rbpf_handle h, const double *z)
 {
+    if (h) h->d.use_dup = 0;       // samples make duplicates diverge
     if (!h || !h->have_scan) { if (h) h->err = "weight: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
     const double *zd = nullptr;
@@ -327,6 +328,7 @@ extern "C" int rbpf_weight(rbpf_handle h, const double *z)
 
 extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
 {
+    if (h) h->d.use_dup = 0;
     if (!h || !h->have_scan) { if (h) h->err = "integrate: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
     rb_launch_raycast_prepare(h->d, h->stream);
@@ -339,6 +341,7 @@ extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
 static void swap_buffers(rbpf_ctx *h)
 {
     RbCtx &d = h->d;
+    d.use_dup = 1;                 // set by the resample that just ran; cleared by anything but motion
     std::swap(d.pose, d.pose2);
     std::swap(d.cov, d.cov2);
     std::swap(d.pt, d.pt2);
@@ -397,6 +400,7 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     MARK(1);
     rb_launch_match(h->d, 0, h->stream);
     MARK(2);
+    h->d.use_dup = 0;
     rb_launch_weight(h->d, nullptr, 0, h->stream);
     MARK(3);
     rb_launch_raycast_prepare(h->d, h->stream);
@@ -468,8 +472,8 @@ static int copy_in(rbpf_ctx *h, void *dst, const void *src, size_t bytes)
 extern "C" int rbpf_get_poses(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.pose, sizeof(double) * 3 * h->d.N) : RBPF_ERR_ARG; }
 extern "C" int rbpf_get_covs(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.cov, sizeof(double) * 9 * h->d.N) : RBPF_ERR_ARG; }
 extern "C" int rbpf_get_weights(rbpf_handle h, double *o) { return h && o ? copy_out(h, o, h->d.weight, sizeof(double) * h->d.N) : RBPF_ERR_ARG; }
-extern "C" int rbpf_set_poses(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.pose, i, sizeof(double) * 3 * h->d.N) : RBPF_ERR_ARG; }
-extern "C" int rbpf_set_covs(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.cov, i, sizeof(double) * 9 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_set_poses(rbpf_handle h, const double *i) { if (h) h->d.use_dup = 0; return h && i ? copy_in(h, h->d.pose, i, sizeof(double) * 3 * h->d.N) : RBPF_ERR_ARG; }
+extern "C" int rbpf_set_covs(rbpf_handle h, const double *i) { if (h) h->d.use_dup = 0; return h && i ? copy_in(h, h->d.cov, i, sizeof(double) * 9 * h->d.N) : RBPF_ERR_ARG; }
 extern "C" int rbpf_set_weights(rbpf_handle h, const double *i) { return h && i ? copy_in(h, h->d.weight, i, sizeof(double) * h->d.N) : RBPF_ERR_ARG; }
 
 extern "C" int rbpf_get_match(rbpf_handle h, double *pose, double *cov, double *score, int32_t *valid, int32_t *best)
@@ -564,6 +568,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_evals = s.match_evals;
     out->match_visits = s.match_visits;
     out->match_points = s.match_points;
+    out->match_runs = s.match_runs;
     return RBPF_OK;
 }
 
@@ -789,5 +794,6 @@ extern "C" int rbpf_checkpoint_read(rbpf_handle h, const char *path)
     CK(cudaMemcpy(d.free_list, fl.data(), sizeof(uint32_t) * d.pool_tiles, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.free_count, &fc, sizeof(int), cudaMemcpyHostToDevice));
     d.step_no = hd.step_no;
+    d.use_dup = 0;
     return RBPF_OK;
 }

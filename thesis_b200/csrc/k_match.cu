@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x + p_offset;
+    if (c.use_dup && !slice_out && c.dup_of[p] != p) return;                // a bit-identical duplicate: result copied afterwards
     const double *pose = c.pose + 3 * (size_t)p, *cov = c.cov + 9 * (size_t)p;
 
     // ---- 0. per-particle frame -------------------------------------------
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             atomicAdd(&c.stats->match_evals, (unsigned long long)(sh->evals + ngroups));
             atomicAdd(&c.stats->match_visits, (unsigned long long)sh->visits);
             atomicAdd(&c.stats->match_points, (unsigned long long)M);
+            atomicAdd(&c.stats->match_runs, 1ull);
         }
         if (!valid) {                                                       // matchScanCustom.m:26-28
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -603,10 +605,27 @@ static void match_set_attr()
     cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb_match_smem_bytes());
 }
 
+// Duplicates of the last resample take their representative's result (the guess is
+// identical, so guess + correction is too).
+__global__ void __launch_bounds__(256) match_copy_dups_kernel(RbCtx c)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.N) return;
+    const int r = c.dup_of[p];
+    if (r == p) return;
+    for (int q = 0; q < 3; q++) c.m_pose[3 * (size_t)p + q] = c.m_pose[3 * (size_t)r + q];
+    for (int q = 0; q < 9; q++) c.m_cov[9 * (size_t)p + q] = c.m_cov[9 * (size_t)r + q];
+    for (int q = 0; q < 4; q++) c.m_best[4 * (size_t)p + q] = c.m_best[4 * (size_t)r + q];
+    c.m_score[p] = c.m_score[r];
+    c.m_valid[p] = c.m_valid[r];
+    if (!c.m_valid[r]) atomicAdd(&c.stats->match_failed, 1ull);
+}
+
 void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)
 {
     match_set_attr();
     match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr, adj);
+    if (c.use_dup) match_copy_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
 }
 
 // Debug/test entry: re-run the matcher for one particle and dump the score slice

@@ -22,7 +22,7 @@ __global__ void init_kernel(RbCtx c)
     }
     if (tid == 0) {
         *c.free_count = (int)c.pool_tiles;
-        RbStats z = {0, 0, 0, 0, 0, 0, 0, 0};
+        RbStats z = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         *c.stats = z;
         RbFlags f = {0, 0, 0, 0, 0, {0, 0, 0}};
         *c.flags = f;

@@ -186,6 +186,26 @@ void rb_launch_resample(const RbCtx &c, const double *weights_all, const double 
     resample_plan_kernel<<<1, RS_THREADS, 0, s>>>(c, weights_all, u01_dev);
 }
 
+// dup_of[j] = first local slot whose ancestor equals slot j's (ancestors are non-decreasing,
+// so that is a lower bound found by bisection).
+__global__ void __launch_bounds__(256) resample_dups_kernel(RbCtx c)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.N) return;
+    int rep = j;
+    if (!c.flags->resample_error && c.flags->did_resample) {
+        const int base = c.rank * c.N;
+        const int a = c.ancestors[base + j];
+        int lo = base, hi = base + j;                 // first index in [base, base + j] with ancestors[idx] >= a
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (c.ancestors[mid] < a) lo = mid + 1; else hi = mid;
+        }
+        rep = lo - base;
+    }
+    c.dup_of[j] = rep;
+}
+
 // Applies the planned ancestors to this rank's particles (local part).
 void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s)
 {
@@ -194,4 +214,5 @@ void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s)
     int blocks = (c.N * 32 + 255) / 256;
     resample_gather_kernel<<<blocks, 256, 0, s>>>(c);
     resample_refs_kernel<<<blocks, 256, 0, s>>>(c);
+    resample_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
 }
