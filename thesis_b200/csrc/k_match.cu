@@ -307,6 +307,25 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         ccx[slot] = qx;
         ccy[slot] = qy;
     }
+#ifndef MT_NO_SHUFFLE
+    // Spread the points: consecutive list entries are consecutive beams (one wall
+    // segment), so the first 64 points of a pass would tell little about the rest.
+    // A stride permutation makes every prefix a sample of the whole sweep and the
+    // abortable passes give up earlier.  Scores are sums: the order changes nothing.
+    __syncthreads();
+    {
+        double *tx_ = reinterpret_cast<double *>(bmg), *ty_ = tx_ + RB_MAXB;     // bmg is free until the dilation
+        const int Mp = sh->M;
+        const int s_ = Mp % 37 ? 37 : (Mp % 41 ? 41 : 43);                      // a prime that does not divide M
+        for (int q = tid; q < Mp; q += MT_THREADS) { tx_[q] = ccx[q]; ty_[q] = ccy[q]; }
+        __syncthreads();
+        for (int q = tid; q < Mp; q += MT_THREADS) {
+            const int src = (int)(((unsigned)q * (unsigned)s_) % (unsigned)Mp);
+            ccx[q] = tx_[src];
+            ccy[q] = ty_[src];
+        }
+    }
+#endif
 
     // ---- 2. occupancy bitmap around the guess cell ---------------------------
     if (adj) {
