@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+REFINE_DEFAULT = 0      # --refine: NDT stage of the matcher on (1) or off (0)
 METRIC = "particle_scan_updates_per_sec"
 UNIT = "updates/s"
 # compulsory cells of the matcher footprint for a 180-degree sweep,
@@ -49,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-particles", type=int, default=0, help="CPU baseline sample (0 = 4 per core)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--refine", type=int, default=REFINE_DEFAULT, choices=[0, 1],
+                    help="NDT refinement stage of the reference matcher (matchScanCustom.m:32-50) after the grid search")
     return ap.parse_args()
 
 
@@ -98,13 +101,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(work, n_particles, max_seconds, beams):
+def cpu_baseline(work, n_particles, max_seconds, beams, refine):
     """The oracle (C port of the reference path, OpenMP over particles) on a
     bounded sample of the same workload.  Returns (updates/s, description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
     cores = O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
+    O.set_refine(bool(refine))
     if n_particles <= 0:
         n_particles = 4 * cores
     f = O.Filter(n_particles, beams, 30)
@@ -146,6 +150,7 @@ def run_reference(args):
     import oracle as O
 
     cores = O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
+    O.set_refine(bool(args.refine))
     n_cpu = args.cpu_particles if args.cpu_particles > 0 else 8 * cores
     n_scans_total = 2 + args.warmup + args.steps
     work = synth.Workload(n_scans_total + 1, args.beams)
@@ -230,9 +235,9 @@ def run_b200(args):
     work = synth.Workload(n_scans, args.beams)
     pool = int(n_local * 26 + 4096)
     if world > 1:
-        ps = ShardedParticleSet(n_local, args.beams, world_tiles=(5, 5), pool_subtiles=pool, device=local_rank, seed=7)
+        ps = ShardedParticleSet(n_local, args.beams, world_tiles=(5, 5), pool_subtiles=pool, device=local_rank, seed=7, ndt_refine=bool(args.refine))
     else:
-        ps = ParticleSet(n_local, args.beams, world_tiles=(5, 5), pool_subtiles=pool, device=local_rank, seed=7)
+        ps = ParticleSet(n_local, args.beams, world_tiles=(5, 5), pool_subtiles=pool, device=local_rank, seed=7, ndt_refine=bool(args.refine))
 
     def barrier():
         if world > 1:
@@ -317,7 +322,9 @@ def run_b200(args):
                        pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
                        match_searches_run_fraction=st["match_runs"] / max(1, n_local * (s - 1)),
                        match_scoring_passes_per_update=st["match_evals"] / max(1, st["match_runs"]),
-                       match_exhaustive_passes_per_update=231,
+                       match_exhaustive_passes_per_update=231, ndt_refine=bool(args.refine),
+                       ndt_evaluations_per_search=st["ndt_evals"] / max(1, st["match_runs"]),
+                       ndt_accepted_fraction=st["ndt_accepted"] / max(1, st["match_runs"]),
                        match_full_pass_equivalents_per_update=st["match_visits"] / max(1, st["match_points"])),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -332,7 +339,7 @@ def run_b200(args):
         "stage_ms_per_step": {k: v / max(nst, 1) for k, v in stage_ms.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams)
+        val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams, args.refine)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     print(json.dumps(line))
     if world > 1:

@@ -54,6 +54,11 @@ typedef enum {
     RBPF_MOTION_UNICYCLE = 2  /* DefaultIMUData.py:25-54   u = (v, w) */
 } rbpf_motion_family;
 
+/* rbpf_config.flags */
+#define RBPF_FLAG_NDT_REFINE 1 /* run the NDT refinement stage of the reference matcher after the grid search
+                                  (matchScanCustom.m:32-50: matchScans(..., 'MaxIterations', 500, 'CellSize', 0.1),
+                                  accepted iff the refined pose passes isValidPose and 2*ndtScore > gridScore) */
+
 typedef struct {
     int32_t n_particles;      /* particles owned by THIS handle (rank-local slice), main.py:44,87 */
     int32_t n_beams;          /* beams per sweep, <= 384 (180 Intel/ACES, 360 Freiburg, 361 UNSW/Bele) */
@@ -64,7 +69,7 @@ typedef struct {
     int32_t device;           /* CUDA device ordinal */
     int32_t rank;             /* rank / world of the particle sharding (0 / 1 on a single GPU) */
     int32_t world;
-    int32_t reserved0;
+    int32_t flags;            /* RBPF_FLAG_* */
     uint64_t stream;          /* cudaStream_t to enqueue on, 0 = legacy default stream */
     uint64_t seed;            /* Philox key for device-side draws when the caller supplies none */
 } rbpf_config;
@@ -85,6 +90,8 @@ typedef struct {
     uint64_t match_runs;      /* matcher searches actually run: duplicates of the last resample are bit-identical
                                  until the next weight stage and take their representative's result */
     uint64_t match_evals;     /* bitmap scoring passes of the matcher (group bounds + member rotations; exhaustive = 231 per match) */
+    uint64_t ndt_evals;       /* NDT score evaluations of the refinement stage (cumulative, searches actually run) */
+    uint64_t ndt_accepted;    /* searches whose refined pose replaced the grid pose (matchScanCustom.m:38-41) */
 } rbpf_stats_t;
 
 /* Replaces `particles = [Robot(eng) for _ in range(NUM_PARTICLES)]` (main.py:87,
@@ -152,6 +159,11 @@ int rbpf_set_weights(rbpf_handle h, const double *in_n);
 /* Matcher results of the last rbpf_scan_match: pose[N*3], cov[N*9] (NaN when
  * invalid), score[N], valid[N], best[N*4] = (i, j, k, n_curr_points). */
 int rbpf_get_match(rbpf_handle h, double *pose_n3, double *cov_n9, double *score_n, int32_t *valid_n, int32_t *best_n4);
+/* NDT stage of the last match (matchScanCustom.m:32-50): out[N*2] = (score evaluations, 1 if the
+ * refined pose replaced the grid pose).  Zeros when the stage is off or the grid match was invalid. */
+int rbpf_get_match_refine(rbpf_handle h, int32_t *out_n2);
+/* Switch the NDT stage on or off for the following matches (initially rbpf_config.flags & RBPF_FLAG_NDT_REFINE). */
+int rbpf_set_refine(rbpf_handle h, int32_t on);
 /* Inject matcher results (pose[N*3], cov[N*9], valid[N]) in place of
  * rbpf_scan_match -- the seam at which the reference calls MATLAB
  * (hybridmap.py:244-256); lets the weighting stage be checked against the

@@ -63,6 +63,8 @@ def lib():
                                     _dp, _dp, _dp, _ip, _ip]
         L.orc_filter_map_update_adj.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int]
         L.orc_match_curr.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, _dp]
+        L.orc_ndt_probe.argtypes = [_dp, _dp]
+        L.orc_ndt_probe.restype = None
         L.orc_motion.argtypes = [C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.orc_resample.argtypes = [_dp, C.c_int, C.c_double, _ip]
         L.orc_filter_new.restype = C.c_void_p
@@ -165,13 +167,13 @@ class Map:
         pose = np.empty(3)
         cov = np.empty(9)
         score = C.c_double()
-        dbg = np.zeros(6, dtype=np.int32)
+        dbg = np.zeros(8, dtype=np.int32)
         sl = np.zeros(SLICE_W * SLICE_W, dtype=np.int32)
         valid = lib().orc_match(self._h, gp, *scan.ptrs(), scan.B, rx, ry, _d(pose)[1], _d(cov)[1],
                                 C.byref(score), _i(dbg), _i(sl))
         return dict(valid=bool(valid), pose=pose, cov=cov.reshape(3, 3), score=score.value,
                     M=int(dbg[0]), best=(int(dbg[1]), int(dbg[2]), int(dbg[3])), nx=int(dbg[4]),
-                    ny=int(dbg[5]), slice=sl.reshape(SLICE_W, SLICE_W))
+                    ny=int(dbg[5]), ndt_evals=int(dbg[6]), ndt_accepted=bool(dbg[7]), slice=sl.reshape(SLICE_W, SLICE_W))
 
 
 def match_adj(guess, scan, prev_xy, rx, ry):
@@ -181,13 +183,32 @@ def match_adj(guess, scan, prev_xy, rx, ry):
     pose = np.empty(3)
     cov = np.empty(9)
     score = C.c_double()
-    dbg = np.zeros(6, dtype=np.int32)
+    dbg = np.zeros(8, dtype=np.int32)
     sl = np.zeros(SLICE_W * SLICE_W, dtype=np.int32)
     valid = lib().orc_match_adj(_d(guess)[1], _d(scan.px)[1], _d(scan.py)[1], scan.B, _d(px)[1], _d(py)[1], len(px),
                                 rx, ry, _d(pose)[1], _d(cov)[1], C.byref(score), _i(dbg), _i(sl))
     return dict(valid=bool(valid), pose=pose, cov=cov.reshape(3, 3), score=score.value, M=int(dbg[0]),
                 best=(int(dbg[1]), int(dbg[2]), int(dbg[3])), nx=int(dbg[4]), ny=int(dbg[5]),
-                slice=sl.reshape(SLICE_W, SLICE_W))
+                ndt_evals=int(dbg[6]), ndt_accepted=bool(dbg[7]), slice=sl.reshape(SLICE_W, SLICE_W))
+
+
+def set_refine(on):
+    """Switch the NDT stage (matchScanCustom.m:32-50) of match()/match_adj()/Filter on or off; returns the old value."""
+    return bool(lib().orc_set_refine(int(bool(on))))
+
+
+def ndt_terms(m, guess, scan, p):
+    """{S, gradient, Hessian, curvature model} of the NDT score of map m at correction p = (cells, cells, rad)."""
+    out = np.zeros(16)
+    pp = np.ascontiguousarray(p, dtype=np.float64)
+    lib().orc_ndt_probe(_d(pp)[1], _d(out)[1])
+    try:
+        m.match(guess, scan, 0.7, 0.7)
+    finally:
+        lib().orc_ndt_probe(None, None)
+    H = np.array([[out[4], out[5], out[6]], [out[5], out[7], out[8]], [out[6], out[8], out[9]]])
+    Cm = np.array([[out[10], out[11], out[12]], [out[11], out[13], out[14]], [out[12], out[14], out[15]]])
+    return dict(S=out[0], grad=out[1:4].copy(), hess=H, model=Cm)
 
 
 def set_threads(n=0):

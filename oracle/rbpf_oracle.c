@@ -488,15 +488,16 @@ static int64_t match_key(int score, int i, int j, int k)
  *              rotation and over the rotation line (+-16 steps) at the best translation,
  *              cross terms zero, plus the lattice quantisation variance.
  *   result     guess + correction, hybridmap.py:253-255.
- * No NDT refinement (matchScanCustom.m:32-50): declared, see DESIGN.md.
+ *   refine     matchScanCustom.m:32-50 : the NDT stage above, when enabled with
+ *              orc_set_refine(1) (off by default).
  * out_pose[3], out_cov[9]; returns 1 if valid else 0.  dbg (nullable) receives
- * {M, best_i, best_j, best_k, nx, ny}; slice (nullable, 29*29 ints) the scores of
+ * {M, best_i, best_j, best_k, nx, ny, ndt_evals, ndt_accepted}; slice (nullable, 29*29 ints) the scores of
  * the translation slice at the best rotation, row j, column i.
  */
 /* Front-end of HybridMap.get_scan_match hybridmap.py:216-228,236,240: the
  * `valid_curr_points` list handed to the matcher.  cx, cy have room for B. */
 static int match_curr(const orc_map *m, const double *guess, const double *px, const double *py,
-                      const double *dist, int B, double *cx, double *cy)
+                      const double *dist, int B, double *cx, double *cy, int *cj)
 {
     int M = 0;
     double c0 = cos(guess[2]), s0 = sin(guess[2]);
@@ -510,7 +511,7 @@ static int match_curr(const orc_map *m, const double *guess, const double *px, c
         double qx = (index_to_distance(ix) + t->cx) - guess[0];               /* :226-228,236 */
         double qy = (index_to_distance(iy) + t->cy) - guess[1];
         if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;               /* :240 */
-        cx[M] = qx; cy[M] = qy; M++;
+        cx[M] = qx; cy[M] = qy; cj[M] = j; M++;
     }
     return M;
 }
@@ -519,18 +520,283 @@ int orc_match_curr(const orc_map *m, const double *guess, const double *px, cons
                    const double *dist, int B, double *out_xy)
 {
     double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
-    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
+    int *cj = (int *)malloc(sizeof(int) * (size_t)B);
+    int M = match_curr(m, guess, px, py, dist, B, cx, cy, cj);
     for (int q = 0; q < M; q++) { out_xy[2 * q] = cx[q]; out_xy[2 * q + 1] = cy[q]; }
-    free(cx); free(cy);
+    free(cx); free(cy); free(cj);
     return M;
 }
+
+/* ---------------------------------------------------- NDT refinement stage -- */
+
+/*
+ * Second half of the reference matcher, matchScanCustom.m:32-50: after the grid
+ * search, `matchScans(curr, ref, 'InitialPose', pose, 'MaxIterations', 500,
+ * 'CellSize', 0.1)` refines the pose continuously and is accepted iff the refined
+ * pose passes isValidPose and 2*ndtScore > gridScore; the covariance stays the
+ * grid stage's.  matchScans is MathWorks' NDT matcher (not in the reference
+ * tree): PARITY UNPINNED.  What follows is OUR restatement of the published
+ * algorithm (Biber & Strasser, "The Normal Distributions Transform", IROS 2003):
+ *   - reference set = the occupancy set the grid stage scores on (proximity
+ *     kernel included), one reference point per set lattice point;
+ *   - NDT cells of 0.1 m = 2x2 lattice points, the four grids shifted by half a
+ *     cell are the four parities of the 2x2 blocks; a block with >= 3 points
+ *     carries a Gaussian (mean, covariance 1/n sum dd^T of its points);
+ *   - score S(p) = sum over curr points and the four blocks containing them of
+ *     exp(-d^T C^-1 d / 2), p = (tx, ty in cells, phi in rad) applied on top of
+ *     the guess; maximised by Newton steps with Levenberg damping on the exact
+ *     gradient and Hessian, from the grid stage's optimum, at most 500 iterations
+ *     (matchScanCustom.m:36), stop when the gain of an accepted step < 1e-6.
+ * Bit-exact contract with the CUDA kernel (k_match.cu mt_ndt_refine): exp/sin/
+ * cos are the polynomial forms below (plain IEEE + - * /), per-beam terms are
+ * summed in the order 12 warps x 32 lanes, xor-butterfly inside a warp, warps
+ * sequentially.
+ */
+#define NDT_MAX_ITERS 500      /* matchScanCustom.m:36 */
+#define NDT_TERMS 16         /* S, gradient (3), Hessian (6), curvature model (6) */
+#define NDT_SLOTS 384          /* 12 warps x 32 lanes: slot = beam index */
+#define NDT_LIMIT 235.0        /* lookups stay inside the occupancy window */
+#define NDT_STEP_T 1e-3       /* cells */
+#define NDT_STEP_R 1e-5       /* rad */
+#define NDT_T1 0.33333333333333331
+#define NDT_T2 0.66666666666666663
+
+static int g_refine = 0;
+/* 1: orc_match()/orc_match_adj() run the NDT stage after the grid stage. */
+int orc_set_refine(int on) { int old = g_refine; g_refine = on; return old; }
+
+/* exp(-e), e >= 0: k = round(-e*log2(e)), Cody-Waite reduction, Taylor to r^13 in
+ * Horner form with fused multiply-adds (fma() is correctly rounded on both sides). */
+static double ndt_exp_neg(double e)
+{
+    if (!(e < 700.0)) return 0.0;
+    double x = -e;
+    double kf = floor(fma(x, 1.4426950408889634, 0.5));
+    double r = fma(-kf, 1.90821492927058770002e-10, fma(-kf, 0.693147180369123816490, x));
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    union { int64_t i; double d; } sc;
+    sc.i = (int64_t)((int)kf + 1023) << 52;                                  /* 2^k, k >= -1010 */
+    return p * sc.d;
+}
+
+/* sin and cos of a small angle (|a| < 1): Taylor series in a^2. */
+static void ndt_sincos(double a, double *sn, double *cs)
+{
+    double z = a * a;
+    double s = -1.0 / 121645100408832000.0;                                  /* 19! */
+    s = s * z + 1.0 / 355687428096000.0;                                     /* 17! */
+    s = s * z - 1.0 / 1307674368000.0;                                       /* 15! */
+    s = s * z + 1.0 / 6227020800.0;
+    s = s * z - 1.0 / 39916800.0;
+    s = s * z + 1.0 / 362880.0;
+    s = s * z - 1.0 / 5040.0;
+    s = s * z + 1.0 / 120.0;
+    s = s * z - 1.0 / 6.0;
+    s = s * z + 1.0;
+    *sn = s * a;
+    double c = 1.0 / 2432902008176640000.0;                                  /* 20! */
+    c = c * z - 1.0 / 6402373705728000.0;                                    /* 18! */
+    c = c * z + 1.0 / 20922789888000.0;                                      /* 16! */
+    c = c * z - 1.0 / 87178291200.0;
+    c = c * z + 1.0 / 479001600.0;
+    c = c * z - 1.0 / 3628800.0;
+    c = c * z + 1.0 / 40320.0;
+    c = c * z - 1.0 / 720.0;
+    c = c * z + 1.0 / 24.0;
+    c = c * z - 0.5;
+    c = c * z + 1.0;
+    *cs = c;
+}
+
+/* S, gradient (3) and curvature C (6: 00 01 02 11 12 22) of the NDT score at p.
+ * C = sum w G J^T B J is the positive semi-definite part of -Hessian (the
+ * majoriser of exp(-e) linearised in e), so every damped step is an ascent
+ * direction even where the narrow Gaussians are not concave.
+ * win = the (2R+1)^2 occupancy window of match_core, centred on the guess cell.
+ * In lattice units (reference points at integers) a curr point (u, v) lies in
+ * the four blocks {n, n+1} x {m, m+1}, n in {iu-1, iu}, m in {iv-1, iv}, iu =
+ * nearest integer: block extent [n-0.5, n+1.5), so that lattice points are
+ * interior.  Each block's Gaussian is weighted by the C1 window w(t) = 1 - 3t^2 +
+ * 2t^3, t = |u - (n+0.5)| (times the same in v): the two parities of an axis sum
+ * to one, the score is continuous where a point changes blocks. */
+static void ndt_eval(const unsigned char *win, int S_, int R_, const double *cx, const double *cy, const int *cj,
+                     int M, double fx, double fy, const double *p, double *tot)
+{
+    static const int orders[5] = {16, 8, 4, 2, 1};
+    double (*slot)[NDT_TERMS] = (double (*)[NDT_TERMS])calloc(NDT_SLOTS, sizeof(double[NDT_TERMS]));
+    double sn, cs;
+    ndt_sincos(p[2], &sn, &cs);
+    for (int q = 0; q < M; q++) {
+        double *a = slot[cj[q]];
+        double X = cs * cx[q] - sn * cy[q], Y = sn * cx[q] + cs * cy[q];
+        double X20 = X * 20.0, Y20 = Y * 20.0;
+        double u = (X + fx) * 20.0 + p[0], v = (Y + fy) * 20.0 + p[1];
+        if (!(fabs(u) < NDT_LIMIT && fabs(v) < NDT_LIMIT)) continue;
+        int iu = (int)floor(u + 0.5), iv = (int)floor(v + 0.5);
+        double f = 0.0, fu = 0.0, fv = 0.0, fuu = 0.0, fuv = 0.0, fvv = 0.0, cuu = 0.0, cuv = 0.0, cvv = 0.0;
+        for (int by = 0; by < 2; by++)
+            for (int bx = 0; bx < 2; bx++) {
+                int nx = iu - 1 + bx, ny = iv - 1 + by;
+                const unsigned char *r0 = win + (size_t)(ny + R_) * S_ + (nx + R_), *r1 = r0 + S_;
+                int pat = r0[0] | (r0[1] << 1) | (r1[0] << 2) | (r1[1] << 3);
+                int n = (pat & 1) + ((pat >> 1) & 1) + ((pat >> 2) & 1) + (pat >> 3);
+                if (n < 3) continue;
+                double mx = 0.5, my = 0.5, Bd = 4.0, Bxy = 0.0;
+                if (n == 3) {
+                    int miss = pat == 14 ? 0 : (pat == 13 ? 1 : (pat == 11 ? 2 : 3));   /* bit = x + 2y of the empty corner */
+                    mx = (miss & 1) ? NDT_T1 : NDT_T2;
+                    my = (miss >> 1) ? NDT_T1 : NDT_T2;
+                    Bd = 6.0;
+                    Bxy = ((miss & 1) == (miss >> 1)) ? 3.0 : -3.0;
+                }
+                double ru = u - (double)nx, rv = v - (double)ny;              /* in [-0.5, 1.5) */
+                double tu = ru - 0.5, tv = rv - 0.5;
+                double au = fmin(fabs(tu), 1.0), av = fmin(fabs(tv), 1.0);
+                double su = tu < 0.0 ? -1.0 : 1.0, sv = tv < 0.0 ? -1.0 : 1.0;
+                double wx = fma(-(au * au), fma(-2.0, au, 3.0), 1.0), wy = fma(-(av * av), fma(-2.0, av, 3.0), 1.0);
+                double wx1 = su * (6.0 * au * (au - 1.0)), wy1 = sv * (6.0 * av * (av - 1.0));
+                double wx2 = fma(12.0, au, -6.0), wy2 = fma(12.0, av, -6.0);
+                double dx = ru - mx, dy = rv - my;
+                double a1 = fma(Bd, dx, Bxy * dy), a2 = fma(Bxy, dx, Bd * dy);
+                double G = ndt_exp_neg(0.5 * fma(dx, a1, dy * a2));
+                double W = wx * wy, WG = W * G, Wu = wx1 * wy, Wv = wx * wy1;
+                double Gu = -(a1 * G), Gv = -(a2 * G);
+                f += WG;
+                fu = fma(-a1, WG, fma(Wu, G, fu));
+                fv = fma(-a2, WG, fma(Wv, G, fv));
+                fuu = fma(fma(a1, a1, -Bd), WG, fma(2.0 * Wu, Gu, fma(wx2 * wy, G, fuu)));
+                fuv = fma(fma(a1, a2, -Bxy), WG, fma(Wv, Gu, fma(Wu, Gv, fma(wx1 * wy1, G, fuv))));
+                fvv = fma(fma(a2, a2, -Bd), WG, fma(2.0 * Wv, Gv, fma(wx * wy2, G, fvv)));
+                cuu = fma(fmax(-wx2, 0.0) * wy, G, fma(WG, Bd, cuu));           /* + concave part of the window */
+                cuv = fma(WG, Bxy, cuv);
+                cvv = fma(wx * fmax(-wy2, 0.0), G, fma(WG, Bd, cvv));
+            }
+        /* chain rule to p = (tx, ty, phi): du/dphi = -Y20, dv/dphi = X20, second derivatives -X20, -Y20 */
+        double J3x = -Y20, J3y = X20;
+        double h13 = fuu * J3x + fuv * J3y, h23 = fuv * J3x + fvv * J3y;
+        double c13 = cuu * J3x + cuv * J3y, c23 = cuv * J3x + cvv * J3y;
+        a[0] = f;
+        a[1] = fu;
+        a[2] = fv;
+        a[3] = fu * J3x + fv * J3y;
+        a[4] = fuu;
+        a[5] = fuv;
+        a[6] = h13;
+        a[7] = fvv;
+        a[8] = h23;
+        a[9] = (J3x * h13 + J3y * h23) - (fu * X20 + fv * Y20);
+        a[10] = cuu;
+        a[11] = cuv;
+        a[12] = c13;
+        a[13] = cvv;
+        a[14] = c23;
+        a[15] = J3x * c13 + J3y * c23;
+    }
+    for (int e = 0; e < NDT_TERMS; e++) {
+        double t = 0.0;
+        for (int w = 0; w < NDT_SLOTS / 32; w++) {
+            double l[32], n2[32];
+            for (int i = 0; i < 32; i++) l[i] = slot[32 * w + i][e];
+            for (int o = 0; o < 5; o++) {
+                for (int i = 0; i < 32; i++) n2[i] = l[i] + l[i ^ orders[o]];
+                memcpy(l, n2, sizeof l);
+            }
+            t = w ? t + l[0] : l[0];
+        }
+        tot[e] = t;
+    }
+    free(slot);
+}
+
+/* Solve A d = g (A symmetric: 00 10 20 11 21 22) by Cholesky with reciprocal pivots;
+ * 0 when A is not positive definite. */
+static int ndt_solve(double A00, double A10, double A20, double A11, double A21, double A22, const double *g, double *d)
+{
+    if (!(A00 > 1e-12)) return 0;
+    double i00 = 1.0 / sqrt(A00), l10 = A10 * i00, l20 = A20 * i00;
+    double t1 = A11 - l10 * l10;
+    if (!(t1 > 1e-12)) return 0;
+    double i11 = 1.0 / sqrt(t1), l21 = (A21 - l20 * l10) * i11;
+    double t2 = (A22 - l20 * l20) - l21 * l21;
+    if (!(t2 > 1e-12)) return 0;
+    double i22 = 1.0 / sqrt(t2);
+    double y0 = g[0] * i00, y1 = (g[1] - l10 * y0) * i11, y2 = ((g[2] - l20 * y0) - l21 * y1) * i22;
+    d[2] = y2 * i22;
+    d[1] = (y1 - l21 * d[2]) * i11;
+    d[0] = ((y0 - l10 * d[1]) - l20 * d[2]) * i00;
+    return 1;
+}
+
+/* p (in/out) = correction (cells, cells, rad); returns the score at the final p, *evals = score evaluations.
+ * Every iteration proposes the Newton step (-H d = g) when -H is positive definite and the step is short
+ * (near the optimum: quadratic convergence), otherwise the damped step of the curvature model
+ * ((C + lam diag C) d = g); a proposal is kept only if the score increases. */
+static double ndt_refine(const unsigned char *win, int S_, int R_, const double *cx, const double *cy, const int *cj,
+                         int M, double fx, double fy, double *p, int *evals)
+{
+    double t[NDT_TERMS], tn[NDT_TERMS], d[3], pn[3], lam = 1e-3;
+    ndt_eval(win, S_, R_, cx, cy, cj, M, fx, fy, p, t);
+    int ne = 1, newton_ok = 1;
+    for (int it = 0; it < NDT_MAX_ITERS; it++) {
+        int newton = newton_ok && ndt_solve(-t[4], -t[5], -t[6], -t[7], -t[8], -t[9], t + 1, d) &&
+                     fabs(d[0]) < 1.0 && fabs(d[1]) < 1.0 && fabs(d[2]) < 0.01;
+        int ok = newton;
+        if (!newton)
+            ok = ndt_solve(t[10] + lam * t[10], t[11], t[12], t[13] + lam * t[13], t[14], t[15] + lam * t[15], t + 1, d);
+        if (!ok && !newton && !(t[10] > 0.0)) break;                           /* no point carries a Gaussian */
+        if (ok) {
+            if (fabs(d[0]) < NDT_STEP_T && fabs(d[1]) < NDT_STEP_T && fabs(d[2]) < NDT_STEP_R) break;   /* step below 50 um / 1e-5 rad */
+            for (int a = 0; a < 3; a++) pn[a] = p[a] + d[a];
+            ok = fabs(pn[0]) < 64.0 && fabs(pn[1]) < 64.0 && fabs(pn[2]) < 1.0;
+        }
+        if (ok) {
+            ndt_eval(win, S_, R_, cx, cy, cj, M, fx, fy, pn, tn);
+            ne++;
+            ok = tn[0] > t[0];
+        }
+        if (ok) {
+            double gain = tn[0] - t[0];
+            memcpy(t, tn, sizeof t);
+            memcpy(p, pn, sizeof pn);
+            if (!newton) lam = lam * 0.1 < 1e-3 ? 1e-3 : lam * 0.1;
+            newton_ok = 1;
+            if (gain < 1e-6) break;
+        } else if (newton) {
+            newton_ok = 0;                                                     /* same point again with the model step */
+        } else {
+            lam *= 10.0;
+            if (lam > 1e9) break;
+        }
+    }
+    *evals = ne;
+    return t[0];
+}
+
+/* Test hook: while set, every match also evaluates the NDT terms at p (cells, cells,
+ * rad) into out16 = {S, gradient 3, Hessian 6, curvature model 6}.  Not thread-safe. */
+static const double *g_probe_p = NULL;
+static double *g_probe_out = NULL;
+void orc_ndt_probe(const double *p, double *out16) { g_probe_p = p; g_probe_out = out16; }
 
 /* Shared search core.  Occupancy comes either from the particle's map (m != NULL,
  * scan-to-map, hybridmap.py:210-261) or from the previous scan's endpoints
  * rasterised on the same lattice (ref_x/ref_y, n_ref; scan-to-scan,
  * hybridmap.py:147-191). */
 static int match_core(const orc_map *m, const double *ref_x, const double *ref_y, int n_ref,
-                      const double *guess, double *cx, double *cy, int M, double rx, double ry,
+                      const double *guess, double *cx, double *cy, const int *cj, int M, double rx, double ry,
                       double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
 {
     /* cell of the guess position and the guess's offset inside it */
@@ -605,9 +871,9 @@ static int match_core(const orc_map *m, const double *ref_x, const double *ref_y
                 if (key > best) { best = key; bi = i; bj = j; bk = k; }
             }
     }
-    free(win);
     int bs = (int)(best >> 32);
-    if (dbg) { dbg[0] = M; dbg[1] = bi; dbg[2] = bj; dbg[3] = bk; dbg[4] = nx; dbg[5] = ny; }
+    if (g_probe_p) ndt_eval(win, S, R, cx, cy, cj, M, fx, fy, g_probe_p, g_probe_out);
+    if (dbg) { dbg[0] = M; dbg[1] = bi; dbg[2] = bj; dbg[3] = bk; dbg[4] = nx; dbg[5] = ny; dbg[6] = 0; dbg[7] = 0; }
     if (slice)
         for (int j = 0; j < W; j++)
             for (int i = 0; i < W; i++) slice[j * W + i] = vol[((size_t)(bk + nk) * W + j) * W + i];
@@ -645,8 +911,23 @@ static int match_core(const orc_map *m, const double *ref_x, const double *ref_y
         out_cov[1] = out_cov[3] = ((double)Wxy / (double)W0 - mx * my) * q;
         out_cov[8] = ((double)T2 / (double)T0 - mt * mt) * qt + qt / 12.0;
         *out_score = (double)bs;
+        if (g_refine) {                                                       /* matchScanCustom.m:32-50 */
+            double pr[3] = {(double)bi, (double)bj, bk * step};
+            int evals = 0;
+            double Sn = ndt_refine(win, S, R, cx, cy, cj, M, fx, fy, pr, &evals);
+            int ok = fabs(pr[0] * CS) < rx && fabs(pr[1] * CS) < ry && fabs(pr[2]) < ROT_RANGE &&
+                     (pr[0] != 0.0 || pr[1] != 0.0 || pr[2] != 0.0);           /* :38 isValidPose(new_pose) */
+            int accepted = ok && Sn * 2.0 > (double)bs;                         /* :39 */
+            if (accepted) {
+                out_pose[0] = guess[0] + pr[0] * CS;
+                out_pose[1] = guess[1] + pr[1] * CS;
+                out_pose[2] = guess[2] + pr[2];
+                *out_score = Sn;
+            }
+            if (dbg) { dbg[6] = evals; dbg[7] = accepted; }
+        }
     }
-    free(vol); free(bx); free(by);
+    free(win); free(vol); free(bx); free(by);
     return valid;
 }
 
@@ -655,9 +936,10 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
               double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
 {
     double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
-    int M = match_curr(m, guess, px, py, dist, B, cx, cy);
-    int v = match_core(m, NULL, NULL, 0, guess, cx, cy, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
-    free(cx); free(cy);
+    int *cj = (int *)malloc(sizeof(int) * (size_t)B);
+    int M = match_curr(m, guess, px, py, dist, B, cx, cy, cj);
+    int v = match_core(m, NULL, NULL, 0, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    free(cx); free(cy); free(cj);
     return v;
 }
 
@@ -670,6 +952,7 @@ int orc_match_adj(const double *guess, const double *px, const double *py, int B
                   double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
 {
     double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
+    int *cj = (int *)malloc(sizeof(int) * (size_t)B);
     double c0 = cos(guess[2]), s0 = sin(guess[2]);
     int M = 0;
     for (int j = 0; j < B; j++) {
@@ -677,10 +960,10 @@ int orc_match_adj(const double *guess, const double *px, const double *py, int B
         xform(c0, s0, guess[0], guess[1], px[j], py[j], &gx, &gy);
         double qx = gx - guess[0], qy = gy - guess[1];
         if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;
-        cx[M] = qx; cy[M] = qy; M++;
+        cx[M] = qx; cy[M] = qy; cj[M] = j; M++;
     }
-    int v = match_core(NULL, prev_x, prev_y, n_prev, guess, cx, cy, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
-    free(cx); free(cy);
+    int v = match_core(NULL, prev_x, prev_y, n_prev, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    free(cx); free(cy); free(cj);
     return v;
 }
 

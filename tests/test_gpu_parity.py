@@ -298,6 +298,91 @@ def test_match_against_oracle(PS, golden):
         assert np.array_equal(ps.match_slice(i), o["slice"])
 
 
+def _refine_case(PS, golden, N=16):
+    ps, m = seeded(PS, golden, N)
+    rng = np.random.default_rng(15)
+    base = np.array([0.6, 0.15, 0.1])
+    poses = base + rng.normal(0, [0.15, 0.15, 0.08], (N, 3))
+    covs = np.zeros((N, 3, 3))
+    covs[:, 0, 0] = covs[:, 1, 1] = rng.uniform(0.002, 0.01, N) ** 2
+    covs[1] = np.diag([1.0, 1.0, 1.0])
+    ps.poses = poses
+    ps.covs = covs
+    return ps, m, poses, covs
+
+
+def test_match_ndt_refine_against_oracle(PS, golden):
+    """NDT stage (matchScanCustom.m:32-50) after the grid search: same number of score
+    evaluations, same accept decision, same refined pose and NDT score as the oracle;
+    the covariance stays the grid stage's.  The arithmetic is shared polynomial
+    exp/sin/cos in a fixed summation order, so the comparison is bit-exact."""
+    N = 16
+    ps, m, poses, covs = _refine_case(PS, golden, N)
+    s = oscan(golden, 4)
+    ps.set_scan(*scan_of(golden, 4))
+    ps.set_refine(True)
+    ps.scan_match()
+    res = ps.match_result()
+    old = O.set_refine(True)
+    try:
+        outs = [m.match(poses[i], s, *O.pose_range(covs[i])) for i in range(N)]
+    finally:
+        O.set_refine(old)
+    grid = [m.match(poses[i], s, *O.pose_range(covs[i])) for i in range(N)]
+    assert any(o["ndt_accepted"] for o in outs) and any(o["ndt_evals"] > 3 for o in outs)
+    for i, (o, g) in enumerate(zip(outs, grid)):
+        b = res["best"][i]
+        assert (int(b[0]), int(b[1]), int(b[2])) == o["best"] and bool(res["valid"][i]) == o["valid"]
+        assert int(res["ndt_evals"][i]) == o["ndt_evals"], "particle %d" % i
+        assert bool(res["ndt_accepted"][i]) == o["ndt_accepted"]
+        assert np.array_equal(res["pose"][i], o["pose"]), "particle %d: %r vs %r" % (i, res["pose"][i], o["pose"])
+        assert res["score"][i] == o["score"]
+        if o["valid"]:
+            assert np.array_equal(res["cov"][i], g["cov"].reshape(3, 3))      # matchScanCustom.m:22 covariance of the grid stage
+            if o["ndt_accepted"]:
+                rx, ry = O.pose_range(covs[i])
+                d = o["pose"] - poses[i]
+                assert abs(d[0]) < rx and abs(d[1]) < ry and abs(d[2]) < np.pi / 6 and 2 * o["score"] > g["score"]
+            else:
+                assert np.array_equal(o["pose"], g["pose"]) and o["score"] == g["score"]
+    # switching the stage off again restores the grid result
+    ps.set_refine(False)
+    ps.scan_match()
+    check_match(ps, [m] * N, poses, covs, s, range(N))
+    assert not ps.match_result()["ndt_evals"].any()
+
+
+def test_match_adj_ndt_refine_against_oracle(PS, golden):
+    """NDT stage on the scan-to-previous-scan variant: the curr points are raw endpoints
+    (cos/sin of the guess heading come from two maths libraries), hence a tolerance."""
+    N = 10
+    rng = np.random.default_rng(8)
+    ps = PS(N, 180, pool_subtiles=64, ndt_refine=True)
+    prev_pose = np.array([0.5, 0.1, 0.2])
+    gx, gy = O.transform(prev_pose, oscan(golden, 3))
+    prev_xy = np.column_stack((gx, gy))
+    base = np.array([0.55, 0.12, -0.25])
+    poses = base + rng.normal(0, [0.1, 0.1, 0.05], (N, 3))
+    covs = np.zeros((N, 3, 3))
+    covs[:, 0, 0] = covs[:, 1, 1] = rng.uniform(0.002, 0.01, N) ** 2
+    ps.poses = poses
+    ps.covs = covs
+    s = oscan(golden, 4)
+    ps.set_scan(*scan_of(golden, 4))
+    ps.scan_match(prev_xy)
+    res = ps.match_result()
+    old = O.set_refine(True)
+    try:
+        outs = [O.match_adj(poses[i], s, prev_xy, *O.pose_range(covs[i])) for i in range(N)]
+    finally:
+        O.set_refine(old)
+    assert any(o["ndt_accepted"] for o in outs)
+    for i, o in enumerate(outs):
+        assert bool(res["valid"][i]) == o["valid"] and bool(res["ndt_accepted"][i]) == o["ndt_accepted"]
+        assert np.allclose(res["pose"][i], o["pose"], rtol=0, atol=1e-7)
+        assert np.isclose(res["score"][i], o["score"], rtol=1e-7)
+
+
 def test_match_empty_map_is_invalid(PS, golden):
     """No occupied cell -> every score 0 -> best is the zero correction ->
     isValidPose rejects it (matchScanCustom.m:55) -> NaN covariance."""

@@ -18,7 +18,7 @@ class RbpfConfig(C.Structure):
     _fields_ = [
         ("n_particles", C.c_int32), ("n_beams", C.c_int32), ("n_samples", C.c_int32),
         ("world_tiles_x", C.c_int32), ("world_tiles_y", C.c_int32), ("pool_subtiles", C.c_uint32),
-        ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("reserved0", C.c_int32),
+        ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("flags", C.c_int32),
         ("stream", C.c_uint64), ("seed", C.c_uint64),
     ]
 
@@ -30,7 +30,7 @@ class RbpfStats(C.Structure):
         ("match_failed", C.c_uint64), ("shared_refs", C.c_uint64), ("total_refs", C.c_uint64),
         ("refcount_sum", C.c_uint64), ("match_visits", C.c_uint64), ("match_points", C.c_uint64),
         ("match_runs", C.c_uint64),
-        ("match_evals", C.c_uint64),
+        ("match_evals", C.c_uint64), ("ndt_evals", C.c_uint64), ("ndt_accepted", C.c_uint64),
     ]
 
 
@@ -60,6 +60,8 @@ SIGNATURES = {
     "rbpf_set_covs": (C.c_int, [_H, _dp]),
     "rbpf_set_weights": (C.c_int, [_H, _dp]),
     "rbpf_get_match": (C.c_int, [_H, _dp, _dp, _dp, _ip, _ip]),
+    "rbpf_get_match_refine": (C.c_int, [_H, _ip]),
+    "rbpf_set_refine": (C.c_int, [_H, C.c_int32]),
     "rbpf_set_match": (C.c_int, [_H, _dp, _dp, _ip]),
     "rbpf_get_match_slice": (C.c_int, [_H, C.c_int32, _ip]),
     "rbpf_export_tile": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, _dp, _ip]),

@@ -56,7 +56,8 @@
 #define RB_SLICE_W (2 * RB_NT_MAX + 1)      // 29
 
 struct RbStats {                            // device-side counters
-    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points, match_runs;
+    unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points, match_runs,
+        ndt_evals, ndt_accepted;
 };
 
 struct RbFlags {                            // device-side status words
@@ -95,7 +96,7 @@ struct RbCtx {
     int nk;
     double rot_step;
     double *m_pose, *m_cov, *m_score;
-    int *m_valid, *m_best;
+    int *m_valid, *m_best, *m_refine;       // m_refine: {NDT evaluations, refined pose accepted} per particle
     // scan-to-previous-scan matching (hybridmap.py:147-191): global endpoints of the previous scan
     const double *prev_x, *prev_y;
     int n_prev;
@@ -109,6 +110,7 @@ struct RbCtx {
     // page table) until the next weight stage: dup_of[j] = first local slot with the same
     // ancestor.  The matcher runs once per representative and its result is copied.
     int *dup_of;                            // N
+    int refine;                             // host-set: run the NDT stage (matchScanCustom.m:32-50) after the grid search
     int use_dup;                            // host-set: dup_of is valid for this launch
     RbStats *stats;
     RbFlags *flags;

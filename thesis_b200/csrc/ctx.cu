@@ -164,6 +164,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     d.ux_max = d.tiles_x * RB_DIM; d.uy_max = d.tiles_y * RB_DIM;
     d.pool_tiles = cfg->pool_subtiles;
     d.seed = cfg->seed;
+    d.refine = (cfg->flags & RBPF_FLAG_NDT_REFINE) ? 1 : 0;
     d.step_no = 0;
     d.nk = rot_count_host();
     d.rot_step = rot_step_host();
@@ -184,7 +185,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_rot, 2 * (2 * d.nk + 1));
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
-    A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4);
+    A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
     A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);
     A(h->d_z, N * d.K * 3);
@@ -226,6 +227,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         return fail(RBPF_ERR_CUDA, "table upload failed");
     h->mg_n = h->mg_tiles = 0;
     cudaMemsetAsync(h->d_mg_mark, 0xFF, sizeof(uint32_t) * (size_t)d.pool_tiles, h->stream);
+    cudaMemsetAsync(d.m_refine, 0, sizeof(int) * 2 * (size_t)N, h->stream);
     rb_launch_init(d, h->stream);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, std::string("init: ") + cudaGetErrorString(e));
@@ -489,6 +491,19 @@ extern "C" int rbpf_get_match(rbpf_handle h, double *pose, double *cov, double *
     return rc;
 }
 
+extern "C" int rbpf_get_match_refine(rbpf_handle h, int32_t *out)
+{
+    if (!h || !out) return RBPF_ERR_ARG;
+    return copy_out(h, out, h->d.m_refine, sizeof(int) * 2 * (size_t)h->d.N);
+}
+
+extern "C" int rbpf_set_refine(rbpf_handle h, int32_t on)
+{
+    if (!h) return RBPF_ERR_ARG;
+    h->d.refine = on ? 1 : 0;
+    return RBPF_OK;
+}
+
 extern "C" int rbpf_set_match(rbpf_handle h, const double *pose, const double *cov, const int32_t *valid)
 {
     if (!h || !pose || !cov || !valid) return RBPF_ERR_ARG;
@@ -569,6 +584,8 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_visits = s.match_visits;
     out->match_points = s.match_points;
     out->match_runs = s.match_runs;
+    out->ndt_evals = s.ndt_evals;
+    out->ndt_accepted = s.ndt_accepted;
     return RBPF_OK;
 }
 

@@ -230,10 +230,292 @@ __device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, co
     }
 }
 
+// curr point of beam j relative to the guess position (hybridmap.py:216-228,236,240; adj: :165-172)
+__device__ __forceinline__ bool mt_curr_point(const RbCtx &c, const MatchShared *sh, unsigned long long exists, int j, int adj,
+                                              double &qx, double &qy)
+{
+    const double d = c.dist[j];
+    double gx, gy;
+    rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, c.px[j], c.py[j], gx, gy);
+    if (adj) {                                                             // hybridmap.py:165-172
+        qx = gx - sh->gx; qy = gy - sh->gy;
+        return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R;
+    }
+    if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) return false;
+    int tx, ty, ix, iy;
+    rb_read_axis(gx, tx, ix);
+    rb_read_axis(gy, ty, iy);
+    if (!rb_tile_exists(c, exists, tx, ty)) return false;
+    qx = rb_cell_corner(ix, tx) - sh->gx; qy = rb_cell_corner(iy, ty) - sh->gy;
+    return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R;
+}
+
+// ---- NDT refinement stage (matchScanCustom.m:32-50) --------------------------------
+// Restated in oracle/rbpf_oracle.c (ndt_eval / ndt_refine), PARITY UNPINNED against
+// MathWorks matchScans, bit-exact against the oracle: exp / sin / cos are the same
+// polynomials in plain IEEE arithmetic, thread = beam, per-beam terms are summed by an
+// xor-butterfly inside each warp and then over the warps in order.
+#define NDT_TERMS 16
+#define NDT_MAX_ITERS 500
+#define NDT_LIMIT 235.0
+#define NDT_STEP_T 1e-3
+#define NDT_STEP_R 1e-5
+#define NDT_T1 0.33333333333333331
+#define NDT_T2 0.66666666666666663
+
+__device__ __forceinline__ double ndt_exp_neg(double e)
+{
+    if (!(e < 700.0)) return 0.0;
+    const double x = -e;
+    const double kf = floor(fma(x, 1.4426950408889634, 0.5));
+    const double r = fma(-kf, 1.90821492927058770002e-10, fma(-kf, 0.693147180369123816490, x));
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * __longlong_as_double((long long)((int)kf + 1023) << 52);
+}
+
+__device__ __forceinline__ void ndt_sincos(double a, double &sn, double &cs)
+{
+    const double z = a * a;
+    double s = -1.0 / 121645100408832000.0;
+    s = s * z + 1.0 / 355687428096000.0;
+    s = s * z - 1.0 / 1307674368000.0;
+    s = s * z + 1.0 / 6227020800.0;
+    s = s * z - 1.0 / 39916800.0;
+    s = s * z + 1.0 / 362880.0;
+    s = s * z - 1.0 / 5040.0;
+    s = s * z + 1.0 / 120.0;
+    s = s * z - 1.0 / 6.0;
+    s = s * z + 1.0;
+    sn = s * a;
+    double c = 1.0 / 2432902008176640000.0;
+    c = c * z - 1.0 / 6402373705728000.0;
+    c = c * z + 1.0 / 20922789888000.0;
+    c = c * z - 1.0 / 87178291200.0;
+    c = c * z + 1.0 / 479001600.0;
+    c = c * z - 1.0 / 3628800.0;
+    c = c * z + 1.0 / 40320.0;
+    c = c * z - 1.0 / 720.0;
+    c = c * z + 1.0 / 24.0;
+    c = c * z - 0.5;
+    c = c * z + 1.0;
+    cs = c;
+}
+
+// One beam's terms (score, gradient, Hessian, curvature model) at p, folded over the
+// warp; lane 2e of every warp writes the warp's sum of term e to red[warp][e].
+__device__ __forceinline__ void ndt_partial(const uint32_t *__restrict__ bm, double *red, int xoff0, double fx, double fy,
+                                            bool has, double cx, double cy, double p0, double p1, double sn, double cs)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a[NDT_TERMS];
+#pragma unroll
+    for (int e = 0; e < NDT_TERMS; e++) a[e] = 0.0;
+    if (has) {
+        const double X = cs * cx - sn * cy, Y = sn * cx + cs * cy;
+        const double X20 = X * 20.0, Y20 = Y * 20.0;
+        const double u = (X + fx) * 20.0 + p0, v = (Y + fy) * 20.0 + p1;
+        if (fabs(u) < NDT_LIMIT && fabs(v) < NDT_LIMIT) {
+            const int iu = __double2int_rd(u + 0.5), iv = __double2int_rd(v + 0.5);
+            const int bx0 = iu - 1 + xoff0, by0 = iv - 1 + RB_WIN_R;
+            uint32_t rows[3];
+#pragma unroll
+            for (int dr = 0; dr < 3; dr++) {
+                const int w = (by0 + dr) * RB_BM_STRIDE + (bx0 >> 5);
+                rows[dr] = __funnelshift_r(bm[w], bm[w + 1], bx0 & 31) & 7u;
+            }
+            double f = 0.0, fu = 0.0, fv = 0.0, fuu = 0.0, fuv = 0.0, fvv = 0.0, cuu = 0.0, cuv = 0.0, cvv = 0.0;
+#pragma unroll
+            for (int by = 0; by < 2; by++)
+#pragma unroll
+                for (int bx = 0; bx < 2; bx++) {
+                    const int pat = (int)((rows[by] >> bx) & 3u) | ((int)((rows[by + 1] >> bx) & 3u) << 2);
+                    const int n = __popc(pat);
+                    if (n < 3) continue;
+                    double mx = 0.5, my = 0.5, Bd = 4.0, Bxy = 0.0;
+                    if (n == 3) {
+                        const int miss = pat == 14 ? 0 : (pat == 13 ? 1 : (pat == 11 ? 2 : 3));
+                        mx = (miss & 1) ? NDT_T1 : NDT_T2;
+                        my = (miss >> 1) ? NDT_T1 : NDT_T2;
+                        Bd = 6.0;
+                        Bxy = ((miss & 1) == (miss >> 1)) ? 3.0 : -3.0;
+                    }
+                    const double ru = u - (double)(iu - 1 + bx), rv = v - (double)(iv - 1 + by);
+                    const double tu = ru - 0.5, tv = rv - 0.5;
+                    const double au = fmin(fabs(tu), 1.0), av = fmin(fabs(tv), 1.0);
+                    const double su = tu < 0.0 ? -1.0 : 1.0, sv = tv < 0.0 ? -1.0 : 1.0;
+                    const double wx = fma(-(au * au), fma(-2.0, au, 3.0), 1.0), wy = fma(-(av * av), fma(-2.0, av, 3.0), 1.0);
+                    const double wx1 = su * (6.0 * au * (au - 1.0)), wy1 = sv * (6.0 * av * (av - 1.0));
+                    const double wx2 = fma(12.0, au, -6.0), wy2 = fma(12.0, av, -6.0);
+                    const double dx = ru - mx, dy = rv - my;
+                    const double a1 = fma(Bd, dx, Bxy * dy), a2 = fma(Bxy, dx, Bd * dy);
+                    const double G = ndt_exp_neg(0.5 * fma(dx, a1, dy * a2));
+                    const double W = wx * wy, WG = W * G, Wu = wx1 * wy, Wv = wx * wy1;
+                    const double Gu = -(a1 * G), Gv = -(a2 * G);
+                    f += WG;
+                    fu = fma(-a1, WG, fma(Wu, G, fu));
+                    fv = fma(-a2, WG, fma(Wv, G, fv));
+                    fuu = fma(fma(a1, a1, -Bd), WG, fma(2.0 * Wu, Gu, fma(wx2 * wy, G, fuu)));
+                    fuv = fma(fma(a1, a2, -Bxy), WG, fma(Wv, Gu, fma(Wu, Gv, fma(wx1 * wy1, G, fuv))));
+                    fvv = fma(fma(a2, a2, -Bd), WG, fma(2.0 * Wv, Gv, fma(wx * wy2, G, fvv)));
+                    cuu = fma(fmax(-wx2, 0.0) * wy, G, fma(WG, Bd, cuu));
+                    cuv = fma(WG, Bxy, cuv);
+                    cvv = fma(wx * fmax(-wy2, 0.0), G, fma(WG, Bd, cvv));
+                }
+            const double J3x = -Y20, J3y = X20;
+            const double h13 = fuu * J3x + fuv * J3y, h23 = fuv * J3x + fvv * J3y;
+            const double c13 = cuu * J3x + cuv * J3y, c23 = cuv * J3x + cvv * J3y;
+            a[0] = f; a[1] = fu; a[2] = fv; a[3] = fu * J3x + fv * J3y;
+            a[4] = fuu; a[5] = fuv; a[6] = h13; a[7] = fvv; a[8] = h23;
+            a[9] = (J3x * h13 + J3y * h23) - (fu * X20 + fv * Y20);
+            a[10] = cuu; a[11] = cuv; a[12] = c13; a[13] = cvv; a[14] = c23;
+            a[15] = J3x * c13 + J3y * c23;
+        }
+    }
+    // warp reduction: a butterfly whose every step halves the terms a lane carries
+    // (same pair sums as the plain xor-butterfly); lane l ends with term l >> 1.
+#define NDT_FOLD(HALF, O)                                                        \
+    {                                                                            \
+        const bool up = lane & (O);                                              \
+        _Pragma("unroll") for (int i = 0; i < (HALF); i++) {                     \
+            const double send = up ? a[i] : a[i + (HALF)];                       \
+            const double keep = up ? a[i + (HALF)] : a[i];                       \
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));               \
+        }                                                                        \
+    }
+    NDT_FOLD(8, 16)
+    NDT_FOLD(4, 8)
+    NDT_FOLD(2, 4)
+    NDT_FOLD(1, 2)
+#undef NDT_FOLD
+    a[0] = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+    if (!(lane & 1)) red[warp * NDT_TERMS + (lane >> 1)] = a[0];
+}
+
+__device__ __forceinline__ bool ndt_solve(double A00, double A10, double A20, double A11, double A21, double A22,
+                                          const double *g, double *d)
+{
+    if (!(A00 > 1e-12)) return false;
+    const double i00 = 1.0 / sqrt(A00), l10 = A10 * i00, l20 = A20 * i00;
+    const double t1 = A11 - l10 * l10;
+    if (!(t1 > 1e-12)) return false;
+    const double i11 = 1.0 / sqrt(t1), l21 = (A21 - l20 * l10) * i11;
+    const double t2 = (A22 - l20 * l20) - l21 * l21;
+    if (!(t2 > 1e-12)) return false;
+    const double i22 = 1.0 / sqrt(t2);
+    const double y0 = g[0] * i00, y1 = (g[1] - l10 * y0) * i11, y2 = ((g[2] - l20 * y0) - l21 * y1) * i22;
+    d[2] = y2 * i22;
+    d[1] = (y1 - l21 * d[2]) * i11;
+    d[0] = ((y0 - l10 * d[1]) - l20 * d[2]) * i00;
+    return true;
+}
+
+// The ascent loop of the oracle's ndt_refine() as a coroutine: every thread takes part in
+// the score evaluations, warp 0 alone (all lanes alike) owns the optimiser state, decides,
+// and posts the next correction to evaluate -- or the end -- in ctl[].
+//   red : MT_WARPS x NDT_TERMS doubles, ctl : 8 doubles {go, p0, p1, p2, S, evals, sin p2, cos p2}.
+__device__ __noinline__ void ndt_refine(const uint32_t *__restrict__ bm, double *red, double *ctl, int xoff0, double fx,
+                                        double fy, bool has, double cx, double cy, double q0, double q1, double q2)
+{
+    const int lane = threadIdx.x & 31;
+    const bool boss = threadIdx.x < 32;
+    double t[NDT_TERMS], p[3] = {q0, q1, q2}, pn[3] = {q0, q1, q2}, d[3], lam = 1e-3;
+    int ne = 0, it = 0;
+    bool newton_ok = true, newton = false, first = true;
+    double sn, cs;
+    ndt_sincos(q2, sn, cs);
+    for (;;) {
+        ndt_partial(bm, red, xoff0, fx, fy, has, cx, cy, pn[0], pn[1], sn, cs);
+        __syncthreads();
+        if (boss) {
+            double s = 0.0, tn[NDT_TERMS];
+            if (lane < NDT_TERMS) {
+                s = red[lane];
+                for (int w = 1; w < MT_WARPS; w++) s = s + red[w * NDT_TERMS + lane];
+            }
+#pragma unroll
+            for (int e = 0; e < NDT_TERMS; e++) tn[e] = __shfl_sync(0xffffffffu, s, e);
+            ne++;
+            bool done = false;
+            // ---- the evaluation that just came back (oracle: second half of the loop body)
+            if (first) {
+                first = false;
+#pragma unroll
+                for (int e = 0; e < NDT_TERMS; e++) t[e] = tn[e];
+            } else {
+                if (tn[0] > t[0]) {
+                    const double gain = tn[0] - t[0];
+#pragma unroll
+                    for (int e = 0; e < NDT_TERMS; e++) t[e] = tn[e];
+                    for (int q = 0; q < 3; q++) p[q] = pn[q];
+                    if (!newton) lam = lam * 0.1 < 1e-3 ? 1e-3 : lam * 0.1;
+                    newton_ok = true;
+                    if (gain < 1e-6) done = true;
+                } else if (newton) {
+                    newton_ok = false;
+                } else {
+                    lam *= 10.0;
+                    if (lam > 1e9) done = true;
+                }
+                it++;
+            }
+            // ---- iterations that need no evaluation, up to the next proposal (first half)
+            bool go = false;
+            while (!done && it < NDT_MAX_ITERS) {
+                newton = newton_ok && ndt_solve(-t[4], -t[5], -t[6], -t[7], -t[8], -t[9], t + 1, d) &&
+                         fabs(d[0]) < 1.0 && fabs(d[1]) < 1.0 && fabs(d[2]) < 0.01;
+                bool ok = newton;
+                if (!newton)
+                    ok = ndt_solve(t[10] + lam * t[10], t[11], t[12], t[13] + lam * t[13], t[14], t[15] + lam * t[15], t + 1, d);
+                if (!ok && !newton && !(t[10] > 0.0)) break;
+                if (ok) {
+                    if (fabs(d[0]) < NDT_STEP_T && fabs(d[1]) < NDT_STEP_T && fabs(d[2]) < NDT_STEP_R) break;
+                    for (int q = 0; q < 3; q++) pn[q] = p[q] + d[q];
+                    ok = fabs(pn[0]) < 64.0 && fabs(pn[1]) < 64.0 && fabs(pn[2]) < 1.0;
+                }
+                if (ok) { go = true; break; }
+                if (newton) {
+                    newton_ok = false;
+                } else {
+                    lam *= 10.0;
+                    if (lam > 1e9) break;
+                }
+                it++;
+            }
+            if (go) ndt_sincos(pn[2], sn, cs);
+            if (lane == 0) {
+                ctl[6] = sn;
+                ctl[7] = cs;
+                ctl[0] = go ? 1.0 : 0.0;
+                ctl[1] = go ? pn[0] : p[0];
+                ctl[2] = go ? pn[1] : p[1];
+                ctl[3] = go ? pn[2] : p[2];
+                ctl[4] = t[0];
+                ctl[5] = (double)ne;
+            }
+        }
+        __syncthreads();
+        if (ctl[0] == 0.0) break;
+        if (!boss) { pn[0] = ctl[1]; pn[1] = ctl[2]; sn = ctl[6]; cs = ctl[7]; }
+    }
+}
+
 // adj = 0: scan-to-map (HybridMap.get_scan_match hybridmap.py:210-261)
 // adj = 1: scan-to-previous-scan (HybridMap.get_scan_adj hybridmap.py:147-191): curr points are
 //          the unsnapped endpoints, occupancy is the previous scan rasterised on the lattice.
-__global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out, int adj)
+__global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out, int adj)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm = smem;
@@ -285,25 +567,9 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     // ---- 1. curr points, hybridmap.py:216-228,236,240 ----------------------
     const unsigned long long exists = c.exists[p];
     for (int j = tid; j < c.B; j += MT_THREADS) {
-        double d = c.dist[j];
-        double gx, gy;
-        rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, c.px[j], c.py[j], gx, gy);
-        if (adj) {                                                         // hybridmap.py:165-172
-            const double ax = gx - sh->gx, ay = gy - sh->gy;
-            if (!(sqrt(ax * ax + ay * ay) < RB_MATCH_MAX_R)) continue;
-            const int slot = atomicAdd(&sh->M, 1);
-            ccx[slot] = ax;
-            ccy[slot] = ay;
-            continue;
-        }
-        if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) continue;
-        int tx, ty, ix, iy;
-        rb_read_axis(gx, tx, ix);
-        rb_read_axis(gy, ty, iy);
-        if (!rb_tile_exists(c, exists, tx, ty)) continue;
-        double qx = rb_cell_corner(ix, tx) - sh->gx, qy = rb_cell_corner(iy, ty) - sh->gy;
-        if (!(sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R)) continue;
-        int slot = atomicAdd(&sh->M, 1);
+        double qx, qy;
+        if (!mt_curr_point(c, sh, exists, j, adj, qx, qy)) continue;
+        const int slot = atomicAdd(&sh->M, 1);
         ccx[slot] = qx;
         ccy[slot] = qy;
     }
@@ -581,6 +847,22 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
     }
     __syncthreads();
 
+    // ---- 5b. NDT refinement, matchScanCustom.m:32-50 ---------------------------------
+    static_assert(MT_THREADS >= RB_MAXB, "NDT stage: one thread per beam");
+    double nd_p[3] = {(double)bi, (double)bj, (double)bk * step}, nd_S = 0.0;
+    int nd_evals = 0;
+    bool nd_accept = false;
+    if (c.refine && valid) {
+        double qx = 0.0, qy = 0.0;
+        const bool has = tid < c.B && mt_curr_point(c, sh, exists, tid, adj, qx, qy);
+        double *red = reinterpret_cast<double *>(bmg), *ctl = red + MT_WARPS * NDT_TERMS;   // bmg is dead after phase A
+        ndt_refine(bm, red, ctl, sh->g0xu - sh->x0, sh->fx, sh->fy, has, qx, qy, nd_p[0], nd_p[1], nd_p[2]);
+        nd_p[0] = ctl[1]; nd_p[1] = ctl[2]; nd_p[2] = ctl[3]; nd_S = ctl[4]; nd_evals = (int)ctl[5];
+        const bool ok = fabs(nd_p[0] * RB_CS) < sh->rx && fabs(nd_p[1] * RB_CS) < sh->ry &&
+                        fabs(nd_p[2]) < 3.14159265358979323846 / 6.0 && (nd_p[0] != 0.0 || nd_p[1] != 0.0 || nd_p[2] != 0.0);
+        nd_accept = ok && nd_S * 2.0 > (double)bs;                          // :38-39
+    }
+
     // ---- 6. result --------------------------------------------------------------
     if (tid == 0) {
         double *op = c.m_pose + 3 * (size_t)p, *oc = c.m_cov + 9 * (size_t)p;
@@ -589,6 +871,12 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
         op[2] = sh->gth + (double)bk * step;
         int *ob = c.m_best + 4 * (size_t)p;
         ob[0] = bi; ob[1] = bj; ob[2] = bk; ob[3] = M;
+        c.m_refine[2 * (size_t)p] = nd_evals;
+        c.m_refine[2 * (size_t)p + 1] = nd_accept ? 1 : 0;
+        if (nd_evals && !slice_out) {
+            atomicAdd(&c.stats->ndt_evals, (unsigned long long)nd_evals);
+            atomicAdd(&c.stats->ndt_accepted, nd_accept ? 1ull : 0ull);
+        }
         c.m_valid[p] = valid ? 1 : 0;
         if (sh->overflow) atomicExch(&c.flags->world_overflow, 1);
         if (!slice_out) {
@@ -612,6 +900,12 @@ __global__ void __launch_bounds__(MT_THREADS) match_kernel(RbCtx c, int p_offset
             oc[1] = oc[3] = ((double)sh->mom[5] / W0 - mx * my) * q;
             oc[8] = ((double)sh->mom[8] / T0 - mt * mt) * qt + qt / 12.0;
             c.m_score[p] = (double)bs;
+            if (nd_accept) {                                                // :40-41, covariance stays the grid stage's
+                op[0] = sh->gx + nd_p[0] * RB_CS;
+                op[1] = sh->gy + nd_p[1] * RB_CS;
+                op[2] = sh->gth + nd_p[2];
+                c.m_score[p] = nd_S;
+            }
         }
     }
 }
@@ -635,6 +929,7 @@ __global__ void __launch_bounds__(256) match_copy_dups_kernel(RbCtx c)
     for (int q = 0; q < 3; q++) c.m_pose[3 * (size_t)p + q] = c.m_pose[3 * (size_t)r + q];
     for (int q = 0; q < 9; q++) c.m_cov[9 * (size_t)p + q] = c.m_cov[9 * (size_t)r + q];
     for (int q = 0; q < 4; q++) c.m_best[4 * (size_t)p + q] = c.m_best[4 * (size_t)r + q];
+    for (int q = 0; q < 2; q++) c.m_refine[2 * (size_t)p + q] = c.m_refine[2 * (size_t)r + q];
     c.m_score[p] = c.m_score[r];
     c.m_valid[p] = c.m_valid[r];
     if (!c.m_valid[r]) atomicAdd(&c.stats->match_failed, 1ull);

@@ -36,14 +36,15 @@ class ParticleSet:
     """N particles on one GPU: poses, covariances, weights, page tables, tile pool."""
 
     def __init__(self, n_particles, n_beams, n_samples=30, world_tiles=(5, 5), pool_subtiles=None,
-                 device=0, rank=0, world=1, stream=0, seed=0):
+                 device=0, rank=0, world=1, stream=0, seed=0, ndt_refine=False):
+        """ndt_refine: run the NDT stage of the reference matcher (matchScanCustom.m:32-50) after the grid search."""
         self._lib = _lib.load()
         self.N, self.B, self.K = int(n_particles), int(n_beams), int(n_samples)
         self.rank, self.world = rank, world
         if pool_subtiles is None:
             pool_subtiles = max(4096, 48 * self.N)
         cfg = _lib.RbpfConfig(self.N, self.B, self.K, world_tiles[0], world_tiles[1], int(pool_subtiles),
-                              device, rank, world, 0, int(stream), int(seed))
+                              device, rank, world, 1 if ndt_refine else 0, int(stream), int(seed))
         self._h = C.c_void_p()
         rc = self._lib.rbpf_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -178,7 +179,14 @@ class ParticleSet:
         self._ck(self._lib.rbpf_get_match(self._h, pose.ctypes.data_as(_dp), cov.ctypes.data_as(_dp),
                                           score.ctypes.data_as(_dp), valid.ctypes.data_as(_ip),
                                           best.ctypes.data_as(_ip)))
-        return dict(pose=pose, cov=cov, score=score, valid=valid.astype(bool), best=best)
+        refine = np.empty((self.N, 2), dtype=np.int32)
+        self._ck(self._lib.rbpf_get_match_refine(self._h, refine.ctypes.data_as(_ip)))
+        return dict(pose=pose, cov=cov, score=score, valid=valid.astype(bool), best=best,
+                    ndt_evals=refine[:, 0].copy(), ndt_accepted=refine[:, 1].astype(bool))
+
+    def set_refine(self, on):
+        """Switch the NDT stage (matchScanCustom.m:32-50) on or off for the following matches."""
+        self._ck(self._lib.rbpf_set_refine(self._h, 1 if on else 0))
 
     def set_match(self, pose, cov, valid):
         pose = np.ascontiguousarray(np.broadcast_to(np.asarray(pose, dtype=np.float64), (self.N, 3)))
