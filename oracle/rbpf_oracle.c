@@ -550,14 +550,14 @@ int orc_match_curr(const orc_map *m, const double *guess, const double *px, cons
  * Bit-exact contract with the CUDA kernel (k_match.cu mt_ndt_refine): exp/sin/
  * cos are the polynomial forms below (plain IEEE + - * /), per-beam terms are
  * summed in the order 12 warps x 32 lanes, xor-butterfly inside a warp, warps
- * sequentially.
+ * 0-5 and 6-11 sequentially, then the two halves.
  */
 #define NDT_MAX_ITERS 500      /* matchScanCustom.m:36 */
 #define NDT_TERMS 16         /* S, gradient (3), Hessian (6), curvature model (6) */
 #define NDT_SLOTS 384          /* 12 warps x 32 lanes: slot = beam index */
 #define NDT_LIMIT 235.0        /* lookups stay inside the occupancy window */
-#define NDT_STEP_T 1e-3       /* cells */
-#define NDT_STEP_R 1e-5       /* rad */
+#define NDT_STEP_T 5e-3       /* cells */
+#define NDT_STEP_R 5e-5       /* rad */
 #define NDT_T1 0.33333333333333331
 #define NDT_T2 0.66666666666666663
 
@@ -706,7 +706,7 @@ static void ndt_eval(const unsigned char *win, int S_, int R_, const double *cx,
         a[15] = J3x * c13 + J3y * c23;
     }
     for (int e = 0; e < NDT_TERMS; e++) {
-        double t = 0.0;
+        double half[2] = {0.0, 0.0};                                          /* warps 0-5 and 6-11, each in order */
         for (int w = 0; w < NDT_SLOTS / 32; w++) {
             double l[32], n2[32];
             for (int i = 0; i < 32; i++) l[i] = slot[32 * w + i][e];
@@ -714,9 +714,10 @@ static void ndt_eval(const unsigned char *win, int S_, int R_, const double *cx,
                 for (int i = 0; i < 32; i++) n2[i] = l[i] + l[i ^ orders[o]];
                 memcpy(l, n2, sizeof l);
             }
-            t = w ? t + l[0] : l[0];
+            int h = w / (NDT_SLOTS / 64);
+            half[h] = (w % (NDT_SLOTS / 64)) ? half[h] + l[0] : l[0];
         }
-        tot[e] = t;
+        tot[e] = half[0] + half[1];
     }
     free(slot);
 }
@@ -758,7 +759,7 @@ static double ndt_refine(const unsigned char *win, int S_, int R_, const double 
             ok = ndt_solve(t[10] + lam * t[10], t[11], t[12], t[13] + lam * t[13], t[14], t[15] + lam * t[15], t + 1, d);
         if (!ok && !newton && !(t[10] > 0.0)) break;                           /* no point carries a Gaussian */
         if (ok) {
-            if (fabs(d[0]) < NDT_STEP_T && fabs(d[1]) < NDT_STEP_T && fabs(d[2]) < NDT_STEP_R) break;   /* step below 50 um / 1e-5 rad */
+            if (fabs(d[0]) < NDT_STEP_T && fabs(d[1]) < NDT_STEP_T && fabs(d[2]) < NDT_STEP_R) break;   /* step below 0.25 mm / 5e-5 rad */
             for (int a = 0; a < 3; a++) pn[a] = p[a] + d[a];
             ok = fabs(pn[0]) < 64.0 && fabs(pn[1]) < 64.0 && fabs(pn[2]) < 1.0;
         }

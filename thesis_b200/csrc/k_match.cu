@@ -258,8 +258,8 @@ __device__ __forceinline__ bool mt_curr_point(const RbCtx &c, const MatchShared 
 #define NDT_TERMS 16
 #define NDT_MAX_ITERS 500
 #define NDT_LIMIT 235.0
-#define NDT_STEP_T 1e-3
-#define NDT_STEP_R 1e-5
+#define NDT_STEP_T 5e-3
+#define NDT_STEP_R 5e-5
 #define NDT_T1 0.33333333333333331
 #define NDT_T2 0.66666666666666663
 
@@ -440,10 +440,15 @@ __device__ __noinline__ void ndt_refine(const uint32_t *__restrict__ bm, double 
         ndt_partial(bm, red, xoff0, fx, fy, has, cx, cy, pn[0], pn[1], sn, cs);
         __syncthreads();
         if (boss) {
-            double s = 0.0, tn[NDT_TERMS];
-            if (lane < NDT_TERMS) {
-                s = red[lane];
-                for (int w = 1; w < MT_WARPS; w++) s = s + red[w * NDT_TERMS + lane];
+            // lanes 0-15 sum warps 0-5 of their term, lanes 16-31 warps 6-11, in order; then the halves
+            double s, tn[NDT_TERMS];
+            {
+                const double *col = red + (lane >> 4) * (MT_WARPS / 2) * NDT_TERMS + (lane & 15);
+                s = col[0];
+#pragma unroll
+                for (int w = 1; w < MT_WARPS / 2; w++) s = s + col[w * NDT_TERMS];
+                const double other = __shfl_xor_sync(0xffffffffu, s, 16);
+                s = lane < 16 ? s + other : other + s;
             }
 #pragma unroll
             for (int e = 0; e < NDT_TERMS; e++) tn[e] = __shfl_sync(0xffffffffu, s, e);
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     __syncthreads();
 
     // ---- 5b. NDT refinement, matchScanCustom.m:32-50 ---------------------------------
-    static_assert(MT_THREADS >= RB_MAXB, "NDT stage: one thread per beam");
+    static_assert(MT_THREADS >= RB_MAXB && MT_WARPS % 2 == 0, "NDT stage: one thread per beam, two halves of warps");
     double nd_p[3] = {(double)bi, (double)bj, (double)bk * step}, nd_S = 0.0;
     int nd_evals = 0;
     bool nd_accept = false;
