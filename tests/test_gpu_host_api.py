@@ -81,10 +81,13 @@ def test_device_rng_mode_runs(gpu, golden):
     assert np.isfinite(ps.poses).all() and ps.stats()["cells_dropped"] == 0
 
 
-def test_long_run_gpu_vs_oracle_all_excerpt_frames(gpu):
+@pytest.mark.parametrize("refine", [False, True])
+def test_long_run_gpu_vs_oracle_all_excerpt_frames(gpu, refine):
     """All 45 sweeps of the Intel excerpt, 48 particles, main.py's map/adj alternation:
     the GPU views and the oracle, driven by the same loop and the same NumPy draws,
-    must pick the same ancestors at every resample and stay within tolerance."""
+    must pick the same ancestors at every resample and stay within tolerance.
+    refine: with the NDT stage of the matcher (matchScanCustom.m:32-50) on in both."""
+    import oracle as O
     import ref_adapter as RA
     from thesis_b200 import harness, sensors
 
@@ -93,11 +96,15 @@ def test_long_run_gpu_vs_oracle_all_excerpt_frames(gpu):
     ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
     op = RA.OracleParticles(n, 180)
     oposes = []
-    harness.run_log(op.views, ld, im, op.resample, seed_fn=op.seed,
-                    on_frame=lambda f, ps: oposes.append([list(p.get_latest_pose().as_tuple()) for p in ps]))
+    old = O.set_refine(refine)
+    try:
+        harness.run_log(op.views, ld, im, op.resample, seed_fn=op.seed,
+                        on_frame=lambda f, ps: oposes.append([list(p.get_latest_pose().as_tuple()) for p in ps]))
+    finally:
+        O.set_refine(old)
     np.random.seed(7)
     ld, im = sensors.Lidar(ExcerptLidar()), sensors.IMU(ExcerptIMU())
-    gpu.new_filter(rng="numpy", keep_history=False, pool_subtiles=20000)
+    gpu.new_filter(rng="numpy", keep_history=False, pool_subtiles=20000, ndt_refine=refine)
     parts = [gpu.Robot("eng") for _ in range(n)]
     anc, gposes = [], []
 
