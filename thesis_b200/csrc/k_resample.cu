@@ -20,13 +20,13 @@
 #include "common.cuh"
 
 #define RS_THREADS 1024
-#define RS_CHUNK 4096
+#define RS_CHUNK 2048
 
 __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, const double *__restrict__ w_in,
                                                                    const double *__restrict__ u01_in)
 {
     __shared__ double red_mx[32], red_mn[32];
-    __shared__ double chunk[RS_CHUNK];
+    __shared__ double chunk[2][RS_CHUNK];
     __shared__ double s_mn2, s_carry, s_slice, s_start;
     __shared__ int s_do;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -76,26 +76,51 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
     __syncthreads();
     const double shift = s_mn2 < 0.0 ? fabs(s_mn2) : 0.0;
     const bool do_shift = s_mn2 < 0.0;
-    // running sum, chunk by chunk: all threads stage a chunk in shared memory,
-    // thread 0 runs the sequential float64 chain, all threads write it back.
-    for (int base = 0; base < NG; base += RS_CHUNK) {
-        const int n = min(RS_CHUNK, NG - base);
-        for (int i = tid; i < n; i += RS_THREADS) {
-            double v = w[base + i];
-            if (do_shift && v != 0.0) v += shift;                            // main.py:55
-            chunk[i] = v;
-        }
-        __syncthreads();
+    // running sum, chunk by chunk: the other threads stage chunk k+1 and write chunk k-1
+    // back while thread 0 runs the sequential float64 chain over chunk k (two shared
+    // buffers); the chain keeps eight values in registers so that consecutive adds are
+    // back to back (the chain is bound by the DADD latency, nothing else).
+    const int n_chunks = (NG + RS_CHUNK - 1) / RS_CHUNK;
+    for (int k = -1; k < n_chunks; k++) {
         if (tid == 0) {
-            double cur = s_carry;
-#pragma unroll 8
-            for (int i = 0; i < n; i++) { cur += chunk[i]; chunk[i] = cur; } // main.py:57 == :62
-            s_carry = cur;
+            if (k >= 0 && k < n_chunks) {
+                double *ch = chunk[k & 1];
+                const int n = min(RS_CHUNK, NG - k * RS_CHUNK);
+                double cur = s_carry;
+                int i = 0;
+                for (; i + 8 <= n; i += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = ch[i + e];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { cur += v[e]; v[e] = cur; } // main.py:57 == :62
+#pragma unroll
+                    for (int e = 0; e < 8; e++) ch[i + e] = v[e];
+                }
+                for (; i < n; i++) { cur += ch[i]; ch[i] = cur; }
+                s_carry = cur;
+            }
+        } else {
+            if (k + 1 < n_chunks) {                                          // stage the next chunk
+                double *ch = chunk[(k + 1) & 1];
+                const int base = (k + 1) * RS_CHUNK, n = min(RS_CHUNK, NG - base);
+                for (int i = tid - 1; i < n; i += RS_THREADS - 1) {
+                    double v = w[base + i];
+                    if (do_shift && v != 0.0) v += shift;                    // main.py:55
+                    ch[i] = v;
+                }
+            }
         }
         __syncthreads();
-        for (int i = tid; i < n; i += RS_THREADS) w[base + i] = chunk[i];
-        __syncthreads();
+        if (tid != 0 && k >= 0 && k < n_chunks) {                            // chunk k is final: write it back
+            const double *ch = chunk[k & 1];
+            const int base = k * RS_CHUNK, n = min(RS_CHUNK, NG - base);
+            for (int i = tid - 1; i < n; i += RS_THREADS - 1) w[base + i] = ch[i];
+        }
+        // the write-back of chunk k overlaps the chain of chunk k+1; buffer k&1 is staged
+        // again at iteration k+1 (for chunk k+2) only after the next barrier
     }
+    __syncthreads();
     if (tid == 0) {
         double slice = s_carry / (double)NG;                                 // main.py:57
         double u;
