@@ -76,7 +76,7 @@ def main():
                 ok &= sorted(tiles.keys()) == sorted(one.list_tiles(j))
                 for c, a in tiles.items():
                     ok &= bool(np.array_equal(a, one.export_tile(j, *c)))
-        print("particles migrated over NCCL: %d; sharded run identical to the single set: %s" % (int(tot_mig), ok), flush=True)
+        print("transport %s: particles migrated: %d; sharded run identical to the single set: %s" % (sh.transport, int(tot_mig), ok), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

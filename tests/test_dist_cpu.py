@@ -91,6 +91,13 @@ def test_plan_is_consistent_between_ranks():
             assert n_in == len(send_ab)
             # what b expects from a, resolved through a's send list, is the global ancestor
             assert np.array_equal(send_ab[rec] + a * n_local, anc[dst + b * n_local])
+    # the pulling receiver's source list is the sender's send list (same slots, same order)
+    for b in range(world):
+        _, recv_b, src_b = plan_migration(anc, n_local, b, world, want_sources=True)
+        for a in range(world):
+            if a != b:
+                assert np.array_equal(src_b[a], plans[a][0][b])
+                assert recv_b[a][2] == len(src_b[a])
     # a sub-set with no cross-rank ancestors moves nothing
     ident = np.arange(world * n_local)
     s, r = plan_migration(ident, n_local, 1, world)

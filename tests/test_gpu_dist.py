@@ -18,14 +18,25 @@ def mods():
     return torch, dist, particles
 
 
-def test_two_rank_emulation_equals_single_set(mods, golden):
+@pytest.mark.parametrize("transport,world", [("nccl", 2), ("peer", 2), ("peer", 3)])
+def test_two_rank_emulation_equals_single_set(mods, golden, transport, world):
+    """Ranks emulated on one GPU.  "nccl": pack -> (copy) -> unpack; "peer": every rank
+    pulls what it needs straight out of the other ranks' buffers (same-process mapping
+    instead of CUDA IPC), then all ranks apply and commit.  Either way the union of the
+    ranks must equal one ParticleSet bit for bit, every step."""
     torch, D, P = mods
-    world, nl, B, K = 2, 6, 180, 30
+    nl, B, K = 6, 180, 30
     N = world * nl
     ang = golden["intel_angles"]
     rng = np.random.default_rng(21)
     one = P.ParticleSet(N, B, pool_subtiles=3000)
     ranks = [D.MigratingSet(nl, B, r, world, pool_subtiles=2000) for r in range(world)]
+    if transport == "peer":
+        views = [ps.peer_view() for ps in ranks]
+        for k, ps in enumerate(ranks):
+            for r_ in range(world):
+                if r_ != k:
+                    ps.attach_peer(r_, views[r_])
     par = (0.002, 0.05, 0.01 * np.pi / 180, 0.05)
     r0 = golden["intel_ranges"][0]
     for ps in [one] + ranks:
@@ -44,13 +55,21 @@ def test_two_rank_emulation_equals_single_set(mods, golden):
             ps.motion(1, u, 1.0, par)
             ps.set_scan(r, ang); ps.scan_match(); ps.weight(z[k * nl:(k + 1) * nl]); ps.integrate(fallback_weights=True)
         w_all = torch.cat([ps.local_weights_tensor().clone() for ps in ranks])       # the all-gather
-        packed = [ps.pack_outgoing(w_all, u01) for ps in ranks]
-        for k, ps in enumerate(ranks):
-            assert packed[k][0] == did1
-            assert np.array_equal(ps._anc, anc1), "step %d: ancestors differ from the single set" % step
-        for k, ps in enumerate(ranks):
-            incoming = {r_: packed[r_][1][k] for r_ in range(world) if r_ != k}      # the all-to-all
-            ps.adopt_incoming(incoming, packed[k][2])
+        if transport == "peer":
+            for ps in ranks:
+                assert ps.plan_and_pull(w_all, u01) == did1
+                assert np.array_equal(ps._anc, anc1), "step %d: ancestors differ from the single set" % step
+            torch.cuda.synchronize()                                                 # the barrier
+            for ps in ranks:
+                ps.finish_resample()
+        else:
+            packed = [ps.pack_outgoing(w_all, u01) for ps in ranks]
+            for k, ps in enumerate(ranks):
+                assert packed[k][0] == did1
+                assert np.array_equal(ps._anc, anc1), "step %d: ancestors differ from the single set" % step
+            for k, ps in enumerate(ranks):
+                incoming = {r_: packed[r_][1][k] for r_ in range(world) if r_ != k}  # the all-to-all
+                ps.adopt_incoming(incoming, packed[k][2])
         poses = np.concatenate([ps.poses for ps in ranks])
         assert np.array_equal(poses, one.poses), "step %d" % step
         assert np.array_equal(np.concatenate([ps.weights for ps in ranks]), one.weights)

@@ -23,6 +23,14 @@ class RbpfConfig(C.Structure):
     ]
 
 
+class RbpfPeerView(C.Structure):
+    _fields_ = [
+        ("ipc", (C.c_ubyte * 64) * 9), ("ptr", C.c_uint64 * 9), ("pid", C.c_int64), ("parity", C.c_int32),
+        ("device", C.c_int32), ("n_particles", C.c_int32), ("pool_subtiles", C.c_uint32), ("nsub", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class RbpfStats(C.Structure):
     _fields_ = [
         ("pool_subtiles", C.c_uint32), ("pool_in_use", C.c_uint32), ("cow_copies", C.c_uint64),
@@ -81,6 +89,9 @@ SIGNATURES = {
     "rbpf_resample_apply_local": (C.c_int, [_H]),
     "rbpf_migrate_unpack": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int32, _ip, _ip, C.c_int32]),
     "rbpf_resample_commit": (C.c_int, [_H]),
+    "rbpf_peer_export": (C.c_int, [_H, C.POINTER(RbpfPeerView)]),
+    "rbpf_peer_attach": (C.c_int, [_H, C.c_int32, C.POINTER(RbpfPeerView)]),
+    "rbpf_migrate_pull": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip, _ip, C.c_int32]),
 }
 
 _LIB = None

@@ -69,6 +69,13 @@ struct RbFlags {                            // device-side status words
     int pad[3];
 };
 
+struct RbPeer {                             // another rank's current particle state, mapped into this process
+    const int8_t *pool;
+    const uint32_t *pt;
+    const double *pose, *cov;
+    const unsigned long long *exists;
+};
+
 struct RbCtx {
     int N, B, K;                            // local particles, beams, samples
     int rank, world, n_global;              // sharding
@@ -252,3 +259,5 @@ void rb_launch_migrate_pack(const RbCtx &c, const int *slots_dev, int n, int n_t
 void rb_launch_migrate_unpack(const RbCtx &c, const unsigned char *buf, int n, int n_tiles, const int *dst_slots_dev,
                               const int *rec_idx_dev, int m, uint32_t *map, cudaStream_t s);
 size_t rb_migrate_bytes(int n, int n_tiles, int nsub);
+void rb_launch_migrate_pull(const RbCtx &c, const RbPeer &peer, const int *src_slots_dev, int n_src, const int *dst_slots_dev,
+                            const int *rec_idx_dev, int m, uint32_t *mark, uint32_t *list, int *count, cudaStream_t s);

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -37,6 +38,11 @@ struct rbpf_ctx {
     uint32_t *d_mg_mark, *d_mg_list;
     int *d_mg_count;
     int mg_n, mg_tiles;
+    int *d_mg_src;                 // N staging ints: remote source slots of a pull
+    void *phys[9];                 // pool, pt x2, pose x2, cov x2, exists x2 as allocated (index 1 + 2*k + parity)
+    int parity;                    // which of the double buffers is current (flips with every commit)
+    struct PeerMap { bool attached = false, ipc = false; void *base[9] = {}; };
+    std::vector<PeerMap> peers;    // by rank
     std::vector<cudaEvent_t> tev;  // (RB_NSTAGES + 1) events per recorded step
     int t_max_steps, t_steps;
 };
@@ -114,6 +120,9 @@ extern "C" int rbpf_destroy(rbpf_handle h)
     if (!h) return RBPF_ERR_ARG;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    for (auto &pm : h->peers)
+        if (pm.attached && pm.ipc)
+            for (void *b : pm.base) cudaIpcCloseMemHandle(b);
     for (void *p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) cudaEventDestroy(h->stage_ev[i]);
@@ -198,8 +207,14 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_mg_mark, d.pool_tiles);
     A(h->d_mg_list, d.pool_tiles);
     A(h->d_mg_count, 4);
+    A(h->d_mg_src, N);
 #undef A
     if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    {
+        void *phys[9] = {d.pool, d.pt, d.pt2, d.pose, d.pose2, d.cov, d.cov2, d.exists, d.exists2};
+        memcpy(h->phys, phys, sizeof(phys));
+        h->parity = 0;
+    }
     if (cudaMallocHost((void **)&h->h_scan, 2 * 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
     h->h_prev = nullptr;
@@ -348,6 +363,7 @@ static void swap_buffers(rbpf_ctx *h)
     std::swap(d.cov, d.cov2);
     std::swap(d.pt, d.pt2);
     std::swap(d.exists, d.exists2);
+    h->parity ^= 1;
 }
 
 static int resample_common(rbpf_ctx *h, const double *weights_all_dev, const double *u01, int32_t *ancestors_out,
@@ -680,6 +696,100 @@ extern "C" int rbpf_resample_commit(rbpf_handle h)
     if (!h) return RBPF_ERR_ARG;
     swap_buffers(h);
     h->d.step_no++;
+    return RBPF_OK;
+}
+
+// ---- pull migration over peer memory ----------------------------------------------
+
+extern "C" int rbpf_peer_export(rbpf_handle h, rbpf_peer_view *out)
+{
+    if (!h || !out) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < 9; i++) {
+        cudaIpcMemHandle_t ih;
+        CK(cudaIpcGetMemHandle(&ih, h->phys[i]));
+        static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out->ipc[i], &ih, 64);
+        out->ptr[i] = (uint64_t)(uintptr_t)h->phys[i];
+    }
+    out->parity = h->parity;
+    out->pid = (int64_t)getpid();
+    out->device = h->cfg.device;
+    out->n_particles = h->d.N;
+    out->pool_subtiles = h->d.pool_tiles;
+    out->nsub = h->d.nsub;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_peer_attach(rbpf_handle h, int32_t peer_rank, const rbpf_peer_view *view)
+{
+    if (!h || !view || peer_rank < 0 || peer_rank >= h->d.world || peer_rank == h->d.rank) return RBPF_ERR_ARG;
+    if (view->n_particles != h->d.N || view->pool_subtiles != h->d.pool_tiles || view->nsub != h->d.nsub ||
+        view->parity != h->parity) {
+        h->err = "peer_attach: the peer's particle count, pool size, world extent or buffer parity differs";
+        return RBPF_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    if ((int)h->peers.size() < h->d.world) h->peers.resize(h->d.world);
+    rbpf_ctx::PeerMap &pm = h->peers[peer_rank];
+    if (pm.attached) { h->err = "peer_attach: already attached"; return RBPF_ERR_ARG; }
+    if (view->pid == (int64_t)getpid()) {                       // same process (tests): the pointers are valid as they are
+        if (view->device != h->cfg.device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, view->device));
+            if (!can) { h->err = "peer_attach: no peer access between the two devices"; return RBPF_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(view->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+        for (int i = 0; i < 9; i++) pm.base[i] = (void *)(uintptr_t)view->ptr[i];
+        pm.ipc = false;
+    } else {
+        for (int i = 0; i < 9; i++) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, view->ipc[i], 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&pm.base[i], ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int k = 0; k < i; k++) cudaIpcCloseMemHandle(pm.base[k]);
+                h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                return RBPF_ERR_CUDA;
+            }
+        }
+        pm.ipc = true;
+    }
+    pm.attached = true;
+    return RBPF_OK;
+}
+
+// Receiver: local destination slot dst_slots[i] becomes a copy of the peer's particle
+// src_slots[rec_index[i]], read through the peer mapping (the job runs in lockstep: the
+// peer's current buffers have this handle's parity).  Asynchronous on the stream.
+extern "C" int rbpf_migrate_pull(rbpf_handle h, int32_t peer_rank, const int32_t *src_slots, int32_t n_src,
+                                 const int32_t *dst_slots, const int32_t *rec_index, int32_t m)
+{
+    if (!h || peer_rank < 0 || peer_rank >= (int)h->peers.size() || !h->peers[peer_rank].attached) {
+        if (h) h->err = "migrate_pull: peer not attached";
+        return RBPF_ERR_ARG;
+    }
+    if (n_src < 0 || n_src > h->d.N || m < 0 || m > h->d.N || (m > 0 && (!src_slots || !dst_slots || !rec_index))) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = upload_ints(h, h->d_mg_src, src_slots, n_src);
+    if (!rc) rc = upload_ints(h, h->d_mg_slots, dst_slots, m);
+    if (!rc) rc = upload_ints(h, h->d_mg_slots + h->d.N, rec_index, m);
+    if (rc) return rc;
+    const rbpf_ctx::PeerMap &pm = h->peers[peer_rank];
+    const int q = h->parity;
+    RbPeer peer;
+    peer.pool = (const int8_t *)pm.base[0];
+    peer.pt = (const uint32_t *)pm.base[1 + q];
+    peer.pose = (const double *)pm.base[3 + q];
+    peer.cov = (const double *)pm.base[5 + q];
+    peer.exists = (const unsigned long long *)pm.base[7 + q];
+    rb_launch_migrate_pull(h->d, peer, h->d_mg_src, n_src, h->d_mg_slots, h->d_mg_slots + h->d.N, m, h->d_mg_mark,
+                           h->d_mg_list, h->d_mg_count, h->stream);
+    CK(cudaGetLastError());
     return RBPF_OK;
 }
 

@@ -149,4 +149,96 @@ void rb_launch_migrate_unpack(const RbCtx &c, const unsigned char *buf, int n, i
     if (m > 0) migrate_place_kernel<<<(m * 32 + 255) / 256, 256, 0, s>>>(c, buf, dst_slots_dev, rec_idx_dev, m, map);
 }
 
+// ---- pull over peer memory -----------------------------------------------------------
+// The receiver reads the source rank's page tables, particle state and sub-tiles
+// directly through NVLink-mapped pointers (CUDA IPC) and writes them straight into
+// their final place: no pack, no staging buffer, no size negotiation, no host
+// synchronisation.  The source's buffers are read-only between its last stage-4
+// kernel and the job-wide barrier that follows the pulls (thesis_b200/dist.py).
+
+// pass 1: every allocated entry of the needed remote particles claims its remote sub-tile once
+__global__ void pull_claim_kernel(RbCtx c, RbPeer peer, const int *__restrict__ src_slots, int n, uint32_t *mark,
+                                  uint32_t *list, int *count)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint32_t *pt = peer.pt + (size_t)src_slots[warp] * c.nsub;
+    for (int e = lane; e < c.nsub; e += 32) {
+        const uint32_t t = pt[e];
+        if (t == RB_NONE || t >= c.pool_tiles) continue;
+        if (atomicCAS(&mark[t], RB_NONE, 0xFFFFFFFEu) == RB_NONE) list[atomicAdd(count, 1)] = t;
+    }
+}
+
+// pass 2: a fresh local sub-tile for every claimed remote one, payload copied across
+// the link (grid-stride over the device-side count); mark[remote] = local index
+__global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeer peer, uint32_t *mark, const uint32_t *__restrict__ list,
+                                                         const int *count)
+{
+    __shared__ uint32_t s_t;
+    const int n = *count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t rt = list[i];
+        if (threadIdx.x == 0) {
+            const int idx = atomicSub(c.free_count, 1) - 1;
+            if (idx < 0) { atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
+            else { s_t = c.free_list[idx]; c.refcnt[s_t] = 0u; }
+            mark[rt] = s_t == RB_NONE ? 0xFFFFFFFDu : s_t;
+        }
+        __syncthreads();
+        const uint32_t t = s_t;
+        if (t != RB_NONE) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(peer.pool + (size_t)rt * RB_SUB_BYTES);
+            uint4 *dst = reinterpret_cast<uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES);
+            for (int q = threadIdx.x; q < RB_SUB_BYTES / 16; q += blockDim.x) dst[q] = src[q];
+        }
+        __syncthreads();
+    }
+}
+
+// pass 3: destination slot j becomes a copy of remote particle src_slots[rec_idx[j]]
+__global__ void pull_place_kernel(RbCtx c, RbPeer peer, const int *__restrict__ src_slots, const int *__restrict__ dst_slots,
+                                  const int *__restrict__ rec_idx, int m, const uint32_t *__restrict__ mark)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    const int j = dst_slots[warp], s = src_slots[rec_idx[warp]];
+    if (lane < 3) c.pose2[3 * (size_t)j + lane] = peer.pose[3 * (size_t)s + lane];
+    if (lane < 9) c.cov2[9 * (size_t)j + lane] = peer.cov[9 * (size_t)s + lane];
+    if (lane == 0) {
+        c.exists2[j] = peer.exists[s];
+        c.weight[j] = 1.0;                                                   // main.py:77-78
+    }
+    const uint32_t *src = peer.pt + (size_t)s * c.nsub;
+    uint32_t *dst = c.pt2 + (size_t)j * c.nsub;
+    for (int e = lane; e < c.nsub; e += 32) {
+        const uint32_t rt = src[e];
+        uint32_t t = RB_NONE;
+        if (rt != RB_NONE && rt < c.pool_tiles) {
+            t = mark[rt];
+            if (t >= c.pool_tiles) t = RB_NONE;                              // pool exhausted (flag is set)
+        }
+        dst[e] = t;
+        if (t != RB_NONE) atomicAdd(&c.refcnt[t], 1u);
+    }
+}
+
+// pass 4: release the claims
+__global__ void pull_release_kernel(uint32_t *mark, const uint32_t *__restrict__ list, const int *count)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mark[list[i]] = RB_NONE;
+}
+
+void rb_launch_migrate_pull(const RbCtx &c, const RbPeer &peer, const int *src_slots_dev, int n_src, const int *dst_slots_dev,
+                            const int *rec_idx_dev, int m, uint32_t *mark, uint32_t *list, int *count, cudaStream_t s)
+{
+    if (n_src <= 0 || m <= 0) return;
+    cudaMemsetAsync(count, 0, sizeof(int), s);
+    pull_claim_kernel<<<(n_src * 32 + 255) / 256, 256, 0, s>>>(c, peer, src_slots_dev, n_src, mark, list, count);
+    pull_tiles_kernel<<<148 * 8, 256, 0, s>>>(c, peer, mark, list, count);
+    pull_place_kernel<<<(m * 32 + 255) / 256, 256, 0, s>>>(c, peer, src_slots_dev, dst_slots_dev, rec_idx_dev, m, mark);
+    pull_release_kernel<<<148, 256, 0, s>>>(mark, list, count);
+}
+
 size_t rb_migrate_bytes(int n, int n_tiles, int nsub) { return mg_header_bytes(n, nsub) + (size_t)n_tiles * RB_SUB_BYTES; }

@@ -7,10 +7,15 @@ particles; the one exchange step is resampling:
   1. all-gather of the weights over NCCL (8 B x N),
   2. every rank runs the identical global systematic resample
      (`rbpf_resample_global`, bit-exact ancestors on all ranks),
-  3. survivors whose ancestor lives on another rank migrate: the sender packs
-     state + page table + the de-duplicated sub-tiles (`rbpf_migrate_count/pack`),
-     NCCL all-to-all moves the buffers over NVLink, the receiver adopts them into
-     its pool (`rbpf_migrate_unpack`).
+  3. survivors whose ancestor lives on another rank migrate.  Transport "peer"
+     (default): every rank maps its peers' particle state once with CUDA IPC and
+     then PULLS what it needs -- page tables, poses and de-duplicated sub-tiles --
+     through NVLink straight into its own pool (`rbpf_migrate_pull`), followed by a
+     one-element all-reduce as the "everybody has read" barrier; no packing, no
+     size negotiation, no host synchronisation in the data path.  Transport "nccl"
+     (fallback, `RBPF_DIST_TRANSPORT=nccl`): the sender packs
+     (`rbpf_migrate_count/pack`), NCCL point-to-point moves the buffers, the
+     receiver adopts them (`rbpf_migrate_unpack`).
 
 `plan_migration` is pure numpy (same result on every rank, no negotiation) and is
 what the gloo CPU tests exercise; the byte movement is torch.distributed.
@@ -29,19 +34,22 @@ def owner_of(global_index, n_local):
     return global_index // n_local
 
 
-def plan_migration(ancestors, n_local, rank, world):
+def plan_migration(ancestors, n_local, rank, world, want_sources=False):
     """From the global ancestor vector derive, for this rank:
       send[r]  = sorted unique LOCAL slots whose particle rank r needs,
       recv[r]  = (dst_slots, rec_index, n_records): local destination slots fed by
                  rank r and, for each, the index into r's send list (== r's send[rank]).
     Every rank computes both sides from the same vector, so sizes agree.  The
     ancestor vector is non-decreasing (systematic resampling), so the slots fed by
-    this rank's particles form one contiguous interval: O(n_local) work."""
+    this rank's particles form one contiguous interval: O(n_local) work.
+    want_sources: also return src[r] = the sorted unique slots of rank r this rank
+    needs (what a pulling receiver reads; equals rank r's send[rank])."""
     anc = np.asarray(ancestors, dtype=np.int64)
     lo_id, hi_id = rank * n_local, (rank + 1) * n_local
     empty = np.zeros(0, dtype=np.int32)
     send = {r: empty for r in range(world) if r != rank}
     recv = {r: (empty, empty, 0) for r in range(world) if r != rank}
+    src_of = {r: empty for r in range(world) if r != rank}
     # what leaves: global slots j whose ancestor is one of my particles and that live elsewhere
     j0, j1 = np.searchsorted(anc, lo_id, "left"), np.searchsorted(anc, hi_id, "left")
     if j1 > j0:
@@ -60,6 +68,9 @@ def plan_migration(ancestors, n_local, rank, world):
         needed = mine[m] - int(r) * n_local
         uniq = np.unique(needed)
         recv[int(r)] = (np.flatnonzero(m).astype(np.int32), np.searchsorted(uniq, needed).astype(np.int32), len(uniq))
+        src_of[int(r)] = uniq.astype(np.int32)
+    if want_sources:
+        return send, recv, src_of
     return send, recv
 
 
@@ -126,6 +137,47 @@ class MigratingSet(ParticleSet):
             self.migrated_bytes += buf.numel()
         return bool(did.value), out, recv
 
+    # -- pull transport
+    def peer_view(self):
+        """Bytes describing this rank's buffers (CUDA IPC handles + raw pointers)."""
+        from . import _lib as L
+
+        v = L.RbpfPeerView()
+        self._ck(self._lib.rbpf_peer_export(self._h, C.byref(v)))
+        return bytes(v)
+
+    def attach_peer(self, peer_rank, view_bytes):
+        from . import _lib as L
+
+        v = L.RbpfPeerView.from_buffer_copy(view_bytes)
+        self._ck(self._lib.rbpf_peer_attach(self._h, int(peer_rank), C.byref(v)))
+
+    def plan_and_pull(self, weights_all, u01=None):
+        """Global resample on the gathered weights, then pull every remote ancestor this
+        rank needs through the peer mappings (asynchronous).  The caller must make sure
+        every rank has finished pulling before any rank calls finish_resample()."""
+        lib = self._lib
+        did = C.c_int32(0)
+        up = None
+        if u01 is not None:
+            u = C.c_double(float(u01))
+            up = C.cast(C.byref(u), C.POINTER(C.c_double))
+        self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, C.byref(did),
+                                          self._anc.ctypes.data_as(_ip)))
+        _, recv, src = plan_migration(self._anc, self.N, self.rank, self.world, want_sources=True)
+        for r, (dst_slots, rec_idx, n_rec) in recv.items():
+            if n_rec == 0:
+                continue
+            s = src[r]
+            self._ck(lib.rbpf_migrate_pull(self._h, r, s.ctypes.data_as(_ip), len(s), dst_slots.ctypes.data_as(_ip),
+                                           rec_idx.ctypes.data_as(_ip), len(dst_slots)))
+            self.migrated_particles += len(s)
+        return bool(did.value)
+
+    def finish_resample(self):
+        self._ck(self._lib.rbpf_resample_apply_local(self._h))
+        self._ck(self._lib.rbpf_resample_commit(self._h))
+
     def adopt_incoming(self, incoming, recv_plan):
         """Local gather / refcounts, then adopt {peer: (buffer, n_particles, n_subtiles)}."""
         lib = self._lib
@@ -153,11 +205,74 @@ class ShardedParticleSet(MigratingSet):
         super().__init__(n_local, n_beams, dist.get_rank(group), dist.get_world_size(group), device=device, **kw)
         self._w_all = self._torch.empty(self.n_global, dtype=self._torch.float64, device=self._dev)
         self._tev = None
+        self.transport = os.environ.get("RBPF_DIST_TRANSPORT", "peer")
+        if self.transport not in ("peer", "nccl"):
+            raise ValueError("RBPF_DIST_TRANSPORT must be 'peer' or 'nccl'")
+        if self.transport == "peer":
+            self._attach_all()
         self._prof = {} if os.environ.get("RBPF_DIST_PROFILE") else None   # host-side phase timers (adds syncs)
+
+    def _attach_all(self):
+        """Exchange the buffer descriptions and map every peer (once per job).  All ranks must
+        agree on the transport, so a failure anywhere switches every rank back to NCCL."""
+        torch, dist = self._torch, self._dist
+        mine = torch.frombuffer(bytearray(self.peer_view()), dtype=torch.uint8).to(self._dev)
+        views = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self._dev)
+        dist.all_gather_into_tensor(views, mine, group=self.group)
+        views = views.cpu().numpy().reshape(self.world, -1)
+        ok = 1
+        why = ""
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            try:
+                self.attach_peer(r, views[r].tobytes())
+            except Exception as e:               # no IPC / no peer access on this box
+                ok, why = 0, str(e)
+                break
+        flag = torch.tensor([ok], dtype=torch.int32, device=self._dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            import sys
+
+            if self.rank == 0 or why:
+                print("[rbpf] rank %d: peer transport unavailable (%s); every rank uses NCCL send/recv" % (self.rank, why or "a peer failed"),
+                      file=sys.stderr)
+            self.transport = "nccl"
+        self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self._dev)
+
+    def _resample_peer(self, u01, want_ancestors):
+        import time
+
+        torch, dist = self._torch, self._dist
+        prof = self._prof
+        t0 = time.perf_counter()
+        dist.all_gather_into_tensor(self._w_all, self._w_local, group=self.group)
+        if prof is not None:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+        did = self.plan_and_pull(self._w_all, u01)
+        if prof is not None:
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+        dist.all_reduce(self._barrier_flag, group=self.group)            # every rank has read what it needs
+        if prof is not None:
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+        self.finish_resample()
+        if prof is not None:
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            for k, v in (("allgather", t1 - t0), ("plan+pull", t2 - t1), ("barrier", t3 - t2), ("apply", t4 - t3)):
+                prof[k] = prof.get(k, 0.0) + v
+            prof["n"] = prof.get("n", 0) + 1
+        return did, (self._anc.copy() if want_ancestors else None)
 
     def resample(self, u01=None, want_ancestors=True):
         import time
 
+        if self.transport == "peer":
+            return self._resample_peer(u01, want_ancestors)
         torch, dist = self._torch, self._dist
         prof = self._prof
         t0 = time.perf_counter()
