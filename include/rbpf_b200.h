@@ -222,12 +222,13 @@ int rbpf_resample_apply_local(rbpf_handle h);
  * reads page tables, poses and sub-tiles straight into their final place.
  * rbpf_peer_export   describes this handle's buffers (to be all-gathered as bytes);
  * rbpf_peer_attach   maps a peer's buffers (same process: the raw pointers are used);
- * rbpf_migrate_pull  local slot dst_slots[i] becomes a copy of the peer's particle
- *                    src_slots[rec_index[i]] (src_slots unique).  Stream-ordered, no
- *                    host synchronisation.  The caller orders the steps of one
- *                    resample as: all ranks pull -> job-wide barrier ->
- *                    rbpf_resample_apply_local -> rbpf_resample_commit, because a
- *                    source may only free or overwrite state after every peer has read it. */
+ * rbpf_migrate_pull  every local slot whose ancestor (last rbpf_resample_global) lives on
+ *                    another rank becomes a copy of that particle.  The plan is the
+ *                    ancestor vector on the device: stream-ordered, no host copy, no
+ *                    host synchronisation.  The caller orders the steps of one resample
+ *                    as: all ranks pull -> job-wide barrier -> rbpf_resample_apply_local
+ *                    -> rbpf_resample_commit, because a source may only free or overwrite
+ *                    state after every peer has read it. */
 typedef struct {
     unsigned char ipc[9][64]; /* cudaIpcMemHandle_t of pool, page tables x2, poses x2, covariances x2, tile masks x2 */
     uint64_t ptr[9];          /* the same allocations as device pointers of the exporting process */
@@ -241,8 +242,7 @@ typedef struct {
 } rbpf_peer_view;
 int rbpf_peer_export(rbpf_handle h, rbpf_peer_view *out);
 int rbpf_peer_attach(rbpf_handle h, int32_t peer_rank, const rbpf_peer_view *view);
-int rbpf_migrate_pull(rbpf_handle h, int32_t peer_rank, const int32_t *src_slots, int32_t n_src,
-                      const int32_t *dst_slots, const int32_t *rec_index, int32_t m);
+int rbpf_migrate_pull(rbpf_handle h);
 /* Receiver: adopt a packed buffer; local slot dst_slots[i] becomes a copy of
  * received record rec_index[i] (weight 1.0, main.py:77-78). */
 int rbpf_migrate_unpack(rbpf_handle h, uint64_t dev_buf, int32_t n_particles, int32_t n_subtiles,

@@ -91,7 +91,7 @@ SIGNATURES = {
     "rbpf_resample_commit": (C.c_int, [_H]),
     "rbpf_peer_export": (C.c_int, [_H, C.POINTER(RbpfPeerView)]),
     "rbpf_peer_attach": (C.c_int, [_H, C.c_int32, C.POINTER(RbpfPeerView)]),
-    "rbpf_migrate_pull": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip, _ip, C.c_int32]),
+    "rbpf_migrate_pull": (C.c_int, [_H]),
 }
 
 _LIB = None

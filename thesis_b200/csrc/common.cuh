@@ -76,6 +76,9 @@ struct RbPeer {                             // another rank's current particle s
     const unsigned long long *exists;
 };
 
+#define RB_MAX_WORLD 16
+struct RbPeers { RbPeer p[RB_MAX_WORLD]; };  // by rank; this rank's own entry is unused
+
 struct RbCtx {
     int N, B, K;                            // local particles, beams, samples
     int rank, world, n_global;              // sharding
@@ -259,5 +262,5 @@ void rb_launch_migrate_pack(const RbCtx &c, const int *slots_dev, int n, int n_t
 void rb_launch_migrate_unpack(const RbCtx &c, const unsigned char *buf, int n, int n_tiles, const int *dst_slots_dev,
                               const int *rec_idx_dev, int m, uint32_t *map, cudaStream_t s);
 size_t rb_migrate_bytes(int n, int n_tiles, int nsub);
-void rb_launch_migrate_pull(const RbCtx &c, const RbPeer &peer, const int *src_slots_dev, int n_src, const int *dst_slots_dev,
-                            const int *rec_idx_dev, int m, uint32_t *mark, uint32_t *list, int *count, cudaStream_t s);
+void rb_launch_migrate_pull(const RbCtx &c, const RbPeers &peers, uint32_t *mark, uint32_t *list, unsigned char *list_rank,
+                            int *count, cudaStream_t s);

@@ -38,7 +38,8 @@ struct rbpf_ctx {
     uint32_t *d_mg_mark, *d_mg_list;
     int *d_mg_count;
     int mg_n, mg_tiles;
-    int *d_mg_src;                 // N staging ints: remote source slots of a pull
+    uint32_t *d_pull_mark = nullptr;   // world x pool_tiles claim table of the pull migration (allocated on first use)
+    unsigned char *d_pull_rank = nullptr;
     void *phys[9];                 // pool, pt x2, pose x2, cov x2, exists x2 as allocated (index 1 + 2*k + parity)
     int parity;                    // which of the double buffers is current (flips with every commit)
     struct PeerMap { bool attached = false, ipc = false; void *base[9] = {}; };
@@ -207,7 +208,6 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_mg_mark, d.pool_tiles);
     A(h->d_mg_list, d.pool_tiles);
     A(h->d_mg_count, 4);
-    A(h->d_mg_src, N);
 #undef A
     if (e != cudaSuccess) return fail(RBPF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     {
@@ -763,32 +763,37 @@ extern "C" int rbpf_peer_attach(rbpf_handle h, int32_t peer_rank, const rbpf_pee
     return RBPF_OK;
 }
 
-// Receiver: local destination slot dst_slots[i] becomes a copy of the peer's particle
-// src_slots[rec_index[i]], read through the peer mapping (the job runs in lockstep: the
-// peer's current buffers have this handle's parity).  Asynchronous on the stream.
-extern "C" int rbpf_migrate_pull(rbpf_handle h, int32_t peer_rank, const int32_t *src_slots, int32_t n_src,
-                                 const int32_t *dst_slots, const int32_t *rec_index, int32_t m)
+// Receiver: every local slot whose ancestor (rbpf_resample_global) lives on another rank
+// becomes a copy of that particle, read through the peer mappings (the job runs in
+// lockstep: the peers' current buffers have this handle's parity).  The plan is the
+// ancestor vector on the device: nothing is copied to or from the host, nothing waits.
+extern "C" int rbpf_migrate_pull(rbpf_handle h)
 {
-    if (!h || peer_rank < 0 || peer_rank >= (int)h->peers.size() || !h->peers[peer_rank].attached) {
-        if (h) h->err = "migrate_pull: peer not attached";
-        return RBPF_ERR_ARG;
-    }
-    if (n_src < 0 || n_src > h->d.N || m < 0 || m > h->d.N || (m > 0 && (!src_slots || !dst_slots || !rec_index))) return RBPF_ERR_ARG;
-    CK(cudaSetDevice(h->cfg.device));
-    int rc = upload_ints(h, h->d_mg_src, src_slots, n_src);
-    if (!rc) rc = upload_ints(h, h->d_mg_slots, dst_slots, m);
-    if (!rc) rc = upload_ints(h, h->d_mg_slots + h->d.N, rec_index, m);
-    if (rc) return rc;
-    const rbpf_ctx::PeerMap &pm = h->peers[peer_rank];
+    if (!h) return RBPF_ERR_ARG;
+    if (h->d.world > RB_MAX_WORLD) { h->err = "migrate_pull: world larger than RB_MAX_WORLD"; return RBPF_ERR_ARG; }
+    RbPeers peers;
+    memset(&peers, 0, sizeof(peers));
     const int q = h->parity;
-    RbPeer peer;
-    peer.pool = (const int8_t *)pm.base[0];
-    peer.pt = (const uint32_t *)pm.base[1 + q];
-    peer.pose = (const double *)pm.base[3 + q];
-    peer.cov = (const double *)pm.base[5 + q];
-    peer.exists = (const unsigned long long *)pm.base[7 + q];
-    rb_launch_migrate_pull(h->d, peer, h->d_mg_src, n_src, h->d_mg_slots, h->d_mg_slots + h->d.N, m, h->d_mg_mark,
-                           h->d_mg_list, h->d_mg_count, h->stream);
+    for (int r = 0; r < h->d.world; r++) {
+        if (r == h->d.rank) continue;
+        if (r >= (int)h->peers.size() || !h->peers[r].attached) { h->err = "migrate_pull: a peer is not attached"; return RBPF_ERR_ARG; }
+        const rbpf_ctx::PeerMap &pm = h->peers[r];
+        peers.p[r].pool = (const int8_t *)pm.base[0];
+        peers.p[r].pt = (const uint32_t *)pm.base[1 + q];
+        peers.p[r].pose = (const double *)pm.base[3 + q];
+        peers.p[r].cov = (const double *)pm.base[5 + q];
+        peers.p[r].exists = (const unsigned long long *)pm.base[7 + q];
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_pull_mark) {                                      // first use: one claim table per source rank
+        const size_t n = (size_t)h->d.world * h->d.pool_tiles;
+        CK(cudaMalloc((void **)&h->d_pull_mark, n * sizeof(uint32_t)));
+        h->allocs.push_back(h->d_pull_mark);
+        CK(cudaMalloc((void **)&h->d_pull_rank, h->d.pool_tiles));
+        h->allocs.push_back(h->d_pull_rank);
+        CK(cudaMemsetAsync(h->d_pull_mark, 0xFF, n * sizeof(uint32_t), h->stream));
+    }
+    rb_launch_migrate_pull(h->d, peers, h->d_pull_mark, h->d_mg_list, h->d_pull_rank, h->d_mg_count, h->stream);
     CK(cudaGetLastError());
     return RBPF_OK;
 }

@@ -150,45 +150,63 @@ void rb_launch_migrate_unpack(const RbCtx &c, const unsigned char *buf, int n, i
 }
 
 // ---- pull over peer memory -----------------------------------------------------------
-// The receiver reads the source rank's page tables, particle state and sub-tiles
+// The receiver reads the source ranks' page tables, particle state and sub-tiles
 // directly through NVLink-mapped pointers (CUDA IPC) and writes them straight into
-// their final place: no pack, no staging buffer, no size negotiation, no host
-// synchronisation.  The source's buffers are read-only between its last stage-4
-// kernel and the job-wide barrier that follows the pulls (thesis_b200/dist.py).
+// their final place: no pack, no staging buffer, no size negotiation, and -- because
+// the plan is the ancestor vector already on the device -- no host synchronisation.
+// The sources' buffers are read-only between their last stage-4 kernel and the
+// job-wide barrier that follows the pulls (thesis_b200/dist.py).
+// mark[r * pool_tiles + t] de-duplicates sub-tile t of rank r; list/list_rank hold the claims.
 
-// pass 1: every allocated entry of the needed remote particles claims its remote sub-tile once
-__global__ void pull_claim_kernel(RbCtx c, RbPeer peer, const int *__restrict__ src_slots, int n, uint32_t *mark,
-                                  uint32_t *list, int *count)
+__device__ __forceinline__ bool pull_source(const RbCtx &c, int j, int &r, int &s)
+{
+    if (c.flags->resample_error || !c.flags->did_resample) return false;     // particles unchanged
+    const int a = c.ancestors[c.rank * c.N + j];
+    r = a / c.N;
+    s = a - r * c.N;
+    return r != c.rank;
+}
+
+// pass 1: every allocated entry of a needed remote particle claims its remote sub-tile once
+__global__ void pull_claim_kernel(RbCtx c, RbPeers peers, uint32_t *mark, uint32_t *list, unsigned char *list_rank, int *count)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const uint32_t *pt = peer.pt + (size_t)src_slots[warp] * c.nsub;
+    if (warp >= c.N) return;
+    int r, s;
+    if (!pull_source(c, warp, r, s)) return;
+    const uint32_t *pt = peers.p[r].pt + (size_t)s * c.nsub;
+    uint32_t *mk = mark + (size_t)r * c.pool_tiles;
     for (int e = lane; e < c.nsub; e += 32) {
         const uint32_t t = pt[e];
         if (t == RB_NONE || t >= c.pool_tiles) continue;
-        if (atomicCAS(&mark[t], RB_NONE, 0xFFFFFFFEu) == RB_NONE) list[atomicAdd(count, 1)] = t;
+        if (atomicCAS(&mk[t], RB_NONE, 0xFFFFFFFEu) == RB_NONE) {
+            const int idx = atomicAdd(count, 1);
+            if ((uint32_t)idx < c.pool_tiles) { list[idx] = t; list_rank[idx] = (unsigned char)r; }
+            else atomicExch(&c.flags->pool_exhausted, 1);
+        }
     }
 }
 
 // pass 2: a fresh local sub-tile for every claimed remote one, payload copied across
-// the link (grid-stride over the device-side count); mark[remote] = local index
-__global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeer peer, uint32_t *mark, const uint32_t *__restrict__ list,
-                                                         const int *count)
+// the link (grid-stride over the device-side count); mark = local index
+__global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeers peers, uint32_t *mark, const uint32_t *__restrict__ list,
+                                                         const unsigned char *__restrict__ list_rank, const int *count)
 {
     __shared__ uint32_t s_t;
-    const int n = *count;
+    const int n = min(*count, (int)c.pool_tiles);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t rt = list[i];
+        const int r = list_rank[i];
         if (threadIdx.x == 0) {
             const int idx = atomicSub(c.free_count, 1) - 1;
-            if (idx < 0) { atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
+            if (idx < 0) { atomicAdd(c.free_count, 1); atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
             else { s_t = c.free_list[idx]; c.refcnt[s_t] = 0u; }
-            mark[rt] = s_t == RB_NONE ? 0xFFFFFFFDu : s_t;
+            mark[(size_t)r * c.pool_tiles + rt] = s_t == RB_NONE ? 0xFFFFFFFDu : s_t;
         }
         __syncthreads();
         const uint32_t t = s_t;
         if (t != RB_NONE) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(peer.pool + (size_t)rt * RB_SUB_BYTES);
+            const uint4 *src = reinterpret_cast<const uint4 *>(peers.p[r].pool + (size_t)rt * RB_SUB_BYTES);
             uint4 *dst = reinterpret_cast<uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES);
             for (int q = threadIdx.x; q < RB_SUB_BYTES / 16; q += blockDim.x) dst[q] = src[q];
         }
@@ -196,13 +214,15 @@ __global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeer peer, u
     }
 }
 
-// pass 3: destination slot j becomes a copy of remote particle src_slots[rec_idx[j]]
-__global__ void pull_place_kernel(RbCtx c, RbPeer peer, const int *__restrict__ src_slots, const int *__restrict__ dst_slots,
-                                  const int *__restrict__ rec_idx, int m, const uint32_t *__restrict__ mark)
+// pass 3: a local slot with a remote ancestor becomes a copy of that particle
+__global__ void pull_place_kernel(RbCtx c, RbPeers peers, const uint32_t *__restrict__ mark)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= m) return;
-    const int j = dst_slots[warp], s = src_slots[rec_idx[warp]];
+    if (warp >= c.N) return;
+    int r, s;
+    if (!pull_source(c, warp, r, s)) return;
+    const int j = warp;
+    const RbPeer &peer = peers.p[r];
     if (lane < 3) c.pose2[3 * (size_t)j + lane] = peer.pose[3 * (size_t)s + lane];
     if (lane < 9) c.cov2[9 * (size_t)j + lane] = peer.cov[9 * (size_t)s + lane];
     if (lane == 0) {
@@ -210,12 +230,13 @@ __global__ void pull_place_kernel(RbCtx c, RbPeer peer, const int *__restrict__ 
         c.weight[j] = 1.0;                                                   // main.py:77-78
     }
     const uint32_t *src = peer.pt + (size_t)s * c.nsub;
+    const uint32_t *mk = mark + (size_t)r * c.pool_tiles;
     uint32_t *dst = c.pt2 + (size_t)j * c.nsub;
     for (int e = lane; e < c.nsub; e += 32) {
         const uint32_t rt = src[e];
         uint32_t t = RB_NONE;
         if (rt != RB_NONE && rt < c.pool_tiles) {
-            t = mark[rt];
+            t = mk[rt];
             if (t >= c.pool_tiles) t = RB_NONE;                              // pool exhausted (flag is set)
         }
         dst[e] = t;
@@ -224,21 +245,23 @@ __global__ void pull_place_kernel(RbCtx c, RbPeer peer, const int *__restrict__ 
 }
 
 // pass 4: release the claims
-__global__ void pull_release_kernel(uint32_t *mark, const uint32_t *__restrict__ list, const int *count)
+__global__ void pull_release_kernel(RbCtx c, uint32_t *mark, const uint32_t *__restrict__ list,
+                                    const unsigned char *__restrict__ list_rank, const int *count)
 {
-    const int n = *count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mark[list[i]] = RB_NONE;
+    const int n = min(*count, (int)c.pool_tiles);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        mark[(size_t)list_rank[i] * c.pool_tiles + list[i]] = RB_NONE;
 }
 
-void rb_launch_migrate_pull(const RbCtx &c, const RbPeer &peer, const int *src_slots_dev, int n_src, const int *dst_slots_dev,
-                            const int *rec_idx_dev, int m, uint32_t *mark, uint32_t *list, int *count, cudaStream_t s)
+void rb_launch_migrate_pull(const RbCtx &c, const RbPeers &peers, uint32_t *mark, uint32_t *list, unsigned char *list_rank,
+                            int *count, cudaStream_t s)
 {
-    if (n_src <= 0 || m <= 0) return;
+    const int wblocks = (c.N * 32 + 255) / 256;
     cudaMemsetAsync(count, 0, sizeof(int), s);
-    pull_claim_kernel<<<(n_src * 32 + 255) / 256, 256, 0, s>>>(c, peer, src_slots_dev, n_src, mark, list, count);
-    pull_tiles_kernel<<<148 * 8, 256, 0, s>>>(c, peer, mark, list, count);
-    pull_place_kernel<<<(m * 32 + 255) / 256, 256, 0, s>>>(c, peer, src_slots_dev, dst_slots_dev, rec_idx_dev, m, mark);
-    pull_release_kernel<<<148, 256, 0, s>>>(mark, list, count);
+    pull_claim_kernel<<<wblocks, 256, 0, s>>>(c, peers, mark, list, list_rank, count);
+    pull_tiles_kernel<<<148 * 8, 256, 0, s>>>(c, peers, mark, list, list_rank, count);
+    pull_place_kernel<<<wblocks, 256, 0, s>>>(c, peers, mark);
+    pull_release_kernel<<<148, 256, 0, s>>>(c, mark, list, list_rank, count);
 }
 
 size_t rb_migrate_bytes(int n, int n_tiles, int nsub) { return mg_header_bytes(n, nsub) + (size_t)n_tiles * RB_SUB_BYTES; }

@@ -152,27 +152,30 @@ class MigratingSet(ParticleSet):
         v = L.RbpfPeerView.from_buffer_copy(view_bytes)
         self._ck(self._lib.rbpf_peer_attach(self._h, int(peer_rank), C.byref(v)))
 
-    def plan_and_pull(self, weights_all, u01=None):
+    def plan_and_pull(self, weights_all, u01=None, check=True):
         """Global resample on the gathered weights, then pull every remote ancestor this
-        rank needs through the peer mappings (asynchronous).  The caller must make sure
-        every rank has finished pulling before any rank calls finish_resample()."""
+        rank needs through the peer mappings.  The plan is the ancestor vector on the
+        device: with check=False nothing is copied to the host and nothing waits (errors
+        surface at the next synchronising call); check=True also fetches the ancestors and
+        the reference's resample assertion.  The caller must make sure every rank has
+        finished pulling before any rank calls finish_resample()."""
         lib = self._lib
-        did = C.c_int32(0)
         up = None
         if u01 is not None:
             u = C.c_double(float(u01))
             up = C.cast(C.byref(u), C.POINTER(C.c_double))
-        self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, C.byref(did),
-                                          self._anc.ctypes.data_as(_ip)))
-        _, recv, src = plan_migration(self._anc, self.N, self.rank, self.world, want_sources=True)
-        for r, (dst_slots, rec_idx, n_rec) in recv.items():
-            if n_rec == 0:
-                continue
-            s = src[r]
-            self._ck(lib.rbpf_migrate_pull(self._h, r, s.ctypes.data_as(_ip), len(s), dst_slots.ctypes.data_as(_ip),
-                                           rec_idx.ctypes.data_as(_ip), len(dst_slots)))
-            self.migrated_particles += len(s)
-        return bool(did.value)
+        did = None
+        if check:
+            d = C.c_int32(0)
+            self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, C.byref(d),
+                                              self._anc.ctypes.data_as(_ip)))
+            did = bool(d.value)
+            mine = self._anc[self.rank * self.N:(self.rank + 1) * self.N] // self.N
+            self.migrated_particles += int(np.count_nonzero(mine != self.rank))
+        else:
+            self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, None, None))
+        self._ck(lib.rbpf_migrate_pull(self._h))
+        return did
 
     def finish_resample(self):
         self._ck(self._lib.rbpf_resample_apply_local(self._h))
@@ -251,7 +254,7 @@ class ShardedParticleSet(MigratingSet):
         if prof is not None:
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-        did = self.plan_and_pull(self._w_all, u01)
+        did = self.plan_and_pull(self._w_all, u01, check=want_ancestors)
         if prof is not None:
             torch.cuda.synchronize()
             t2 = time.perf_counter()
