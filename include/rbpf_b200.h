@@ -164,6 +164,9 @@ int rbpf_get_match(rbpf_handle h, double *pose_n3, double *cov_n9, double *score
 int rbpf_get_match_refine(rbpf_handle h, int32_t *out_n2);
 /* Switch the NDT stage on or off for the following matches (initially rbpf_config.flags & RBPF_FLAG_NDT_REFINE). */
 int rbpf_set_refine(rbpf_handle h, int32_t on);
+/* Running sum of the adjusted weights of the last triggered resample (main.py:57,62),
+ * n_global doubles; for parity checks of the float64 summation order. */
+int rbpf_get_resample_cumsum(rbpf_handle h, double *out_n_global);
 /* Inject matcher results (pose[N*3], cov[N*9], valid[N]) in place of
  * rbpf_scan_match -- the seam at which the reference calls MATLAB
  * (hybridmap.py:244-256); lets the weighting stage be checked against the

@@ -432,6 +432,61 @@ def test_resample_vs_oracle_sizes(PS, n):
     assert np.array_equal(ps.poses, poses[anc])                    # Robot.copy robot.py:141-149
 
 
+def _cumsum_cases():
+    rng = np.random.default_rng(77)
+    n = 20000
+    cases = {}
+    cases["lognormal"] = np.exp(rng.normal(5.0, 3.0, n))
+    cases["negative_shift"] = rng.normal(0, 1, n) * 1e6 - 3e5                 # main.py:54-55 path, some -inf
+    cases["negative_shift"][rng.integers(0, n, 5)] = -np.inf
+    w = np.ones(n)
+    w[0] = 2.0 ** 53                                                         # every later add is a tie: 2^53 + 1 -> 2^53
+    cases["all_ties"] = w
+    w = rng.integers(1, 9, n).astype(np.float64) * 0.5                       # halves and integers: ties at every binade
+    w[::97] = 1000.0
+    cases["halves"] = w
+    w = np.exp(rng.normal(0.0, 1.0, n))
+    w[rng.integers(0, n, n // 3)] = 0.0                                      # zeros are skipped by the shift and add exactly
+    w[7] = 500.0
+    cases["zeros"] = w
+    w = np.exp(rng.normal(0.0, 12.0, n))                                     # 30 binades of dynamic range
+    cases["wide"] = w
+    w = np.full(n, 5e-324)
+    w[:3] = [1e-310, 300.0, 2.2250738585072014e-308]                         # denormals next to normal weights
+    cases["denormals"] = w
+    w = 2.0 ** rng.integers(-30, 11, n).astype(np.float64)                   # powers of two: exact halves of an ulp are common
+    cases["powers_of_two"] = w
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_cumsum_cases().keys()))
+def test_resample_running_sum_bit_exact(PS, name):
+    """The running sum of the weights is the one quantity of the path whose float64
+    ROUNDING ORDER matters (main.py:57,62 adds left to right).  The kernel replaces the
+    chain of N dependent adds by an exact integer prefix sum wherever the sum stays in one
+    binade and no add is a tie; every c_i must equal the sequential sum bit for bit."""
+    w = _cumsum_cases()[name]
+    n = len(w)
+    ps = PS(n, 180, world_tiles=(1, 1), pool_subtiles=64)
+    ps.weights = w
+    did, anc = ps.resample(0.618)
+    assert did
+    adj = np.where(np.isneginf(w), 0.0, w)
+    mn = adj.min()
+    if mn < 0:
+        adj = np.where(adj != 0.0, adj + abs(mn), adj)                       # main.py:54-55
+    ref = np.empty(n)
+    c = 0.0
+    for i, v in enumerate(adj.tolist()):                                     # plain Python floats: sequential float64
+        c += v
+        ref[i] = c
+    got = ps.resample_cumsum()
+    bad = np.flatnonzero(got.view(np.uint64) != ref.view(np.uint64))
+    assert bad.size == 0, "first mismatch at %d: %r vs %r" % (bad[0], got[bad[0]], ref[bad[0]])
+    rc, oanc = O.resample(w, 0.618)
+    assert rc == 1 and np.array_equal(anc, oanc)
+
+
 def test_resample_not_triggered_keeps_particles(PS):
     ps = PS(64, 180, world_tiles=(1, 1), pool_subtiles=64)
     w = np.linspace(1.0, 150.0, 64)                                # max - min <= 200, main.py:50

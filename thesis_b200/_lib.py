@@ -70,6 +70,7 @@ SIGNATURES = {
     "rbpf_get_match": (C.c_int, [_H, _dp, _dp, _dp, _ip, _ip]),
     "rbpf_get_match_refine": (C.c_int, [_H, _ip]),
     "rbpf_set_refine": (C.c_int, [_H, C.c_int32]),
+    "rbpf_get_resample_cumsum": (C.c_int, [_H, _dp]),
     "rbpf_set_match": (C.c_int, [_H, _dp, _dp, _ip]),
     "rbpf_get_match_slice": (C.c_int, [_H, C.c_int32, _ip]),
     "rbpf_export_tile": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, _dp, _ip]),

@@ -507,6 +507,12 @@ extern "C" int rbpf_get_match(rbpf_handle h, double *pose, double *cov, double *
     return rc;
 }
 
+extern "C" int rbpf_get_resample_cumsum(rbpf_handle h, double *out)
+{
+    if (!h || !out) return RBPF_ERR_ARG;
+    return copy_out(h, out, h->d.w_all, sizeof(double) * (size_t)h->d.n_global);
+}
+
 extern "C" int rbpf_get_match_refine(rbpf_handle h, int32_t *out)
 {
     if (!h || !out) return RBPF_ERR_ARG;

@@ -6,10 +6,12 @@
 //
 // resample_plan   one CTA over the (all-gathered) weights of ALL ranks:
 //                   min/max and trigger (main.py:50), -inf -> 0 (:53), additive
-//                   shift of the non-zero entries (:54-55), the running sum in
-//                   the reference's left-to-right order (:57,:61-62 -- a single
-//                   thread, because float64 addition is not associative and the
-//                   ancestors must be bit-exact), then ancestors in parallel.
+//                   shift of the non-zero entries (:54-55), the running sum with
+//                   the reference's left-to-right float64 roundings (:57,:61-62;
+//                   float64 addition is not associative and the ancestors must be
+//                   bit-exact: an exact integer prefix sum while the sum stays in
+//                   one binade, a single-thread chain otherwise), then ancestors
+//                   in parallel.
 //                 Every rank runs it on identical input and gets identical output.
 // resample_gather builds the new particle slots of this rank from the ancestor
 //                 vector: pose, covariance, weight <- 1.0 (main.py:77-78),
@@ -20,13 +22,14 @@
 #include "common.cuh"
 
 #define RS_THREADS 1024
-#define RS_CHUNK 2048
+static_assert(RS_THREADS == 1024, "the block scan assumes 32 warps");
 
 __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, const double *__restrict__ w_in,
                                                                    const double *__restrict__ u01_in)
 {
     __shared__ double red_mx[32], red_mn[32];
-    __shared__ double chunk[2][RS_CHUNK];
+    __shared__ double chunk[RS_THREADS];
+    __shared__ long long scan_tot[32];
     __shared__ double s_mn2, s_carry, s_slice, s_start;
     __shared__ int s_do;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -76,50 +79,106 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
     __syncthreads();
     const double shift = s_mn2 < 0.0 ? fabs(s_mn2) : 0.0;
     const bool do_shift = s_mn2 < 0.0;
-    // running sum, chunk by chunk: the other threads stage chunk k+1 and write chunk k-1
-    // back while thread 0 runs the sequential float64 chain over chunk k (two shared
-    // buffers); the chain keeps eight values in registers so that consecutive adds are
-    // back to back (the chain is bound by the DADD latency, nothing else).
-    const int n_chunks = (NG + RS_CHUNK - 1) / RS_CHUNK;
-    for (int k = -1; k < n_chunks; k++) {
-        if (tid == 0) {
-            if (k >= 0 && k < n_chunks) {
-                double *ch = chunk[k & 1];
-                const int n = min(RS_CHUNK, NG - k * RS_CHUNK);
-                double cur = s_carry;
-                int i = 0;
-                for (; i + 8 <= n; i += 8) {
-                    double v[8];
+    // running sum c_i = fl(c_{i-1} + v_i) (main.py:57 == :62), float64, round to nearest even:
+    // inherently a chain of N dependent adds -- except that while the sum stays inside one
+    // binade [2^k, 2^(k+1)) every add rounds to a multiple of u = 2^(k-52).  With S = c/u
+    // (an integer in [2^52, 2^53)) and v = (m + f) u, m integer, 0 <= f < 1:
+    //     S' = S + m + [f > 1/2]          (f == 1/2, a tie, depends on the parity of S + m)
+    // so a chunk without ties that does not leave the binade is an exact INTEGER prefix sum,
+    // done in parallel (one element per thread, two barriers).  Chunks with a tie, a
+    // binade crossing, a denormal or the very first chunk take the sequential chain.
+    const int n_chunks = (NG + RS_THREADS - 1) / RS_THREADS;
+    const unsigned long long MANT = (1ull << 52) - 1ull;
+    double carry = 0.0;                                                      // uniform over the block
+    auto load = [&](int i) {
+        double v = 0.0;
+        if (i < NG) {
+            v = w[i];
+            if (do_shift && v != 0.0) v += shift;                            // main.py:55
+        }
+        return v;
+    };
+    double v_next = load(tid);
+    for (int k = 0; k < n_chunks; k++) {
+        const int i = k * RS_THREADS + tid;
+        const bool active = i < NG;
+        const double v = v_next;
+        v_next = load(i + RS_THREADS);
+        const unsigned long long cb = (unsigned long long)__double_as_longlong(carry);
+        const int kexp = (int)((cb >> 52) & 0x7ffull);
+        const bool fast_ok = !(cb >> 63) && kexp >= 54 && kexp < 0x7ff;      // carry > 0, normal, u normal
+        long long a = 0;
+        bool slow = !fast_ok;
+        if (active && fast_ok && v != 0.0) {
+            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+            const int ve = (int)((vb >> 52) & 0x7ffull);
+            if ((vb >> 63) || ve == 0x7ff || ve == 0) slow = true;           // negative, inf / nan, denormal
+            else {
+                const unsigned long long M = (vb & MANT) | (1ull << 52);
+                const int sft = kexp - ve;
+                if (sft < 1) slow = true;                                    // v >= 2^k: the sum leaves the binade
+                else if (sft <= 54) {
+                    const unsigned long long r = M & ((1ull << sft) - 1ull), half = 1ull << (sft - 1);
+                    a = (long long)(M >> sft);
+                    if (r > half) a += 1;
+                    else if (r == half) slow = true;                         // tie
+                }                                                            // sft > 54: v < u/4, rounds away
+            }
+        }
+        bool done = false;
+        if (!__syncthreads_or(slow)) {
+            // inclusive integer scan over the block
+            long long p = a;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] = ch[i + e];
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long q = __shfl_up_sync(0xffffffffu, p, o);
+                if (lane >= o) p += q;
+            }
+            if (lane == 31) scan_tot[warp] = p;
+            __syncthreads();
+            long long t = scan_tot[lane];                                    // RS_THREADS / 32 == 32 warps
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { cur += v[e]; v[e] = cur; } // main.py:57 == :62
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long q = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += q;
+            }
+            const long long total = __shfl_sync(0xffffffffu, t, 31);
+            const long long before = warp ? __shfl_sync(0xffffffffu, t, warp - 1) : 0ll;
+            const unsigned long long S_in = (cb & MANT) | (1ull << 52);
+            if (S_in + (unsigned long long)total < (1ull << 53)) {            // stays in the binade
+                const unsigned long long hi = (unsigned long long)kexp << 52;
+                if (active) w[i] = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)(before + p)) & MANT)));
+                carry = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)total) & MANT)));
+                done = true;
+            }
+            __syncthreads();                                                 // scan_tot is reused by the next chunk
+        }
+        if (!done) {                                                         // sequential chain for this chunk
+            chunk[tid] = v;
+            __syncthreads();
+            if (tid == 0) {
+                const int n = min(RS_THREADS, NG - k * RS_THREADS);
+                double cur = carry;
+                int e0 = 0;
+                for (; e0 + 8 <= n; e0 += 8) {
+                    double x[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) ch[i + e] = v[e];
+                    for (int e = 0; e < 8; e++) x[e] = chunk[e0 + e];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { cur += x[e]; x[e] = cur; }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) chunk[e0 + e] = x[e];
                 }
-                for (; i < n; i++) { cur += ch[i]; ch[i] = cur; }
+                for (; e0 < n; e0++) { cur += chunk[e0]; chunk[e0] = cur; }
                 s_carry = cur;
             }
-        } else {
-            if (k + 1 < n_chunks) {                                          // stage the next chunk
-                double *ch = chunk[(k + 1) & 1];
-                const int base = (k + 1) * RS_CHUNK, n = min(RS_CHUNK, NG - base);
-                for (int i = tid - 1; i < n; i += RS_THREADS - 1) {
-                    double v = w[base + i];
-                    if (do_shift && v != 0.0) v += shift;                    // main.py:55
-                    ch[i] = v;
-                }
-            }
+            __syncthreads();
+            if (active) w[i] = chunk[tid];
+            carry = s_carry;
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid != 0 && k >= 0 && k < n_chunks) {                            // chunk k is final: write it back
-            const double *ch = chunk[k & 1];
-            const int base = k * RS_CHUNK, n = min(RS_CHUNK, NG - base);
-            for (int i = tid - 1; i < n; i += RS_THREADS - 1) w[base + i] = ch[i];
-        }
-        // the write-back of chunk k overlaps the chain of chunk k+1; buffer k&1 is staged
-        // again at iteration k+1 (for chunk k+2) only after the next barrier
     }
+    if (tid == 0) s_carry = carry;
     __syncthreads();
     if (tid == 0) {
         double slice = s_carry / (double)NG;                                 // main.py:57

@@ -184,6 +184,12 @@ class ParticleSet:
         return dict(pose=pose, cov=cov, score=score, valid=valid.astype(bool), best=best,
                     ndt_evals=refine[:, 0].copy(), ndt_accepted=refine[:, 1].astype(bool))
 
+    def resample_cumsum(self):
+        """Running sum of the adjusted weights of the last triggered resample (main.py:57,62)."""
+        out = np.empty(self.N * self.world)
+        self._ck(self._lib.rbpf_get_resample_cumsum(self._h, out.ctypes.data_as(_dp)))
+        return out
+
     def set_refine(self, on):
         """Switch the NDT stage (matchScanCustom.m:32-50) on or off for the following matches."""
         self._ck(self._lib.rbpf_set_refine(self._h, 1 if on else 0))
