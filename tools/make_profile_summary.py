@@ -74,6 +74,37 @@ def main():
            "Roofline entry of the JSON line: match_kernel, %.0f GB/s algorithmic = %.1f %% of the measured %.0f GB/s -- the"
            % (b["roofline"]["achieved"], 100 * b["roofline"]["frac"], b["roofline"]["peak"]),
            "kernel is bound by instruction issue / shared-memory lookups (see below), not by HBM.", ""]
+    nd = os.path.join(P, "r1_bench_n1_65536p_ndt.json")
+    if os.path.exists(nd):
+        n = json.load(open(nd))
+        md += ["With the NDT refinement stage of the matcher on (`bench.py --refine 1`, `r1_bench_n1_65536p_ndt.json`): %.0f updates/s,"
+               % n["value"],
+               "%.2f ms/step, match stage %.2f ms; %.1f NDT score evaluations per search, %.0f %% of the refined poses accepted."
+               % (n["ms_per_step"], n["stage_ms_per_step"]["match"], n["config"]["ndt_evaluations_per_search"],
+                  100 * n["config"]["ndt_accepted_fraction"]),
+               "An `ncu --set full` source view of that launch (8,192 particles) puts 43 % of the kernel's warp samples in the NDT",
+               "stage: 52 % of those in the per-beam fp64 evaluation, 11 % waiting for the slowest warp at the first barrier, 36 %",
+               "waiting for warp 0 (totals, 3x3 Cholesky solves, sin/cos of the next proposal) at the second.", ""]
+    sc = []
+    for g in (2, 4, 8):
+        f = os.path.join(P, "r1_scale_n%d.json" % g)
+        if os.path.exists(f):
+            sc.append((g, json.load(open(f))))
+    if sc:
+        md += ["## Strong scaling, 65,536 particles over N GPUs (`torchrun ... bench.py --gpus N --steps 20 --warmup 5`)", "",
+               "| GPUs | updates/s | ms/step | efficiency vs N=1 | match | weight | ray-cast | resample + exchange |", "|---|---|---|---|---|---|---|---|",
+               "| 1 | %.0f | %.2f | 100 %% | %.2f | %.2f | %.2f | %.2f |"
+               % (b["value"], b["ms_per_step"], b["stage_ms_per_step"]["match"], b["stage_ms_per_step"]["weight"],
+                  b["stage_ms_per_step"]["raycast_prepare"] + b["stage_ms_per_step"]["raycast_cast"] + b["stage_ms_per_step"]["weight_fallback"],
+                  b["stage_ms_per_step"]["resample_plan"] + b["stage_ms_per_step"]["resample_apply"])]
+        for g, d in sc:
+            st = d["stage_ms_per_step"]
+            md.append("| %d | %.0f | %.2f | %.0f %% | %.2f | %.2f | %.2f | %.2f |"
+                      % (g, d["value"], d["ms_per_step"], 100 * d["value"] / (g * b["value"]), st["match"], st["weight"],
+                         st["raycast_cast"], st["resample_plan"]))
+        md += ["", "`r1_scale_n{2,4,8}.json`.  Exchange = NCCL all-gather of the weights, the global plan on every rank, pull of the",
+               "remote ancestors' page tables and sub-tiles over NVLink peer mappings, a one-element all-reduce as barrier,",
+               "local gather / reference counts (thesis_b200/dist.py, transport \"peer\").", ""]
     for tag, title in (("final", "final kernels"),
                        ("baseline", "first working version: exhaustive 231-rotation matcher, per-cell closed-form ray-cast")):
         f = os.path.join(P, "r1_launches_8192p_%s.csv" % tag)
