@@ -72,3 +72,32 @@ def test_resample_assertion_maps_to_python_assertion(P):
     else:
         # NaN compares false everywhere: max - min > 200 may not fire; then nothing must have changed
         assert np.array_equal(ps.poses, poses if not did else poses[anc])
+
+
+def test_peer_mapping_errors(P):
+    """Pull migration (include/rbpf_b200.h rbpf_peer_*): a peer whose layout differs, a
+    second attach, an unattached peer and the handle's own rank are refused with a status."""
+    from thesis_b200 import dist as D
+
+    a = D.MigratingSet(8, 180, 0, 2, pool_subtiles=300)
+    b = D.MigratingSet(8, 180, 1, 2, pool_subtiles=300)
+    other_pool = D.MigratingSet(8, 180, 1, 2, pool_subtiles=200)
+    other_n = D.MigratingSet(16, 180, 1, 2, pool_subtiles=300)
+    with pytest.raises(P.RbpfError):
+        a._ck(a._lib.rbpf_migrate_pull(a._h))                 # nobody attached yet
+    with pytest.raises(P.RbpfError, match="differs"):
+        a.attach_peer(1, other_pool.peer_view())
+    with pytest.raises(P.RbpfError, match="differs"):
+        a.attach_peer(1, other_n.peer_view())
+    with pytest.raises(P.RbpfError):
+        a.attach_peer(0, b.peer_view())                       # own rank
+    with pytest.raises(P.RbpfError):
+        a.attach_peer(2, b.peer_view())                       # outside the world
+    a.attach_peer(1, b.peer_view())
+    with pytest.raises(P.RbpfError, match="already"):
+        a.attach_peer(1, b.peer_view())
+    # buffers flipped on one side only: the parities disagree and the attach is refused
+    c = D.MigratingSet(8, 180, 0, 2, pool_subtiles=300)
+    b._ck(b._lib.rbpf_resample_commit(b._h))
+    with pytest.raises(P.RbpfError, match="differs"):
+        c.attach_peer(1, b.peer_view())
