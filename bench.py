@@ -329,7 +329,10 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(args.steps * (11 if world == 1 else 19)),
+        # kernels of _librbpf.so per step (ncu launch list in profiles/): motion, match, match_copy_dups, weight x2
+        # (samples + fallback), raycast prepare + cast, resample plan, mult, gather, refs, dups = 12; sharded runs add
+        # the four pull kernels (claim, tiles, place, release); NCCL's own kernels are not counted
+        "gpu_launches": int(args.steps * (12 if world == 1 else 16)),
         "roofline": {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": MATCH_DRAM_BYTES_PER_UPDATE_NCU * n_local,
                      "traffic_source": "ncu --set full on an 8,192-particle launch, scaled per update", "peak_source": peak_src,
