@@ -328,7 +328,9 @@ def run_b200(args):
                        match_full_pass_equivalents_per_update=st["match_visits"] / max(1, st["match_points"])),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h)},
+                "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h),
+                "note": "the K scans that follow the device-timed ones on the same trajectory (the state cannot be rewound); "
+                        "work per scan varies with the ray lengths, so e2e and value are not the same scans"},
         # kernels of _librbpf.so per step (ncu launch list in profiles/): motion, match, match_copy_dups, weight x2
         # (samples + fallback), raycast prepare + cast, resample plan, mult, gather, refs, dups = 12; sharded runs add
         # the four pull kernels (claim, tiles, place, release); NCCL's own kernels are not counted
