@@ -24,13 +24,22 @@ def mods():
     return particles, synth
 
 
-def test_config2_intel_1024_particles_vs_oracle(mods, golden):
+@pytest.fixture()
+def oracle_refine(request):
+    old = O.set_refine(bool(request.param))
+    yield bool(request.param)
+    O.set_refine(old)
+
+
+@pytest.mark.parametrize("oracle_refine", [False, True], indirect=True)
+def test_config2_intel_1024_particles_vs_oracle(mods, golden, oracle_refine):
     """configs[1]: Intel log, 1,024 particles, 180-beam scans, one GPU -- two scans
-    with host-supplied draws against the oracle (ancestors bit-exact)."""
+    with host-supplied draws against the oracle (ancestors bit-exact); also with the
+    NDT stage of the matcher on in both."""
     P, _ = mods
     N, K, B = 1024, 30, 180
     rng = np.random.default_rng(4)
-    ps = P.ParticleSet(N, B, pool_subtiles=60000)
+    ps = P.ParticleSet(N, B, pool_subtiles=60000, ndt_refine=oracle_refine)
     f = O.Filter(N, B, K)
     ang = golden["intel_angles"]
     for _ in range(2):
@@ -58,13 +67,15 @@ def test_config2_intel_1024_particles_vs_oracle(mods, golden):
     assert st["refcount_sum"] == st["total_refs"]
 
 
-def test_identical_particles_stay_identical_at_8192(mods):
+@pytest.mark.parametrize("refine", [False, True])
+def test_identical_particles_stay_identical_at_8192(mods, refine):
     """configs[2]-sized set (8,192 particles): identical inputs and identical draws
-    must give identical poses, weights and maps for every particle."""
+    must give identical poses, weights and maps for every particle (also with the
+    NDT stage: its reductions have a fixed order)."""
     P, synth = mods
     N, K, B = 8192, 30, 360
     w = synth.Workload(5, n_beams=B)
-    ps = P.ParticleSet(N, B, pool_subtiles=N * 30)
+    ps = P.ParticleSet(N, B, pool_subtiles=N * 30, ndt_refine=refine)
     ps.set_scan(w.ranges[0], w.angles); ps.integrate(); ps.integrate()
     rng = np.random.default_rng(0)
     for s in range(1, 4):

@@ -24,6 +24,8 @@
 //   4. bit-sliced max + tie-break key per lane, warp-shuffle argmax, CTA argmax.
 //   5. covariance from the score slice at the best rotation and the score line
 //      at the best translation (integer moments, weights 2^(score - best)).
+//   5b. optional NDT refinement of the grid optimum (matchScanCustom.m:32-50) on the
+//      same bitmap, thread = beam: ndt_partial / ndt_refine below, DESIGN.md 3.1-8.
 //
 // Branch and bound over rotations (exact): rotations are grouped by MT_GROUP
 // consecutive lattice steps.  A point at range <= 11 m moves at most one cell per
