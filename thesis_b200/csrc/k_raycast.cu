@@ -124,6 +124,10 @@ __device__ __forceinline__ bool particle_frame(const RbCtx &c, int p, double &x,
 
 // ------------------------------------------------------------- prepare --
 
+#ifndef RC_COPY_UNROLL
+#define RC_COPY_UNROLL 5                // 16-byte loads in flight per lane of a copy-on-write sub-tile copy
+#endif
+constexpr int kCopyUnroll = RC_COPY_UNROLL;
 __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
 {
     __shared__ uint32_t mask_s[RC_WARPS][52];                      // 64 tiles * 25 sub-tiles = 1600 bits
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
                 for (int q = lane; q < RB_SUB_BYTES / 16; q += 32) dst[q] = z;
             } else {
                 const uint4 *src = reinterpret_cast<const uint4 *>(c.pool + (size_t)told * RB_SUB_BYTES);
-#pragma unroll 5
+#pragma unroll kCopyUnroll
                 for (int q = lane; q < RB_SUB_BYTES / 16; q += 32) dst[q] = src[q];
             }
             if (lane == 0) pt[sub] = tnew;
