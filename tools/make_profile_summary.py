@@ -105,6 +105,21 @@ def main():
         md += ["", "`r1_scale_n{2,4,8}.json`.  Exchange = NCCL all-gather of the weights, the global plan on every rank, pull of the",
                "remote ancestors' page tables and sub-tiles over NVLink peer mappings, a one-element all-reduce as barrier,",
                "local gather / reference counts (thesis_b200/dist.py, transport \"peer\").", ""]
+    w8 = os.path.join(P, "r1_bench_n1_8192p.json")
+    s8 = os.path.join(P, "r1_scale_n8.json")
+    if os.path.exists(w8) and os.path.exists(s8):
+        a1, a8 = json.load(open(w8)), json.load(open(s8))
+        md += ["Weak scaling at 8,192 particles per GPU (SURVEY 8d): 1 GPU x 8,192 = %.0f updates/s (%.2f ms/step, `r1_bench_n1_8192p.json`),"
+               % (a1["value"], a1["ms_per_step"]),
+               "8 GPUs x 8,192 = %.0f updates/s (%.2f ms/step): %.0f %% -- the exchange adds %.2f ms to a rank's scan." %
+               (a8["value"], a8["ms_per_step"], 100 * a8["value"] / (8 * a1["value"]), a8["ms_per_step"] - a1["ms_per_step"]), ""]
+    fr = os.path.join(P, "r1_bench_n1_65536p_fresh.json")
+    if os.path.exists(fr):
+        f = json.load(open(fr))
+        md += ["Divergence regimes (SURVEY 8d): the headline line is the DIVERGED regime (30 burn-in scans with resampling, unique",
+               "sub-tile fraction %.2f: descendants of one ancestor share what they have not written since); FRESH (`bench.py --burnin 0 --warmup 3 --steps 5`, scans 4-8 of a new map, unique fraction %.2f,"
+               % (b["config"]["unique_subtile_fraction"], f["config"]["unique_subtile_fraction"]),
+               "`r1_bench_n1_65536p_fresh.json`): %.0f updates/s, %.2f ms/step." % (f["value"], f["ms_per_step"]), ""]
     for tag, title in (("final", "final kernels"),
                        ("baseline", "first working version: exhaustive 231-rotation matcher, per-cell closed-form ray-cast")):
         f = os.path.join(P, "r1_launches_8192p_%s.csv" % tag)
