@@ -1,5 +1,5 @@
 """Development aid: step a 1,024-particle set and the oracle side by side and report where they first differ
-(weights, matcher results, map cells).  Run on a GPU box: python tools/compare_with_oracle_1024.py"""
+(weights, matcher results, map cells).  Run on a GPU box: python tests/dev_compare_with_oracle_1024.py (a checker like the tests: the only places that may load oracle/)"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
