@@ -211,6 +211,8 @@ class ShardedParticleSet(MigratingSet):
         self.transport = os.environ.get("RBPF_DIST_TRANSPORT", "peer")
         if self.transport not in ("peer", "nccl"):
             raise ValueError("RBPF_DIST_TRANSPORT must be 'peer' or 'nccl'")
+        if self.transport == "peer" and self.world > 16:       # RB_MAX_WORLD peer mappings per kernel launch
+            self.transport = "nccl"
         if self.transport == "peer":
             self._attach_all()
         self._prof = {} if os.environ.get("RBPF_DIST_PROFILE") else None   # host-side phase timers (adds syncs)
