@@ -35,7 +35,7 @@ MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
 # dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch over 8,192 particles
 # (profiles/r1_full_8192p_final_raw.csv), per update; below the algorithmic figure because
 # particles that share sub-tiles after a resample hit in L2
-MATCH_DRAM_BYTES_PER_UPDATE_NCU = 694.7e6 / 8192
+MATCH_DRAM_BYTES_PER_UPDATE_NCU = (853.2e6 + 5.4e6) / 8192
 
 
 def parse():
