@@ -44,31 +44,39 @@ def plan_migration(ancestors, n_local, rank, world, want_sources=False):
     this rank's particles form one contiguous interval: O(n_local) work.
     want_sources: also return src[r] = the sorted unique slots of rank r this rank
     needs (what a pulling receiver reads; equals rank r's send[rank])."""
-    anc = np.asarray(ancestors, dtype=np.int64)
+    anc = np.asarray(ancestors)
     lo_id, hi_id = rank * n_local, (rank + 1) * n_local
     empty = np.zeros(0, dtype=np.int32)
     send = {r: empty for r in range(world) if r != rank}
     recv = {r: (empty, empty, 0) for r in range(world) if r != rank}
     src_of = {r: empty for r in range(world) if r != rank}
-    # what leaves: global slots j whose ancestor is one of my particles and that live elsewhere
-    j0, j1 = np.searchsorted(anc, lo_id, "left"), np.searchsorted(anc, hi_id, "left")
-    if j1 > j0:
-        js = np.arange(j0, j1)
-        dst = js // n_local
-        for r in np.unique(dst):
-            if r != rank:
-                send[int(r)] = np.unique(anc[js[dst == r]] - lo_id).astype(np.int32)
-    # what arrives: my slots whose ancestor lives elsewhere
-    mine = anc[lo_id:hi_id]
-    src = mine // n_local
-    for r in np.unique(src):
+
+    def uniq_sorted(a):
+        """(unique values, index of every element in them) of a non-decreasing array, without sorting."""
+        first = np.empty(len(a), dtype=bool)
+        first[0] = True
+        np.not_equal(a[1:], a[:-1], out=first[1:])
+        return a[first], np.cumsum(first) - 1
+
+    # what leaves: global slots j in [j0, j1) have an ancestor among my particles; the part of that
+    # interval that lies in rank r's slice goes to r
+    j0, j1 = int(np.searchsorted(anc, lo_id, "left")), int(np.searchsorted(anc, hi_id, "left"))
+    for r in range(j0 // n_local, (j1 - 1) // n_local + 1 if j1 > j0 else 0):
         if r == rank:
             continue
-        m = src == r
-        needed = mine[m] - int(r) * n_local
-        uniq = np.unique(needed)
-        recv[int(r)] = (np.flatnonzero(m).astype(np.int32), np.searchsorted(uniq, needed).astype(np.int32), len(uniq))
-        src_of[int(r)] = uniq.astype(np.int32)
+        a, b = max(j0, r * n_local), min(j1, (r + 1) * n_local)
+        if b > a:
+            send[r] = (uniq_sorted(anc[a:b])[0] - lo_id).astype(np.int32)
+    # what arrives: my slots whose ancestor lives elsewhere (mine is non-decreasing: one interval per source rank)
+    mine = anc[lo_id:hi_id]
+    cuts = np.searchsorted(mine, np.arange(world + 1) * n_local, "left")
+    for r in range(world):
+        a, b = int(cuts[r]), int(cuts[r + 1])
+        if r == rank or b <= a:
+            continue
+        uniq, idx = uniq_sorted(mine[a:b])
+        recv[r] = (np.arange(a, b, dtype=np.int32), idx.astype(np.int32), len(uniq))
+        src_of[r] = (uniq - r * n_local).astype(np.int32)
     if want_sources:
         return send, recv, src_of
     return send, recv
