@@ -37,7 +37,7 @@
 // only while its bound can still beat the best key so far.  Every pass gives up
 // as soon as its best partial count plus the points still to come cannot reach
 // the best complete score (admissible).  The result is identical to the
-// exhaustive search of the oracle; ~31 full-pass equivalents instead of 231.
+// exhaustive search of the oracle; ~28 full-pass equivalents instead of 231.
 #include "common.cuh"
 
 #ifndef MT_GROUP
