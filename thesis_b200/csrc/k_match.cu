@@ -37,7 +37,7 @@
 // only while its bound can still beat the best key so far.  Every pass gives up
 // as soon as its best partial count plus the points still to come cannot reach
 // the best complete score (admissible).  The result is identical to the
-// exhaustive search of the oracle; ~28 full-pass equivalents instead of 231.
+// exhaustive search of the oracle; ~31 full-pass equivalents instead of 231.
 #include "common.cuh"
 
 #ifndef MT_GROUP
@@ -125,45 +125,18 @@ __device__ __forceinline__ uint32_t mt_pack4(uint32_t bytes)
 // the best complete score found so far (best_key, shared): when even hitting all
 // remaining points cannot reach it, the pass is abandoned (returns false).  The
 // bound is admissible, so the search result is unchanged.
-struct MatchShared;
-// Rasterise on demand: an abortable pass rotates and rasterises its points MT_LAZY_BLOCK at a time, just before it
-// scores them, so that a pass that gives up after 16 points has not paid for rotating all of them (most passes do).
-#define MT_LAZY_BLOCK 64
-struct MtLazy {
-    const RbCtx *c;
-    MatchShared *sh;
-    const double *ccx, *ccy;
-    uint32_t *pts;
-    int k, lane, shift_i, shift_j, span_i, span_j;
-};
-__device__ __forceinline__ void mt_rasterise_range(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
-                                                   uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j,
-                                                   int q0, int q1);
-
 template <bool ABORT>
-__device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *pts, int M,
+__device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
                                               int lane_off, uint32_t pl[MT_PLANES], uint32_t rowmask = 0u,
                                               const volatile unsigned long long *best_key = nullptr,
-                                              int *visited = nullptr, const MtLazy *lz = nullptr)
+                                              int *visited = nullptr)
 {
     uint32_t ones = 0, twos = 0, fours = 0;
 #pragma unroll
     for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
-    int q = 0, ras_end = lz ? 0 : M;
+    int q = 0;
     for (; q + 8 <= M; q += 8) {
-        if (q >= ras_end) {
-            mt_rasterise_range(*lz->c, lz->sh, lz->ccx, lz->ccy, lz->k, lz->pts, lz->lane, lz->shift_i, lz->shift_j,
-                               lz->span_i, lz->span_j, ras_end, ras_end + MT_LAZY_BLOCK);
-            ras_end += MT_LAZY_BLOCK;
-            __syncwarp();
-        }
-#ifndef MT_NO_EARLY_ABORT
-        // the best scores of a built map are close to M: a wrong rotation is over the miss budget after a few
-        // points, so the first checks come early (16, 32), then every MT_ABORT_EVERY points
-        if (ABORT && q && ((q & (MT_ABORT_EVERY - 1)) == 0 || q == 16 || q == 32)) {
-#else
         if (ABORT && q && (q & (MT_ABORT_EVERY - 1)) == 0) {
-#endif
             // bit-sliced max of the partial counts of this lane's row
             uint32_t cand = rowmask;
             int sc = 0;
@@ -201,11 +174,6 @@ __device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, c
         for (int p = 3; p < MT_PLANES; p++) { uint32_t t = pl[p] & e8; pl[p] ^= e8; e8 = t; }
     }
     pl[0] = ones; pl[1] = twos; pl[2] = fours;
-    if (q < M && q >= ras_end) {
-        mt_rasterise_range(*lz->c, lz->sh, lz->ccx, lz->ccy, lz->k, lz->pts, lz->lane, lz->shift_i, lz->shift_j,
-                           lz->span_i, lz->span_j, ras_end, ras_end + MT_LAZY_BLOCK);
-        __syncwarp();
-    }
     for (; q < M; q++) {                                                   // tail: plain ripple add
         const uint32_t pk = pts[q];
         const uint32_t a = (pk >> 5) + lane_off;
@@ -245,14 +213,13 @@ __device__ __forceinline__ unsigned long long mt_lane_key(const uint32_t pl[MT_P
 }
 
 // Rasterise the curr points for rotation k into packed bitmap addresses.
-__device__ __forceinline__ void mt_rasterise_range(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
-                                                   uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j,
-                                                   int q0, int q1)
+__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
+                                             uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j)
 {
     const double ck = c.rot_cs[2 * (k + c.nk)], sk = c.rot_cs[2 * (k + c.nk) + 1];
-    const int M = min(sh->M, q1);
+    const int M = sh->M;
     const int xoff = sh->g0xu - sh->x0 + shift_i, yoff = RB_WIN_R + shift_j;
-    for (int q = q0 + lane; q < M; q += 32) {
+    for (int q = lane; q < M; q += 32) {
         double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
         double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
         int ox = __double2int_rd(rxq * 20.0 + 0.5), oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
@@ -263,12 +230,6 @@ __device__ __forceinline__ void mt_rasterise_range(const RbCtx &c, MatchShared *
         }
         pts[q] = ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << 5) | (uint32_t)(bx & 31);
     }
-}
-
-__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
-                                             uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j)
-{
-    mt_rasterise_range(c, sh, ccx, ccy, k, pts, lane, shift_i, shift_j, span_i, span_j, 0, sh->M);
 }
 
 // curr point of beam j relative to the guess position (hybridmap.py:216-228,236,240; adj: :165-172)
@@ -759,9 +720,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             if (g >= ngroups) break;
             const int kmid = min(g * MT_GROUP + MT_GROUP / 2, nrot - 1) - c.nk;
             __syncwarp();
-            const MtLazy lz = {&c, sh, ccx, ccy, pts, kmid, lane, -nx, -ny, 2 * nx, 2 * ny};
+            mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+            __syncwarp();
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key, &visited, &lz);
+            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key, &visited);
             if (!done) {                                                    // even the bound cannot reach the seeded best
                 if (lane == 0) sh->group_ub[g] = -1;
                 continue;
@@ -810,9 +772,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             if (ub < (int)(cur >> 32)) break;                               // groups are sorted: nothing left can win
             if (mt_key(ub, 0, 0, k) < cur) continue;                        // this rotation cannot beat the best key
             __syncwarp();
-            const MtLazy lz = {&c, sh, ccx, ccy, pts, k, lane, -nx, -ny, 2 * nx, 2 * ny};
+            mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
+            __syncwarp();
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest, &visited, &lz);
+            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest, &visited);
             if (lane == 0) atomicAdd(&sh->evals, 1);
             if (!done) continue;                                            // cannot reach the best score any more
             unsigned long long key = 0ull;

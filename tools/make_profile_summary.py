@@ -135,7 +135,7 @@ def main():
     md += ["## Reading", "",
            "* `match_kernel`: ~70 % of issue slots busy, DRAM a few %: bound by instruction issue (LOP3 carry-save adders, LDS,",
            "  address arithmetic) of the bit-parallel scoring passes; the levers were fewer passes (exact branch and bound over",
-           "  rotation groups, seeding with the rotations around the guess, admissible early abort: 231 -> ~28 full-pass",
+           "  rotation groups, seeding with the rotations around the guess, admissible early abort: 231 -> ~31 full-pass",
            "  equivalents per update) and fewer instructions per pass.",
            "* `raycast_cast_kernel`: byte read-modify-writes along rays.  Baseline: ~15 sectors per store request, bound by L1/L2",
            "  sector traffic; not storing unchanged (saturated) cells, the 8x4-cell sector blocks and the interior fast path",
