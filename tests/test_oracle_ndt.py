@@ -130,3 +130,21 @@ def test_filter_runs_with_the_stage(golden, refine_on):
         f.set_scan(golden["intel_ranges"][si], golden["intel_angles"])
         f.map_update(rng.standard_normal((N, 30, 3)))
     assert np.isfinite(f.pose).all()
+
+
+def test_known_answers_of_the_restatement():
+    """tests/golden/ndt_oracle_kat.npz (made by tests/golden/make_ndt_regression.py) holds outputs of
+    OUR restatement, not of MathWorks matchScans: a regression pin, bit for bit."""
+    import os
+    import sys
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_ndt_regression as K
+
+    want = np.load(os.path.join(here, "ndt_oracle_kat.npz"))
+    got = K.run()
+    assert want["accepted"].sum() >= 3
+    for k in ("valid", "evals", "accepted", "best"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["score"], want["score"])
