@@ -258,6 +258,7 @@ def run_b200(args):
     ps.synchronize()
     # ---- timed region: device-resident inputs apart from the 360-double sweep ----
     ps.timing_enable(args.steps)
+    ph0 = ps.match_phase_clocks() if hasattr(ps, "match_phase_clocks") else None
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -272,6 +273,7 @@ def run_b200(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     stage_ms, nst = ps.timing_read()
+    ph1 = ps.match_phase_clocks() if ph0 is not None else None
     ps.timing_enable(0)
     ps.synchronize()
     # ---- end-to-end through the public API with host buffers ----
@@ -343,6 +345,14 @@ def run_b200(args):
                      "note": "the correlative search is shared-memory-lookup bound, not HBM bound; see DESIGN.md"},
         "stage_ms_per_step": {k: v / max(nst, 1) for k, v in stage_ms.items()},
     }
+    if ph1 is not None:
+        d = {k: ph1[k] - ph0[k] for k in ph1}
+        cta = sum(v for k, v in d.items() if k.startswith("cta_")) or 1
+        line["match_phase_share"] = {k[4:]: round(v / cta, 4) for k, v in d.items() if k.startswith("cta_")}
+        line["match_warp_busy_share"] = {k[5:]: round(d[k] / (12.0 * d["cta_" + c] or 1), 4) for k, c in (
+            ("warp_seeds", "seeds_bounds"), ("warp_bounds", "seeds_bounds"), ("warp_members", "members"))}
+        line["match_visits_share"] = {k[7:]: round(d[k] / (sum(d[q] for q in d if q.startswith("visits_")) or 1), 4)
+                                      for k in d if k.startswith("visits_")}
     if world == 1 and not args.no_cpu_baseline:
         val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams, args.refine)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}

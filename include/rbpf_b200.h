@@ -172,7 +172,8 @@ int rbpf_get_resample_cumsum(rbpf_handle h, double *out_n_global);
  * (hybridmap.py:244-256); lets the weighting stage be checked against the
  * reference with a canned matcher answer. */
 int rbpf_set_match(rbpf_handle h, const double *pose_n3, const double *cov_n9, const int32_t *valid_n);
-/* Score slice (29x29 int32, row j, column i) at the best rotation of one particle. */
+/* Score slice (29x29 int32, row j, column i) at the best rotation of one particle: re-runs the
+ * last match (scan-to-map or scan-to-previous-scan) for that particle. */
 int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *out_29x29);
 
 /* One 40 m reference tile of one particle as the reference stores it: 800x800
@@ -192,7 +193,20 @@ int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out_xy, int64_
 int rbpf_checkpoint_write(rbpf_handle h, const char *path);
 int rbpf_checkpoint_read(rbpf_handle h, const char *path);
 
+/* Device-side errors are sticky and deferred: the kernels set a flag (pool exhausted -> RBPF_ERR_POOL, the
+ * reference's resample assertion main.py:66-67 -> RBPF_ERR_RESAMPLE, internal bound -> RBPF_ERR_WORLD) and go
+ * on without corrupting state -- after pool exhaustion scans are no longer integrated and resampling is
+ * frozen.  The status is returned by the next synchronising call (rbpf_synchronize, getters, rbpf_resample with
+ * outputs) and by rbpf_step at most two steps later, and keeps being returned until rbpf_clear_errors. */
+int rbpf_clear_errors(rbpf_handle h);
 int rbpf_stats(rbpf_handle h, rbpf_stats_t *out);
+/* Where the matcher kernel (the MATLAB matchScanCustom call of hybridmap.py:244-251) spends its time:
+ * SM clocks since creation, out[16].  Slots 0-8 are summed over CTAs (one search each, thread 0 between
+ * barriers): 0 frame + curr points, 1 map gather + threshold, 2 3x3 dilation, 3 group-bound dilation,
+ * 4 seed rotations + group bounds, 5 group ranking, 6 member rotations, 7 covariance, 8 NDT stage.
+ * Slots 10-12 are summed over warps (busy time, without barrier waits): seeds, group bounds, member
+ * rotations; 13-15 are the points those three phases visited. */
+int rbpf_match_phase_clocks(rbpf_handle h, uint64_t *out16);
 int rbpf_synchronize(rbpf_handle h);
 
 /* Constants of the restated matcher, for callers that need the lattice. */

@@ -40,6 +40,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* sin / cos / exp in plain IEEE operations, shared with the CUDA kernels so that weights (and with
+ * them the resampled ancestors) agree bit for bit; within 1 ulp of libm, equal to it for > 99.8 % of
+ * arguments (tests/test_rb_math.py). */
+#include "../thesis_b200/csrc/rb_math.h"
+
 #define CS 0.05            /* hybridmap.py:67  cell size, metres */
 #define TILE_LEN 40        /* hybridmap.py:68  tile side, metres (an int in the reference) */
 #define DIM 800            /* gridmap.py:31    round(40/0.05) */
@@ -236,7 +241,8 @@ static inline void xform(double c, double s, double x, double y, double px, doub
 void orc_transform(const double *pose, const double *px, const double *py, int B,
                    double *gx, double *gy)
 {
-    double c = cos(pose[2]), s = sin(pose[2]);
+    double c, s;
+    rb_sincos(pose[2], &s, &c);
     for (int j = 0; j < B; j++) xform(c, s, pose[0], pose[1], px[j], py[j], &gx[j], &gy[j]);
 }
 
@@ -278,7 +284,8 @@ void orc_map_update(orc_map *m, const double *pose, const double *px, const doub
 {
     if (!map_with_pos(m, pose[0], pose[1])) return;               /* :98-100 */
     int sx = (int)(pose[0] / CS), sy = (int)(pose[1] / CS);      /* :102 */
-    double c = cos(pose[2]), s = sin(pose[2]);
+    double c, s;
+    rb_sincos(pose[2], &s, &c);
     int cap = 4096, *pts = (int *)malloc(sizeof(int) * 2 * (size_t)cap);
     for (int j = 0; j < B; j++) {
         double gx, gy;
@@ -352,15 +359,21 @@ void orc_sample_weight(const orc_map *m, const double *guesses, int K, const dou
 {
     for (int k = 0; k < K; k++) {
         const double *g = guesses + 3 * k;
-        double c = cos(g[2]), s = sin(g[2]), obs = 1.0;
+        double c, s;
+        long tenths = 10;                                                   /* the 1 + ... of robot.py:135 */
+        rb_sincos(g[2], &s, &c);
         for (int j = 0; j < B; j++) {
             if (dist[j] < W_MAX_R && dist[j] > W_MIN_R) {
                 double gx, gy, L;
                 xform(c, s, g[0], g[1], px[j], py[j], &gx, &gy);
-                if (orc_get_odds_at(m, gx, gy, &L)) obs += L;
+                /* Declared deviation: the log-odds are summed exactly, in tenths (a cell is a multiple of
+                 * 0.1 to within 1.1e-14), where the reference adds the float64 cells; the
+                 * two sums differ by < B * 1.1e-14.  The CUDA path holds int8 tenths and forms the same
+                 * integer, which makes the weights -- and the resampled ancestors -- agree bit for bit. */
+                if (orc_get_odds_at(m, gx, gy, &L)) tenths += lrint(L * 10.0);
             }
         }
-        w[k] = obs * prs[k];
+        w[k] = ((double)tenths / 10.0) * prs[k];
     }
 }
 
@@ -394,7 +407,7 @@ void orc_propose(const double *mean, const double *cov, const double *z, int K,
         double y1 = (d1 - l[1] * y0) / l[3];
         double y2 = ((d2 - l[2] * y0) - l[4] * y1) / l[5];
         double maha = (y0 * y0 + y1 * y1) + y2 * y2;
-        prs[k] = exp(-0.5 * maha) / nrm * 10.0;
+        prs[k] = rb_exp(-0.5 * maha) / nrm * 10.0;
     }
 }
 
@@ -500,7 +513,8 @@ static int match_curr(const orc_map *m, const double *guess, const double *px, c
                       const double *dist, int B, double *cx, double *cy, int *cj)
 {
     int M = 0;
-    double c0 = cos(guess[2]), s0 = sin(guess[2]);
+    double c0, s0;
+    rb_sincos(guess[2], &s0, &c0);
     for (int j = 0; j < B; j++) {
         if (!(dist[j] < MATCH_MAX_R && dist[j] > MATCH_MIN_R)) continue;      /* :217-218 */
         double gx, gy;
@@ -954,7 +968,8 @@ int orc_match_adj(const double *guess, const double *px, const double *py, int B
 {
     double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
     int *cj = (int *)malloc(sizeof(int) * (size_t)B);
-    double c0 = cos(guess[2]), s0 = sin(guess[2]);
+    double c0, s0;
+    rb_sincos(guess[2], &s0, &c0);
     int M = 0;
     for (int j = 0; j < B; j++) {
         double gx, gy;
@@ -999,10 +1014,12 @@ void orc_motion(int family, const double *u, double dt, const double *par, doubl
         Q[0] = fabs(q0 * q0); Q[4] = fabs(q1 * q1); Q[8] = fabs(q2 * q2);
     } else {
         double th = pose[2] + dt * u[1];
-        np_[0] = pose[0] + dt * u[0] * cos(th);
-        np_[1] = pose[1] + dt * u[0] * sin(th);
+        double ct, st, cp, sp;
+        rb_sincos(th, &st, &ct);
+        rb_sincos(pose[2], &sp, &cp);
+        np_[0] = pose[0] + dt * u[0] * ct;
+        np_[1] = pose[1] + dt * u[0] * st;
         np_[2] = th;
-        double cp = cos(pose[2]), sp = sin(pose[2]);
         F[2] = dt * u[0] * cp;
         F[5] = dt * u[0] * sp;
         double g0 = dt * cp, g1 = dt * sp, g2 = dt, m0 = 0.05 * 0.05, m1 = (M_PI / 180 / 2) * (M_PI / 180 / 2);

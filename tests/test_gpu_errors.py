@@ -101,3 +101,78 @@ def test_peer_mapping_errors(P):
     b._ck(b._lib.rbpf_resample_commit(b._h))
     with pytest.raises(P.RbpfError, match="differs"):
         c.attach_peer(1, b.peer_view())
+
+
+def test_pool_exhaustion_inside_step_keeps_the_pool_consistent(P, golden):
+    """rbpf_step never synchronises: when the pool runs out inside a step the ray-cast is skipped,
+    resampling is frozen, the free-list counter stays inside [0, pool] (resample_refs pushes with it)
+    and the status surfaces from rbpf_step two steps later, sticky until rbpf_clear_errors."""
+    N = 64
+    ps = P.ParticleSet(N, 180, pool_subtiles=1200, seed=3)
+    r, a = golden["intel_ranges"], golden["intel_angles"]
+    ps.set_scan(r[0], a)
+    ps.integrate()
+    ps.integrate()
+    ps.synchronize()
+    rng = np.random.default_rng(1)
+    seen = None
+    for s in range(1, 16):
+        # teleport inside the existing tile: every scan needs fresh private sub-tiles, and weights that resample
+        ps.poses = np.column_stack([rng.uniform(-18, 18, N), rng.uniform(-18, 18, N), rng.uniform(-3, 3, N)])   # inside tile (0, 0)
+        ps.weights = np.linspace(0.0, 1000.0, N)
+        try:
+            ps.step(r[s], a)
+        except P.RbpfError as e:
+            seen = (s, str(e))
+            break
+    assert seen is not None and "pool" in seen[1], "pool exhaustion must surface from rbpf_step itself"
+    with pytest.raises(P.RbpfError, match="pool"):
+        ps.synchronize()                                                  # sticky
+    st = ps.stats()
+    assert st["pool_in_use"] <= st["pool_subtiles"]
+    assert st["refcount_sum"] == st["total_refs"]
+    ps.clear_errors()
+    ps.synchronize()                                                      # clean again
+    did, anc = ps.resample(0.25)                                          # pushes freed sub-tiles through the counter
+    st = ps.stats()
+    assert st["refcount_sum"] == st["total_refs"]
+    assert st["pool_in_use"] <= st["pool_subtiles"]
+
+
+def test_resample_assertion_is_sticky_without_outputs(P):
+    """rbpf_resample(h, u, NULL, NULL) cannot report: the assertion (main.py:66-67) is kept and
+    returned by the next synchronising call."""
+    import ctypes as C
+
+    ps = P.ParticleSet(16, 180, world_tiles=(1, 1), pool_subtiles=64)
+    w = np.linspace(0.0, 1000.0, 16)
+    w[5] = np.inf                                                         # sum = inf: floor((c - u)/slice) is NaN
+    ps.weights = w
+    u = C.c_double(0.5)
+    rc = ps._lib.rbpf_resample(ps._h, C.byref(u), None, None)
+    assert rc == 0
+    with pytest.raises(AssertionError, match="Incorrect number of resampled weights"):
+        ps.synchronize()
+    ps.clear_errors()
+    ps.synchronize()
+
+
+def test_checkpoint_read_validates(P, golden, tmp_path):
+    ps = P.ParticleSet(8, 180, pool_subtiles=400)
+    ps.set_scan(golden["intel_ranges"][0], golden["intel_angles"])
+    ps.integrate()
+    path = str(tmp_path / "ck.bin")
+    ps.save(path)
+    poses = ps.poses.copy()
+    data = open(path, "rb").read()
+    open(path, "wb").write(data[: len(data) // 2])                        # truncated
+    ps.poses = poses + 1.0
+    with pytest.raises(P.RbpfError, match="size"):
+        ps.load(path)
+    assert np.array_equal(ps.poses, poses + 1.0)                          # nothing was touched
+    other = P.ParticleSet(8, 180, pool_subtiles=400, rank=1, world=2)
+    open(path, "wb").write(data)
+    with pytest.raises(P.RbpfError, match="rank"):
+        other.load(path)
+    ps.load(path)
+    assert np.array_equal(ps.poses, poses)

@@ -78,7 +78,9 @@ SIGNATURES = {
     "rbpf_occupied_points": (C.c_int, [_H, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_int64)]),
     "rbpf_checkpoint_write": (C.c_int, [_H, C.c_char_p]),
     "rbpf_checkpoint_read": (C.c_int, [_H, C.c_char_p]),
+    "rbpf_clear_errors": (C.c_int, [_H]),
     "rbpf_stats": (C.c_int, [_H, C.POINTER(RbpfStats)]),
+    "rbpf_match_phase_clocks": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "rbpf_synchronize": (C.c_int, [_H]),
     "rbpf_rot_step": (C.c_double, []),
     "rbpf_rot_count": (C.c_int32, []),

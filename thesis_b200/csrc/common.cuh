@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "rb_math.h"                       // sin / cos / exp shared bit for bit with the CPU oracle
+
 // ---- constants of the reference (file:line into the reference checkout) ----
 #define RB_CS 0.05              // hybridmap.py:67  cell size [m]
 #define RB_TILE_LEN 40.0        // hybridmap.py:68  reference tile side [m]
@@ -58,6 +60,8 @@
 struct RbStats {                            // device-side counters
     unsigned long long cow_copies, fresh_allocs, cells_dropped, resamples, match_failed, match_evals, match_visits, match_points, match_runs,
         ndt_evals, ndt_accepted;
+    // match_kernel phase split (SM clocks summed over CTAs resp. warps, see rbpf_match_phase_clocks)
+    unsigned long long match_clk[16];
 };
 
 struct RbFlags {                            // device-side status words
@@ -66,7 +70,8 @@ struct RbFlags {                            // device-side status words
     int did_resample;                       // last resample triggered
     int world_overflow;                     // matcher window left the world / internal bound hit
     int remote_needed;                      // multi-GPU: local slots whose ancestor is remote
-    int pad[3];
+    int resample_error_sticky;              // resample_error of any plan since the last rbpf_clear_errors
+    int pad[2];
 };
 
 struct RbPeer {                             // another rank's current particle state, mapped into this process
@@ -243,7 +248,7 @@ __device__ __forceinline__ double rb_u01(uint32_t hi, uint32_t lo)   // (0,1), 5
 // ---- launchers (one per kernel file) ----
 void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, const double *par, cudaStream_t s);
 void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s);
-void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s);
+void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, int adj, cudaStream_t s);
 void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s);
 void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);
 void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s);

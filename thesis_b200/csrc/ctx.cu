@@ -46,6 +46,13 @@ struct rbpf_ctx {
     std::vector<PeerMap> peers;    // by rank
     std::vector<cudaEvent_t> tev;  // (RB_NSTAGES + 1) events per recorded step
     int t_max_steps, t_steps;
+    // deferred error reporting of rbpf_step: the flags are copied to pinned memory after every step
+    // and looked at two steps later (the host stays one step ahead of the device)
+    RbFlags *h_flags = nullptr;    // 2 pinned slots
+    cudaEvent_t flag_ev[2] = {nullptr, nullptr};
+    int flag_pending[2] = {0, 0};
+    int last_adj = 0;              // mode of the last match (rbpf_get_match_slice re-runs it)
+    void *ckpt_host = nullptr;     // pinned bounce buffer of the checkpoint calls, allocated on first use
 };
 
 #define RB_NSTAGES 8               // set_scan, match, weight, raycast_prepare, raycast_cast, weight_fallback, resample_plan, resample_apply
@@ -128,6 +135,9 @@ extern "C" int rbpf_destroy(rbpf_handle h)
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) cudaEventDestroy(h->stage_ev[i]);
     if (h->h_scan) cudaFreeHost(h->h_scan);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->ckpt_host) cudaFreeHost(h->ckpt_host);
+    for (int i = 0; i < 2; i++) if (h->flag_ev[i]) cudaEventDestroy(h->flag_ev[i]);
     delete h;
     return RBPF_OK;
 }
@@ -148,6 +158,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         fprintf(stderr, "rbpf_create: %s\n", msg.c_str());
         for (void *p : h->allocs) cudaFree(p);
         if (h->h_scan) cudaFreeHost(h->h_scan);
+        if (h->h_flags) cudaFreeHost(h->h_flags);
+        for (int i = 0; i < 2; i++) if (h->flag_ev[i]) cudaEventDestroy(h->flag_ev[i]);
         delete h;
         return code;
     };
@@ -217,6 +229,12 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     }
     if (cudaMallocHost((void **)&h->h_scan, 2 * 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
+    if (cudaMallocHost((void **)&h->h_flags, 2 * sizeof(RbFlags)) != cudaSuccess)
+        return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
+    memset(h->h_flags, 0, 2 * sizeof(RbFlags));
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&h->flag_ev[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(RBPF_ERR_CUDA, "cudaEventCreate failed");
     h->h_prev = nullptr;
     h->stage_slot = 0;
     for (int i = 0; i < 2; i++)
@@ -250,13 +268,37 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     return RBPF_OK;
 }
 
+// Sticky device-side errors -> status.  They stay set until rbpf_clear_errors.
+static int flags_status(rbpf_ctx *h, const RbFlags &f)
+{
+    if (f.pool_exhausted) {
+        h->err = "tile pool exhausted (raise pool_subtiles): scans since then were not integrated and resampling is frozen";
+        return RBPF_ERR_POOL;
+    }
+    if (f.resample_error_sticky) { h->err = "Incorrect number of resampled weights."; return RBPF_ERR_RESAMPLE; }   // main.py:67
+    if (f.world_overflow) { h->err = "matcher window / ray-cast internal bound hit"; return RBPF_ERR_WORLD; }
+    return RBPF_OK;
+}
+
 static int check_flags(rbpf_ctx *h)
 {
     RbFlags f;
     CK(cudaMemcpyAsync(&f, h->d.flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (f.pool_exhausted) { h->err = "tile pool exhausted (raise pool_subtiles)"; return RBPF_ERR_POOL; }
-    if (f.world_overflow) { h->err = "matcher window / ray-cast internal bound hit"; return RBPF_ERR_WORLD; }
+    return flags_status(h, f);
+}
+
+extern "C" int rbpf_clear_errors(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    RbFlags f;
+    CK(cudaMemcpy(&f, h->d.flags, sizeof(f), cudaMemcpyDeviceToHost));
+    f.pool_exhausted = f.world_overflow = f.resample_error = f.resample_error_sticky = 0;
+    CK(cudaMemcpy(h->d.flags, &f, sizeof(f), cudaMemcpyHostToDevice));
+    h->flag_pending[0] = h->flag_pending[1] = 0;
+    h->err.clear();
     return RBPF_OK;
 }
 
@@ -305,6 +347,7 @@ extern "C" int rbpf_scan_match(rbpf_handle h)
     if (!h || !h->have_scan) { if (h) h->err = "scan_match: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
     rb_launch_match(h->d, 0, h->stream);
+    h->last_adj = 0;
     CK(cudaGetLastError());
     return RBPF_OK;
 }
@@ -324,6 +367,7 @@ extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, in
     CK(cudaEventRecord(h->stage_ev[h->stage_slot], h->stream));
     h->d.n_prev = n_points;
     rb_launch_match(h->d, 1, h->stream);
+    h->last_adj = 1;
     CK(cudaGetLastError());
     return RBPF_OK;
 }
@@ -409,6 +453,17 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
 {
     if (!h) return RBPF_ERR_ARG;
     if (h->d.world != 1) { h->err = "step: sharded handle, drive the stages from thesis_b200.dist"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    // errors of the step before the previous one (pool exhausted, world overflow, resample assertion):
+    // their flags were copied to pinned memory behind that step; waiting for them keeps the host at
+    // most two steps ahead of the device
+    const int fs = (int)(h->d.step_no & 1ull);
+    if (h->flag_pending[fs]) {
+        CK(cudaEventSynchronize(h->flag_ev[fs]));
+        h->flag_pending[fs] = 0;
+        const int frc = flags_status(h, h->h_flags[fs]);
+        if (frc) return frc;
+    }
     const bool timed = h->t_max_steps > 0 && h->t_steps < h->t_max_steps;
     cudaEvent_t *ev = timed ? &h->tev[(size_t)h->t_steps * (RB_NSTAGES + 1)] : nullptr;
 #define MARK(i) if (timed) cudaEventRecord(ev[i], h->stream)
@@ -417,6 +472,7 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     if (rc) return rc;
     MARK(1);
     rb_launch_match(h->d, 0, h->stream);
+    h->last_adj = 0;
     MARK(2);
     h->d.use_dup = 0;
     rb_launch_weight(h->d, nullptr, 0, h->stream);
@@ -433,6 +489,9 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     MARK(8);
 #undef MARK
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h->h_flags[fs], h->d.flags, sizeof(RbFlags), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->flag_ev[fs], h->stream));
+    h->flag_pending[fs] = 1;
     if (timed) h->t_steps++;
     swap_buffers(h);
     h->d.step_no++;
@@ -541,7 +600,7 @@ extern "C" int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *ou
     if (!h || !out || particle < 0 || particle >= h->d.N || !h->have_scan) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemsetAsync(h->d_slice, 0, sizeof(int) * RB_SLICE_W * RB_SLICE_W, h->stream));
-    rb_launch_match_slice(h->d, particle, h->d_slice, h->stream);
+    rb_launch_match_slice(h->d, particle, h->d_slice, h->last_adj, h->stream);
     CK(cudaGetLastError());
     return copy_out(h, out, h->d_slice, sizeof(int) * RB_SLICE_W * RB_SLICE_W);
 }
@@ -608,6 +667,16 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_runs = s.match_runs;
     out->ndt_evals = s.ndt_evals;
     out->ndt_accepted = s.ndt_accepted;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_match_phase_clocks(rbpf_handle h, uint64_t *out16)
+{
+    if (!h || !out16) return RBPF_ERR_ARG;
+    RbStats s;
+    int rc = copy_out(h, &s, h->d.stats, sizeof(s));
+    if (rc) return rc;
+    for (int i = 0; i < 16; i++) out16[i] = s.match_clk[i];
     return RBPF_OK;
 }
 
@@ -844,13 +913,12 @@ struct CkptHeader {
 };
 
 static const size_t CKPT_CH = 32u << 20;
-static void *g_ckpt_host = nullptr;             // pinned bounce buffer, allocated on first use
 
 static int ckpt_io(rbpf_ctx *h, FILE *f, void *dev, size_t bytes, bool write)
 {
     const size_t CH = CKPT_CH;
-    if (!g_ckpt_host) CK(cudaMallocHost(&g_ckpt_host, CH));
-    void *host = g_ckpt_host;
+    if (!h->ckpt_host) CK(cudaMallocHost(&h->ckpt_host, CH));
+    void *host = h->ckpt_host;
     int rc = RBPF_OK;
     for (size_t off = 0; off < bytes && rc == RBPF_OK; off += CH) {
         const size_t n = bytes - off < CH ? bytes - off : CH;
@@ -904,12 +972,23 @@ extern "C" int rbpf_checkpoint_read(rbpf_handle h, const char *path)
     if (!f) { h->err = std::string("checkpoint: cannot open ") + path; return RBPF_ERR_ARG; }
     CkptHeader hd;
     if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "RBPFCK01", 8) != 0 || hd.N != d.N || hd.nsub != d.nsub ||
-        hd.tiles_x != d.tiles_x || hd.tiles_y != d.tiles_y || hd.pool_tiles != d.pool_tiles) {
+        hd.tiles_x != d.tiles_x || hd.tiles_y != d.tiles_y || hd.pool_tiles != d.pool_tiles || hd.rank != d.rank ||
+        hd.world != d.world) {
         fclose(f);
-        h->err = "checkpoint: header does not match this handle's configuration";
+        h->err = "checkpoint: header does not match this handle's configuration (particles, world extent, pool, rank / world)";
         return RBPF_ERR_ARG;
     }
     const size_t N = d.N;
+    {   // nothing of the handle is touched unless the file holds everything the header promises
+        const size_t want = sizeof(hd) + sizeof(double) * 13 * N + sizeof(unsigned long long) * N + sizeof(uint32_t) * N * d.nsub +
+                            sizeof(uint32_t) * d.pool_tiles + (size_t)hd.in_use * RB_SUB_BYTES;
+        if (hd.in_use > d.pool_tiles || fseek(f, 0, SEEK_END) != 0 || (size_t)ftell(f) != want ||
+            fseek(f, (long)sizeof(hd), SEEK_SET) != 0) {
+            fclose(f);
+            h->err = "checkpoint: file size does not match its header (truncated?)";
+            return RBPF_ERR_ARG;
+        }
+    }
     std::vector<uint32_t> rc(d.pool_tiles);
     int r = ckpt_io(h, f, d.pose, sizeof(double) * 3 * N, false);
     if (!r) r = ckpt_io(h, f, d.cov, sizeof(double) * 9 * N, false);
@@ -933,5 +1012,6 @@ extern "C" int rbpf_checkpoint_read(rbpf_handle h, const char *path)
     CK(cudaMemcpy(d.free_count, &fc, sizeof(int), cudaMemcpyHostToDevice));
     d.step_no = hd.step_no;
     d.use_dup = 0;
+    h->flag_pending[0] = h->flag_pending[1] = 0;
     return RBPF_OK;
 }

@@ -50,17 +50,50 @@
 #define MT_WARPS 12
 #endif
 #ifndef MT_SEEDS
-#define MT_SEEDS 8                      // rotations around the guess scored first (by as many warps)
+#define MT_SEEDS 12                     // rotations around the guess scored first (by as many warps)
 #endif
 #ifndef MT_ABORT_EVERY
 #define MT_ABORT_EVERY 64              // points between two abort checks of a scoring pass (power of two, multiple of 8)
 #endif
 #define MT_THREADS (MT_WARPS * 32)
 #define MT_PLANES 9                     // bit-sliced counters up to 511 >= RB_MAXB
+// staging buffer: the 477 map rows the 3x3 dilation reads, starting on a multiple of 4 in
+// storage coordinates (a 32-byte sector of the pool holds 8 x 4 cells) -> up to 3 rows more
+#define MT_RAW_ROWS 484
+#define MT_NRB ((MT_RAW_ROWS + 31) / 32) // 16 bands of 32 rows
+#define MT_NBLK (MT_NRB * RB_RAW_STRIDE) // 288 blocks of 32 rows x 32 cells
+#define MT_NBINS 64                     // polar bins of the curr points (which blocks can a lookup reach?)
+#define MT_REACH 60.0f                  // cells: half diagonal of a block (22.7) + lookup reach around a rotated point
+                                        // (14 translation + 5 group dilation + 1 proximity + rounding, as a Euclidean
+                                        // distance: 29.7) + the guess inside its cell (1.4) + slack
+#ifndef MT_GATHER_U
+#define MT_GATHER_U 4                   // blocks (= 32-byte sectors per lane) in flight per warp and round of the gather
+#endif
+#define MT_SEG_ROWS 20                  // rows per thread of the fused dilation pass (24 segments x 16 words)
+
+// Phase clocks (include/rbpf_b200.h rbpf_match_phase_clocks): thread 0 of a CTA adds the SM
+// clocks between two barriers to slot i; MT_WCLK adds a warp's own busy time.
+#define MT_CLK(i)                                                                         \
+    if (tid == 0 && !slice_out) {                                                         \
+        const long long t_ = clock64();                                                   \
+        atomicAdd(&c.stats->match_clk[i], (unsigned long long)(t_ - clk_prev));           \
+        clk_prev = t_;                                                                    \
+    }
+#define MT_WCLK(i, t0)                                                                    \
+    if (lane == 0 && !slice_out) atomicAdd(&c.stats->match_clk[i], (unsigned long long)(clock64() - (t0)));
 
 struct MatchShared {
     double gx, gy, gth, cs0, sn0, fx, fy, rx, ry;
     int M, nx, ny, g0xu, g0yu, x0, y0, t0x, t0y, ok, overflow;
+    int slot_warp;                      // warp whose slot holds the counters of the best rotation
+    int a0, dy0;                        // first staged row (storage coordinates, multiple of 4); y0 - 1 - a0
+    int nblk;                           // blocks to gather
+    int rbin[MT_NBINS], rdil[MT_NBINS]; // farthest curr point per polar bin [cells]; the same over +-30 degrees of rotation
+    uint32_t need[MT_NRB];              // per band: which 32-cell words a lookup can reach
+    unsigned short blist[MT_NBLK];      // compacted list of those blocks
+    int ord_cnt[4 * MT_WARPS];          // far-first ordering of the points: per range class and warp
+    uint32_t ptw[25];                   // page-table entries of the <= 5 x 5 sub-tiles under the staging window
+    int sxb0, syb0;                     // sub-tile coordinates of ptw[0] (may be negative at the world border)
     unsigned long long best_key;
     long long mom[9];                   // W0 Wx Wy Wxx Wyy Wxy T0 T1 T2
     int group_ub[MT_MAXGROUPS];         // phase A: upper bound of every rotation group
@@ -72,13 +105,13 @@ struct MatchShared {
 };
 
 __host__ __device__ inline size_t mt_bm_words() { return ((size_t)RB_BM_ROWS * RB_BM_STRIDE + 3) & ~(size_t)3; }  // keeps raw/pts 16-B aligned
-__host__ __device__ inline size_t mt_raw_words() { return (size_t)RB_RAW_ROWS * RB_RAW_STRIDE; }
+__host__ __device__ inline size_t mt_raw_words() { return (size_t)MT_RAW_ROWS * RB_RAW_STRIDE; }
 
 size_t rb_match_smem_bytes()
 {
     size_t words = 2 * mt_bm_words() + mt_raw_words();
     words = (words + 1) & ~(size_t)1;
-    return words * 4 + 2 * RB_MAXB * sizeof(double) + sizeof(MatchShared);
+    return words * 4 + 2 * RB_MAXB * sizeof(double) + RB_MAXB * sizeof(float2) + sizeof(MatchShared);
 }
 
 __device__ __forceinline__ unsigned long long mt_key(int score, int i, int j, int k)
@@ -118,71 +151,27 @@ __device__ __forceinline__ uint32_t mt_pack4(uint32_t bytes)
     return (m * 0x00204081u) >> 28;
 }
 
-// Accumulate the hit masks of all points of one rotation into bit-sliced
-// counters.  pts[q] = (word address << 5) | bit shift for row shift 0.
-//
-// ABORT: every 64 points the best partial count of the warp is compared with
-// the best complete score found so far (best_key, shared): when even hitting all
-// remaining points cannot reach it, the pass is abandoned (returns false).  The
-// bound is admissible, so the search result is unchanged.
-template <bool ABORT>
-__device__ __forceinline__ bool mt_accumulate(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pts, int M,
-                                              int lane_off, uint32_t pl[MT_PLANES], uint32_t rowmask = 0u,
-                                              const volatile unsigned long long *best_key = nullptr,
-                                              int *visited = nullptr)
+// Packed point: (byte offset of the bitmap word << 5) | bit shift, for row shift 0.  The
+// scoring loop turns it into a shared-memory address with one multiply-add-high on the
+// FMA pipe (the ALU pipe is the busy one: LOP3 carry-save adders and funnel shifts).
+#define MT_PT_WORD_SHIFT 7
+__device__ __forceinline__ uint32_t mt_lds(uint32_t addr)
 {
-    uint32_t ones = 0, twos = 0, fours = 0;
-#pragma unroll
-    for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
-    int q = 0;
-    for (; q + 8 <= M; q += 8) {
-        if (ABORT && q && (q & (MT_ABORT_EVERY - 1)) == 0) {
-            // bit-sliced max of the partial counts of this lane's row
-            uint32_t cand = rowmask;
-            int sc = 0;
-#pragma unroll
-            for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
-                const uint32_t plane = pbit >= 3 ? pl[pbit] : (pbit == 2 ? fours : (pbit == 1 ? twos : ones));
-                const uint32_t t = cand & plane;
-                if (t) { cand = t; sc |= 1 << pbit; }
-            }
-            const int wmax = __reduce_max_sync(0xffffffffu, rowmask ? sc : 0);
-            if (wmax + (M - q) < (int)(*best_key >> 32)) {
-                if (visited) *visited += q;
-                return false;
-            }
-        }
-        uint32_t h[8];
-        const uint4 pa = *reinterpret_cast<const uint4 *>(pts + q);
-        const uint4 pb = *reinterpret_cast<const uint4 *>(pts + q + 4);
-        const uint32_t pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const uint32_t a = (pk[e] >> 5) + lane_off;
-            h[e] = __funnelshift_r(bm[a], bm[a + 1], pk[e]);
-        }
-        uint32_t t0, t1, f0, f1, e8;
-        CSA(t0, ones, ones, h[0], h[1]);
-        CSA(t1, ones, ones, h[2], h[3]);
-        CSA(f0, twos, twos, t0, t1);
-        CSA(t0, ones, ones, h[4], h[5]);
-        CSA(t1, ones, ones, h[6], h[7]);
-        CSA(f1, twos, twos, t0, t1);
-        CSA(e8, fours, fours, f0, f1);
-        // ripple the eights into planes 3..8
-#pragma unroll
-        for (int p = 3; p < MT_PLANES; p++) { uint32_t t = pl[p] & e8; pl[p] ^= e8; e8 = t; }
-    }
-    pl[0] = ones; pl[1] = twos; pl[2] = fours;
-    for (; q < M; q++) {                                                   // tail: plain ripple add
-        const uint32_t pk = pts[q];
-        const uint32_t a = (pk >> 5) + lane_off;
-        uint32_t carry = __funnelshift_r(bm[a], bm[a + 1], pk);
-#pragma unroll
-        for (int p = 0; p < MT_PLANES; p++) { uint32_t t = pl[p] & carry; pl[p] ^= carry; carry = t; }
-    }
-    if (visited) *visited += M;
-    return true;
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t mt_lds4(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t mt_pt_addr(uint32_t pk, uint32_t lane_base)
+{
+    uint32_t a;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(pk), "r"(1u << 27), "r"(lane_base));   // (pk >> 5) + lane_base
+    return a;
 }
 
 __device__ __forceinline__ int mt_decode(const uint32_t pl[MT_PLANES], int bit)
@@ -213,32 +202,175 @@ __device__ __forceinline__ unsigned long long mt_lane_key(const uint32_t pl[MT_P
 }
 
 // Rasterise the curr points for rotation k into packed bitmap addresses.
-__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy, int k,
-                                             uint32_t *pts, int lane, int shift_i, int shift_j, int span_i, int span_j)
+//
+// The lattice point is floor(v) of a float64 expression (same operations as the oracle).  A
+// float32 evaluation of v (points pre-scaled to cells, fused multiply-adds) is within 1e-4
+// of it (|v| < 256: conversions 2 x 1.3e-5, two roundings 1.4e-5 each, per term), so its floor
+// is the same unless v32 lies within MT_RAS_EPS of an integer -- only those points (0.4 %)
+// take the float64 expression.
+#define MT_RAS_EPS 2e-3f
+struct MtRot {                                                             // one rotation of the search, per lane
+    float ckf, skf, fxf, fyf;
+    int k, xoff, yoff;
+};
+
+__device__ __forceinline__ MtRot mt_rot(const RbCtx &c, const MatchShared *sh, int k, int shift_i, int shift_j)
 {
-    const double ck = c.rot_cs[2 * (k + c.nk)], sk = c.rot_cs[2 * (k + c.nk) + 1];
-    const int M = sh->M;
-    const int xoff = sh->g0xu - sh->x0 + shift_i, yoff = RB_WIN_R + shift_j;
-    for (int q = lane; q < M; q += 32) {
-        double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
-        double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
-        int ox = __double2int_rd(rxq * 20.0 + 0.5), oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
-        int bx = ox + xoff, by = oy + yoff;
-        if (bx < 0 || bx + span_i >= 32 * (RB_BM_STRIDE - 1) || by < 0 || by + span_j >= RB_BM_ROWS) {
-            sh->overflow = 1;                                              // cannot happen for |c| < 11 m
-            bx = 0; by = 0;
-        }
-        pts[q] = ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << 5) | (uint32_t)(bx & 31);
+    MtRot r;
+    r.k = k;
+    r.ckf = (float)c.rot_cs[2 * (k + c.nk)];
+    r.skf = (float)c.rot_cs[2 * (k + c.nk) + 1];
+    r.fxf = (float)(sh->fx * 20.0 + 0.5);
+    r.fyf = (float)(sh->fy * 20.0 + 0.5);
+    r.xoff = sh->g0xu - sh->x0 + shift_i;
+    r.yoff = RB_WIN_R + shift_j;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
+                                                    const float2 *__restrict__ ccf, const MtRot &r, int q, int span_i, int span_j)
+{
+    const float2 cf = ccf[q];
+    const float vx = fmaf(r.ckf, cf.x, fmaf(-r.skf, cf.y, r.fxf)), vy = fmaf(r.skf, cf.x, fmaf(r.ckf, cf.y, r.fyf));
+    const float flx = floorf(vx), fly = floorf(vy);
+    int ox = (int)flx, oy = (int)fly;
+    const float dx = vx - flx, dy = vy - fly;
+    if (!(dx > MT_RAS_EPS && dx < 1.0f - MT_RAS_EPS && dy > MT_RAS_EPS && dy < 1.0f - MT_RAS_EPS)) {
+        const double ck = c.rot_cs[2 * (r.k + c.nk)], sk = c.rot_cs[2 * (r.k + c.nk) + 1];
+        const double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
+        const double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
+        ox = __double2int_rd(rxq * 20.0 + 0.5); oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
     }
+    int bx = ox + r.xoff, by = oy + r.yoff;
+    if (bx < 0 || bx + span_i >= 32 * (RB_BM_STRIDE - 1) || by < 0 || by + span_j >= RB_BM_ROWS) {
+        sh->overflow = 1;                                                  // cannot happen for |c| < 11 m
+        bx = 0; by = 0;
+    }
+    return ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << MT_PT_WORD_SHIFT) | (uint32_t)(bx & 31);
+}
+
+__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
+                                             const float2 *__restrict__ ccf, int k, uint32_t *pts, int lane, int shift_i,
+                                             int shift_j, int span_i, int span_j)
+{
+    const MtRot r = mt_rot(c, sh, k, shift_i, shift_j);
+    const int M = sh->M;
+    for (int q = lane; q < M; q += 32) pts[q] = mt_raster_point(c, sh, ccx, ccy, ccf, r, q, span_i, span_j);
+}
+
+// One scoring pass: the points of rotation k are rasterised MT_CHUNK at a time, just before
+// they are scored, so a pass that is given up has rasterised only what it looked at.  Hit
+// masks go into bit-sliced counters (carry-save adders over 16 points, then a ripple into
+// the upper planes).
+//
+// ABORT: after every chunk the partial counts are compared with the best complete score
+// found so far (best_key, shared): when no translation can reach it even if all remaining
+// points hit, the pass is abandoned (returns false).  The bound is admissible, so the search
+// result is unchanged.
+#ifndef MT_CHUNK
+#define MT_CHUNK 64                     // multiple of 32
+#endif
+template <bool ABORT>
+__device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
+                                        const float2 *__restrict__ ccf, int k, int nx, int ny, uint32_t bm_lane, uint32_t *pts,
+                                        int M, int lane, uint32_t pl[MT_PLANES], uint32_t rowmask = 0u,
+                                        const volatile unsigned long long *best_key = nullptr, int *visited = nullptr)
+{
+    const MtRot r = mt_rot(c, sh, k, -nx, -ny);
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0;
+#pragma unroll
+    for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
+#define MT_LOAD8(Q)                                                                     \
+    uint32_t h[8];                                                                      \
+    {                                                                                   \
+        const uint4 pa = *reinterpret_cast<const uint4 *>(pts + (Q));                   \
+        const uint4 pb = *reinterpret_cast<const uint4 *>(pts + (Q) + 4);               \
+        const uint32_t pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};        \
+        _Pragma("unroll") for (int e = 0; e < 8; e++) {                                 \
+            const uint32_t a = mt_pt_addr(pk[e], bm_lane);                              \
+            h[e] = __funnelshift_r(mt_lds(a), mt_lds4(a), pk[e]);                       \
+        }                                                                               \
+    }
+#define MT_TREE8(E8)                                                                    \
+    {                                                                                   \
+        uint32_t t0, t1, f0, f1;                                                        \
+        CSA(t0, ones, ones, h[0], h[1]);                                                \
+        CSA(t1, ones, ones, h[2], h[3]);                                                \
+        CSA(f0, twos, twos, t0, t1);                                                    \
+        CSA(t0, ones, ones, h[4], h[5]);                                                \
+        CSA(t1, ones, ones, h[6], h[7]);                                                \
+        CSA(f1, twos, twos, t0, t1);                                                    \
+        CSA(E8, fours, fours, f0, f1);                                                  \
+    }
+    for (int q0 = 0; q0 < M; q0 += MT_CHUNK) {
+        if (ABORT && q0) {
+            // hits a translation must have by now to still reach the best complete score
+            const int need = (int)(*best_key >> 32) - (M - q0);
+            if (need > 0) {
+                // bit-sliced "count >= need" over this lane's row, most significant plane first
+                uint32_t gt = 0u, eq = rowmask;
+#pragma unroll
+                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+                    const uint32_t plane = pbit >= 4 ? pl[pbit] : (pbit == 3 ? eights : (pbit == 2 ? fours : (pbit == 1 ? twos : ones)));
+                    const uint32_t tb = (need >> pbit) & 1 ? 0xffffffffu : 0u;
+                    gt |= eq & plane & ~tb;
+                    eq &= ~(plane ^ tb);
+                }
+                if (!__any_sync(0xffffffffu, (gt | eq) != 0u)) {
+                    if (visited) *visited += q0;
+                    return false;
+                }
+            }
+        }
+        const int n = min(MT_CHUNK, M - q0);
+        __syncwarp();                                                       // the previous chunk has been read
+#pragma unroll
+        for (int e = 0; e < MT_CHUNK; e += 32)
+            if (e + lane < n) pts[e + lane] = mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + e + lane, 2 * nx, 2 * ny);
+        __syncwarp();
+        int q = 0;
+        for (; q + 16 <= n; q += 16) {
+            uint32_t ea, eb, s16;
+            { MT_LOAD8(q) MT_TREE8(ea) }
+            { MT_LOAD8(q + 8) MT_TREE8(eb) }
+            CSA(s16, eights, eights, ea, eb);
+            // ripple the sixteens into planes 4..8
+#pragma unroll
+            for (int p = 4; p < MT_PLANES; p++) { uint32_t t = pl[p] & s16; pl[p] ^= s16; s16 = t; }
+        }
+        if (q + 8 <= n) {                                                   // only the last chunk gets here
+            uint32_t e8;
+            { MT_LOAD8(q) MT_TREE8(e8) }
+            uint32_t t = eights & e8; eights ^= e8; e8 = t;
+#pragma unroll
+            for (int p = 4; p < MT_PLANES; p++) { uint32_t t2 = pl[p] & e8; pl[p] ^= e8; e8 = t2; }
+            q += 8;
+        }
+        for (; q < n; q++) {                                                // tail: plain ripple add
+            const uint32_t pk = pts[q];
+            const uint32_t a = mt_pt_addr(pk, bm_lane);
+            uint32_t carry = __funnelshift_r(mt_lds(a), mt_lds4(a), pk), t;
+            t = ones & carry; ones ^= carry; carry = t;
+            t = twos & carry; twos ^= carry; carry = t;
+            t = fours & carry; fours ^= carry; carry = t;
+            t = eights & carry; eights ^= carry; carry = t;
+#pragma unroll
+            for (int p = 4; p < MT_PLANES; p++) { t = pl[p] & carry; pl[p] ^= carry; carry = t; }
+        }
+    }
+#undef MT_LOAD8
+#undef MT_TREE8
+    pl[0] = ones; pl[1] = twos; pl[2] = fours; pl[3] = eights;
+    if (visited) *visited += M;
+    return true;
 }
 
 // curr point of beam j relative to the guess position (hybridmap.py:216-228,236,240; adj: :165-172)
-__device__ __forceinline__ bool mt_curr_point(const RbCtx &c, const MatchShared *sh, unsigned long long exists, int j, int adj,
-                                              double &qx, double &qy)
+__device__ __forceinline__ bool mt_curr_point(const RbCtx &c, const MatchShared *sh, unsigned long long exists, double d, double bpx,
+                                              double bpy, int adj, double &qx, double &qy)
 {
-    const double d = c.dist[j];
     double gx, gy;
-    rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, c.px[j], c.py[j], gx, gy);
+    rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, bpx, bpy, gx, gy);
     if (adj) {                                                             // hybridmap.py:165-172
         qx = gx - sh->gx; qy = gy - sh->gy;
         return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R;
@@ -531,17 +663,25 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     size_t w_end = (2 * mt_bm_words() + mt_raw_words() + 1) & ~(size_t)1;
     double *ccx = reinterpret_cast<double *>(smem + w_end);
     double *ccy = ccx + RB_MAXB;
-    MatchShared *sh = reinterpret_cast<MatchShared *>(ccy + RB_MAXB);
+    float2 *ccf = reinterpret_cast<float2 *>(ccy + RB_MAXB);                // the same points in cells, float32
+    MatchShared *sh = reinterpret_cast<MatchShared *>(ccf + RB_MAXB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x + p_offset;
     if (c.use_dup && !slice_out && c.dup_of[p] != p) return;                // a bit-identical duplicate: result copied afterwards
     const double *pose = c.pose + 3 * (size_t)p, *cov = c.cov + 9 * (size_t)p;
+    long long clk_prev = clock64();
+    if (tid < MT_NBINS) sh->rbin[tid] = 0;
+    if (tid < MT_NRB) sh->need[tid] = 0u;
+    // this thread's beam (one per thread) and the tile mask are on their way while thread 0 sets up the frame
+    const bool has_beam = tid < c.B;
+    const double b_d = has_beam ? c.dist[tid] : 0.0, b_px = has_beam ? c.px[tid] : 0.0, b_py = has_beam ? c.py[tid] : 0.0;
+    const unsigned long long exists = c.exists[p];
 
     // ---- 0. per-particle frame -------------------------------------------
     if (tid == 0) {
         sh->gx = pose[0]; sh->gy = pose[1]; sh->gth = pose[2];
-        sh->cs0 = cos(pose[2]); sh->sn0 = sin(pose[2]);
+        { double sn_, cs_; rb_sincos(pose[2], &sn_, &cs_); sh->cs0 = cs_; sh->sn0 = sn_; }
         // search window, robot.py:62-65
         double p0 = sqrt(cov[0]) * 30.0, p1 = sqrt(cov[4]) * 30.0;
         sh->rx = fmax(fmin(4 * p0, 0.7), 0.1);
@@ -559,6 +699,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         sh->fy = pose[1] - rb_cell_corner(iy, ty);
         sh->x0 = (sh->g0xu - RB_WIN_R) & ~31;
         sh->y0 = sh->g0yu - RB_WIN_R;
+        sh->a0 = (sh->y0 - 1) & ~3;
+        sh->dy0 = sh->y0 - 1 - sh->a0;
+        sh->sxb0 = (sh->x0 - 32 + 160 * 1024) / RB_SUB - 1024;             // floor division, also for negative coordinates
+        sh->syb0 = (sh->a0 + 160 * 1024) / RB_SUB - 1024;
+        sh->nblk = 0;
+        sh->slot_warp = -1;
         sh->M = 0;
         sh->overflow = 0;
         sh->best_key = 0ull;
@@ -572,120 +718,247 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     __syncthreads();
 
     // ---- 1. curr points, hybridmap.py:216-228,236,240 ----------------------
-    const unsigned long long exists = c.exists[p];
-    for (int j = tid; j < c.B; j += MT_THREADS) {
-        double qx, qy;
-        if (!mt_curr_point(c, sh, exists, j, adj, qx, qy)) continue;
-        const int slot = atomicAdd(&sh->M, 1);
-        ccx[slot] = qx;
-        ccy[slot] = qy;
+    const bool gate = !adj && !c.refine;                                    // gather only the blocks a lookup can reach
+    if (tid < 25 && !adj) {                                                 // page-table entries under the window
+        const int sxb = sh->sxb0 + tid % 5, syb = sh->syb0 + tid / 5;
+        sh->ptw[tid] = (sxb >= 0 && sxb < c.subs_x && syb >= 0 && syb < c.subs_y) ? c.pt[(size_t)p * c.nsub + syb * c.subs_x + sxb] : RB_NONE;
     }
+    static_assert(MT_THREADS >= RB_MAXB, "one thread per beam");
+    {
+        double qx = 0.0, qy = 0.0;
+        const bool is_pt = has_beam && mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy);
+        const unsigned bal = __ballot_sync(0xffffffffu, is_pt);
+        int base = 0;
+        if (bal && lane == 0) base = atomicAdd(&sh->M, __popc(bal));        // one slot range per warp
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_pt) {
+            const int slot = base + __popc(bal & ((1u << lane) - 1u));
+            ccx[slot] = qx;
+            ccy[slot] = qy;
+            if (gate) {                                                     // farthest point per polar bin, in cells
+                const float fx_ = (float)qx, fy_ = (float)qy;
+                int bin = (int)((atan2f(fy_, fx_) + 3.14159265f) * (MT_NBINS / 6.28318531f));
+                bin = min(max(bin, 0), MT_NBINS - 1);
+                atomicMax(&sh->rbin[bin], (int)(sqrtf(fx_ * fx_ + fy_ * fy_) * 20.0f) + 2);
+            }
+        }
+    }
+    __syncthreads();
 #ifndef MT_NO_SHUFFLE
     // Spread the points: consecutive list entries are consecutive beams (one wall
     // segment), so the first 64 points of a pass would tell little about the rest.
     // A stride permutation makes every prefix a sample of the whole sweep and the
     // abortable passes give up earlier.  Scores are sums: the order changes nothing.
-    __syncthreads();
     {
         double *tx_ = reinterpret_cast<double *>(bmg), *ty_ = tx_ + RB_MAXB;     // bmg is free until the dilation
         const int Mp = sh->M;
         const int s_ = Mp % 37 ? 37 : (Mp % 41 ? 41 : 43);                      // a prime that does not divide M
         for (int q = tid; q < Mp; q += MT_THREADS) { tx_[q] = ccx[q]; ty_[q] = ccy[q]; }
+        // the rotation search turns every point by up to +-30 degrees (5.33 bins) around the guess
+        if (tid < MT_NBINS) {
+            int m = 0;
+#pragma unroll
+            for (int d = -7; d <= 7; d++) m = max(m, sh->rbin[(tid + d) & (MT_NBINS - 1)]);
+            sh->rdil[tid] = m;
+        }
         __syncthreads();
-        for (int q = tid; q < Mp; q += MT_THREADS) {
-            const int src = (int)(((unsigned)q * (unsigned)s_) % (unsigned)Mp);
-            ccx[q] = tx_[src];
-            ccy[q] = ty_[src];
+        // ... and far points first (stable within four range classes): a wrong rotation moves a
+        // point by range x angle, so the far points are the ones that miss, and the passes that
+        // cannot win are given up after fewer points.
+        double mx_ = 0.0, my_ = 0.0;
+        int key = -1;
+        if (tid < Mp) {
+            const int src = (int)(((unsigned)tid * (unsigned)s_) % (unsigned)Mp);
+            mx_ = tx_[src]; my_ = ty_[src];
+            const double r2 = mx_ * mx_ + my_ * my_;
+            key = r2 >= 64.0 ? 0 : (r2 >= 25.0 ? 1 : (r2 >= 6.25 ? 2 : 3));           // 8 m, 5 m, 2.5 m
+        }
+        int intra = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const unsigned mb = __ballot_sync(0xffffffffu, key == b);
+            if (key == b) intra = __popc(mb & ((1u << lane) - 1u));
+            if (lane == 0) sh->ord_cnt[b * MT_WARPS + warp] = __popc(mb);
+        }
+        __syncthreads();
+        if (tid == 0) {                                                         // exclusive prefix, class-major then warp
+            int run = 0;
+            for (int e = 0; e < 4 * MT_WARPS; e++) { const int n = sh->ord_cnt[e]; sh->ord_cnt[e] = run; run += n; }
+        }
+        __syncthreads();
+        if (key >= 0) {
+            const int slot = sh->ord_cnt[key * MT_WARPS + warp] + intra;
+            ccx[slot] = mx_;
+            ccy[slot] = my_;
+        }
+        __syncthreads();
+    }
+#else
+    if (tid < MT_NBINS) {
+        int m = 0;
+        for (int d = -7; d <= 7; d++) m = max(m, sh->rbin[(tid + d) & (MT_NBINS - 1)]);
+        sh->rdil[tid] = m;
+    }
+    __syncthreads();
+#endif
+    if (tid < sh->M) ccf[tid] = make_float2((float)(ccx[tid] * 20.0), (float)(ccy[tid] * 20.0));
+    MT_CLK(0)
+    // Which 32 x 32-cell blocks of the window can a lookup touch?  A lookup lies within
+    // MT_REACH - 22.7 cells of a point turned by at most 30 degrees, so a block matters only if
+    // the disc of radius MT_REACH around its centre reaches the polar region the points
+    // sweep (conservative: float slack on the angles, two cells on the radii).
+    const int a0 = sh->a0, dy0 = sh->dy0;
+    if (tid < MT_NBLK) {
+        const int rb = tid / RB_RAW_STRIDE, wc = tid - rb * RB_RAW_STRIDE;
+        bool needed = !gate;
+        if (gate && sh->M > 0) {
+            const float bx = (float)(sh->x0 - 32 + 32 * wc + 16 - sh->g0xu), by = (float)(a0 + 32 * rb + 16 - sh->g0yu);
+            const float d = sqrtf(bx * bx + by * by);
+            if (d <= MT_REACH + 1.0f) {
+                needed = true;
+            } else {
+                const float al = asinf(MT_REACH / d) + 0.02f, ac = atan2f(by, bx) + 3.14159265f;
+                const int lo = (int)floorf((ac - al) * (MT_NBINS / 6.28318531f)), hi = (int)floorf((ac + al) * (MT_NBINS / 6.28318531f));
+                const int far = (int)(d - MT_REACH);
+                for (int bb = lo; bb <= hi && bb < lo + MT_NBINS; bb++) needed |= sh->rdil[bb & (MT_NBINS - 1)] >= far;
+            }
+        }
+        if (needed) {
+            atomicOr(&sh->need[rb], 1u << wc);
+            sh->blist[atomicAdd(&sh->nblk, 1)] = (unsigned short)tid;
         }
     }
-#endif
 
     // ---- 2. occupancy bitmap around the guess cell ---------------------------
+    MT_CLK(3)
     if (adj) {
         // previous scan rasterised relative to the guess cell, like curr points at rotation 0
-        for (int idx = tid; idx < RB_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
+        for (int idx = tid; idx < MT_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
         __syncthreads();
-        const int xb = sh->g0xu - sh->x0 + 32, yb = RB_WIN_R + 1;
+        const int xb = sh->g0xu - sh->x0 + 32, yb = RB_WIN_R + 1 + dy0;
         for (int q = tid; q < c.n_prev; q += MT_THREADS) {
             const double qx = c.prev_x[q] - sh->gx, qy = c.prev_y[q] - sh->gy;
             if (!(sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R)) continue;     // hybridmap.py:171
             const int a = __double2int_rd((qx + sh->fx) * 20.0 + 0.5) + xb, b = __double2int_rd((qy + sh->fy) * 20.0 + 0.5) + yb;
-            if (a < 0 || a >= 32 * RB_RAW_STRIDE || b < 0 || b >= RB_RAW_ROWS) continue;
+            if (a < 0 || a >= 32 * RB_RAW_STRIDE || b < 0 || b >= MT_RAW_ROWS) continue;
             atomicOr(&raw[b * RB_RAW_STRIDE + (a >> 5)], 1u << (a & 31));
         }
     } else {
-        const int x0 = sh->x0, y0 = sh->y0;
-        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-        // four consecutive lanes take the same word of four consecutive rows, so that
-        // together they consume whole 8x4-cell sectors
-        for (int it = tid; it < ((RB_RAW_ROWS + 3) / 4) * RB_RAW_STRIDE * 4; it += MT_THREADS) {
-            const int grp = it / (RB_RAW_STRIDE * 4), within = it - grp * (RB_RAW_STRIDE * 4);
-            const int rw = within >> 2, rr = 4 * grp + (within & 3);
-            if (rr >= RB_RAW_ROWS) continue;
-            const int idx = rr * RB_RAW_STRIDE + rw;
-            const int uy = y0 - 1 + rr, ux = x0 - 32 + 32 * rw;
-            uint32_t word = 0;
-            if (uy >= 0 && uy < c.uy_max && ux >= 0 && ux < c.ux_max) {
-                const uint32_t t = pt[(uy / RB_SUB) * c.subs_x + ux / RB_SUB];
-                if (t != RB_NONE) {
-                    // 32 cells of one row = the same 8-byte row slice of four consecutive 8x4 blocks
-                    const uint2 *src = reinterpret_cast<const uint2 *>(c.pool + (size_t)t * RB_SUB_BYTES +
-                                                                       RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB));
-                    const uint2 q0 = src[0], q1 = src[4], q2 = src[8], q3 = src[12];
-                    const uint4 a = make_uint4(q0.x, q0.y, q1.x, q1.y), b = make_uint4(q2.x, q2.y, q3.x, q3.y);
-                    word = mt_pack4(a.x) | (mt_pack4(a.y) << 4) | (mt_pack4(a.z) << 8) | (mt_pack4(a.w) << 12) |
-                           (mt_pack4(b.x) << 16) | (mt_pack4(b.y) << 20) | (mt_pack4(b.z) << 24) |
-                           (mt_pack4(b.w) << 28);
+        __syncthreads();                                                    // need[], blist[] complete
+        const int x0 = sh->x0, nblk = sh->nblk;
+        unsigned char *rawb = reinterpret_cast<unsigned char *>(raw);
+        // blocks no lookup can reach stay empty
+        for (int b = warp; b < MT_NBLK; b += MT_WARPS) {
+            const int rb = b / RB_RAW_STRIDE, wc = b - rb * RB_RAW_STRIDE;
+            if ((sh->need[rb] >> wc) & 1u) continue;
+            const int row = 32 * rb + lane;
+            if (row < MT_RAW_ROWS) raw[row * RB_RAW_STRIDE + wc] = 0u;
+        }
+        // One warp per block, one lane per 32-byte sector (8 cells of 4 rows): whole sectors
+        // in flight, MT_GATHER_U blocks per round, page-table entries from shared memory (one
+        // global-memory latency per round).  Thresholded bytes go straight to their place.
+        const int sx = lane & 3, sy = lane >> 2;
+        const int sxb0 = sh->sxb0, syb0 = sh->syb0;
+        for (int i0 = warp; i0 < nblk; i0 += MT_GATHER_U * MT_WARPS) {
+            uint4 v[MT_GATHER_U][2];
+            int row0[MT_GATHER_U], wcs[MT_GATHER_U];
+#pragma unroll
+            for (int u = 0; u < MT_GATHER_U; u++) {
+                const int i = i0 + u * MT_WARPS;
+                v[u][0] = v[u][1] = make_uint4(0u, 0u, 0u, 0u);
+                row0[u] = -1;
+                if (i >= nblk) continue;
+                const int b = sh->blist[i], rb = b / RB_RAW_STRIDE, wc = b - rb * RB_RAW_STRIDE;
+                const int r0 = 32 * rb + 4 * sy;
+                if (r0 >= MT_RAW_ROWS) continue;
+                row0[u] = r0; wcs[u] = wc;
+                const int uy = a0 + r0, ux = x0 - 32 + 32 * wc + 8 * sx;
+                if (uy >= 0 && uy < c.uy_max && ux >= 0 && ux < c.ux_max) {
+                    const int syb = uy / RB_SUB, sxb = ux / RB_SUB;
+                    const uint32_t t = sh->ptw[(syb - syb0) * 5 + (sxb - sxb0)];
+                    if (t != RB_NONE) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES +
+                                                                           RB_OFF_Y(uy - syb * RB_SUB) + RB_OFF_X(ux - sxb * RB_SUB));
+                        v[u][0] = __ldg(src);
+                        v[u][1] = __ldg(src + 1);
+                    }
                 }
             }
-            raw[idx] = word;
-        }
-    }
-    __syncthreads();
-    // 3x3 dilation: a lookup counts when the cell or one of its 8 neighbours is occupied
-    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
-        const int r = idx / RB_BM_STRIDE, w = idx - r * RB_BM_STRIDE;
-        uint32_t v = 0;
-        if (w < RB_BM_STRIDE - 1) {
 #pragma unroll
-            for (int dr = 0; dr < 3; dr++) {
-                const uint32_t *row = raw + (r + dr) * RB_RAW_STRIDE + w;
-                const uint32_t lw = row[0], cw = row[1], rw = row[2];
-                v |= cw | (cw << 1) | (cw >> 1) | (lw >> 31) | (rw << 31);
+            for (int u = 0; u < MT_GATHER_U; u++) {
+                if (row0[u] < 0) continue;
+                unsigned char *dst = rawb + ((size_t)row0[u] * RB_RAW_STRIDE + wcs[u]) * 4 + sx;
+                dst[0] = (unsigned char)(mt_pack4(v[u][0].x) | (mt_pack4(v[u][0].y) << 4));
+                dst[RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][0].z) | (mt_pack4(v[u][0].w) << 4));
+                dst[2 * RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][1].x) | (mt_pack4(v[u][1].y) << 4));
+                dst[3 * RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][1].z) | (mt_pack4(v[u][1].w) << 4));
             }
         }
-        bm[idx] = v;
     }
     __syncthreads();
+    MT_CLK(1)
 
-    // dilation by MT_GRAD for the rotation-group bounds: horizontal pass bm -> raw,
-    // vertical pass raw -> bmg (rows / words outside the window are empty)
-    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
-        const int r = idx / RB_BM_STRIDE, w = idx - r * RB_BM_STRIDE;
-        uint32_t v = 0;
-        if (w < RB_BM_STRIDE - 1) {
-            const uint32_t cur = bm[idx], prev = w > 0 ? bm[idx - 1] : 0u, next = bm[idx + 1];
-            v = cur;
-#pragma unroll
-            for (int d = 1; d <= MT_GRAD; d++) v |= (cur << d) | (cur >> d) | (prev >> (32 - d)) | (next << (32 - d));
+    // ---- 2b. both dilations in one pass down the rows --------------------------------
+    //   bm  = raw dilated by 1 (a lookup counts when the cell or one of its 8 neighbours is
+    //         occupied: the proximity kernel of our matcher)
+    //   bmg = raw dilated by 1 + MT_GRAD (upper bound for every rotation of a group)
+    // A thread owns one 32-cell word column over MT_SEG_ROWS rows and walks down the staged
+    // rows once: three loads per row, the vertical windows are running ORs in registers
+    // (13 rows = doubling 2, 4, 8 and two of those 5 apart).  Rows of raw beyond the buffer
+    // count as empty, like rows of bm beyond the window.
+    {
+        static_assert(MT_GRAD == 5, "the running OR below is a 13-row window");
+        static_assert((MT_THREADS / 16) * MT_SEG_ROWS >= RB_BM_ROWS, "segments must cover the window");
+        const int w = tid & 15, r0 = (tid >> 4) * MT_SEG_ROWS, r1 = min(r0 + MT_SEG_ROWS, RB_BM_ROWS);
+        bool live = false;
+        if (r0 < RB_BM_ROWS) {
+            const int rb0 = max(r0 + dy0 + 1 - 6, 0) >> 5, rb1 = min(r1 + dy0 + 6, MT_RAW_ROWS - 1) >> 5;
+            for (int rb = rb0; rb <= rb1; rb++) live |= (sh->need[rb] >> (w + 1)) & 1u;
         }
-        raw[idx] = v;
+        if (r0 < RB_BM_ROWS && !live) {
+            for (int r = r0; r < r1; r++) { bm[r * RB_BM_STRIDE + w] = 0u; bmg[r * RB_BM_STRIDE + w] = 0u; }
+        } else if (r0 < RB_BM_ROWS) {
+            // step s reads raw row rho = rs + s; bm row rho - dy0 - 2 and bmg row rho - dy0 - 7 complete there
+            const int rs = r0 + dy0 - 5;
+            uint32_t h1p = 0, h1pp = 0;                                     // 3-wide rows rho-1, rho-2
+            uint32_t h6p = 0, A[2] = {0, 0}, Bq[4] = {0, 0, 0, 0}, Cq[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+            for (int s_ = 0; s_ < MT_SEG_ROWS + 12; s_++) {
+                const int rho = rs + s_;
+                uint32_t l = 0, cw = 0, rw = 0;
+                if (rho >= 0 && rho < MT_RAW_ROWS) {
+                    const uint32_t *row = raw + rho * RB_RAW_STRIDE + w;
+                    l = row[0]; cw = row[1]; rw = row[2];
+                }
+                const uint32_t h1 = cw | (cw << 1) | (cw >> 1) | (l >> 31) | (rw << 31);
+                uint32_t h6 = h1;
+#pragma unroll
+                for (int d = 2; d <= MT_GRAD + 1; d++) h6 |= __funnelshift_l(l, cw, d) | __funnelshift_r(cw, rw, d);
+                const int rbm = rho - dy0 - 2;
+                if (rbm >= r0 && rbm < r1) bm[rbm * RB_BM_STRIDE + w] = h1 | h1p | h1pp;
+                h1pp = h1p; h1p = h1;
+                const uint32_t a_ = h6 | h6p;                               // rows rho-1 .. rho
+                const uint32_t b_ = a_ | A[s_ & 1];                         // | a(rho-2): rows rho-3 .. rho
+                const uint32_t c_ = b_ | Bq[s_ & 3];                        // | b(rho-4): rows rho-7 .. rho
+                const uint32_t o_ = c_ | Cq[s_ % 5];                        // | c(rho-5): rows rho-12 .. rho
+                h6p = h6; A[s_ & 1] = a_; Bq[s_ & 3] = b_; Cq[s_ % 5] = c_;
+                const int rg = rho - dy0 - 7;
+                if (rg >= r0 && rg < r1) bmg[rg * RB_BM_STRIDE + w] = o_;
+            }
+        }
+        if (tid < RB_BM_ROWS) { bm[tid * RB_BM_STRIDE + 16] = 0u; bmg[tid * RB_BM_STRIDE + 16] = 0u; }
+        if (tid + MT_THREADS < RB_BM_ROWS) { bm[(tid + MT_THREADS) * RB_BM_STRIDE + 16] = 0u; bmg[(tid + MT_THREADS) * RB_BM_STRIDE + 16] = 0u; }
     }
     __syncthreads();
-    for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) {
-        const int r = idx / RB_BM_STRIDE;
-        const int r0 = max(r - MT_GRAD, 0), r1 = min(r + MT_GRAD, RB_BM_ROWS - 1);
-        uint32_t v = 0;
-        for (int rr = r0; rr <= r1; rr++) v |= raw[idx + (rr - r) * RB_BM_STRIDE];
-        bmg[idx] = v;
-    }
-    __syncthreads();
+    MT_CLK(2)
 
     const int M = sh->M, nx = sh->nx, ny = sh->ny;
     const int nrows = 2 * ny + 1, ncols = 2 * nx + 1;
     const uint32_t colmask = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
     uint32_t *pts = raw + warp * RB_MAXB;                                   // raw is dead now: per-warp point lists
-    const int lane_off = (lane < nrows ? lane : 0) * RB_BM_STRIDE;
+    const uint32_t lane_off = (uint32_t)((lane < nrows ? lane : 0) * RB_BM_STRIDE * 4);
+    const uint32_t bm_lane = (uint32_t)__cvta_generic_to_shared(bm) + lane_off;
+    const uint32_t bmg_lane = (uint32_t)__cvta_generic_to_shared(bmg) + lane_off;
     const int nrot = 2 * c.nk + 1, ngroups = (nrot + MT_GROUP - 1) / MT_GROUP;
 
     // ---- 3a0. seed the best key with MT_SEEDS rotations around the guess ---------
@@ -693,24 +966,39 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     // early).  The other warps start on the group bounds right away.
     const int seed_lo = -(MT_SEEDS / 2), seed_hi = seed_lo + MT_SEEDS - 1;
     int visited = 0;                                                        // per warp (all lanes count alike)
+    // A pass that raises the best key keeps its bit-sliced counters in this warp's slot (raw is
+    // dead, the point lists take its first MT_WARPS * RB_MAXB words): the warp that holds the
+    // final best key has the score slice of the best rotation without another pass.
+    uint32_t *slot = raw + MT_WARPS * RB_MAXB + warp * (MT_PLANES * 32);
+    unsigned long long saved_key = 0ull;
+    long long wclk = clock64();
     if (sh->ok && warp < MT_SEEDS && seed_lo + warp >= -c.nk && seed_lo + warp <= c.nk) {
         const int k = seed_lo + warp;
-        mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
-        __syncwarp();
         uint32_t pl[MT_PLANES];
-        mt_accumulate<false>(bm, pts, M, lane_off, pl, 0u, nullptr, &visited);
+        mt_pass<false>(c, sh, ccx, ccy, ccf, k, nx, ny, bm_lane, pts, M, lane, pl, 0u, nullptr, &visited);
         unsigned long long key = 0ull;
         if (lane < nrows) key = mt_lane_key(pl, colmask, nx, lane - ny, k);
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
             if (other > key) key = other;
         }
+        unsigned long long old = 0ull;
         if (lane == 0) {
-            atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
+            old = atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
             atomicAdd(&sh->evals, 1);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (key > old) {                                                    // best so far: keep its counters for the covariance
+            saved_key = key;
+#pragma unroll
+            for (int pb = 0; pb < MT_PLANES; pb++) slot[pb * 32 + lane] = pl[pb];
         }
     }
 
+    MT_WCLK(10, wclk)
+    if (lane == 0 && !slice_out && visited) atomicAdd(&c.stats->match_clk[13], (unsigned long long)visited);
+    int visited_seed = visited;
+    wclk = clock64();
     // ---- 3a. upper bound of every rotation group (shared queue) -------------------
     if (sh->ok) {
         for (;;) {
@@ -719,11 +1007,13 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= ngroups) break;
             const int kmid = min(g * MT_GROUP + MT_GROUP / 2, nrot - 1) - c.nk;
-            __syncwarp();
-            mt_rasterise(c, sh, ccx, ccy, kmid, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
-            __syncwarp();
+            if (g * MT_GROUP - c.nk >= seed_lo && min(g * MT_GROUP + MT_GROUP - 1, nrot - 1) - c.nk <= seed_hi) {
+                if (lane == 0) { sh->group_ub[g] = -1; atomicAdd(&sh->evals, -1); }   // every member is a seed: nothing to bound
+                continue;
+            }
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bmg, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, &sh->best_key, &visited);
+            const bool done = mt_pass<true>(c, sh, ccx, ccy, ccf, kmid, nx, ny, bmg_lane, pts, M, lane, pl, lane < nrows ? colmask : 0u,
+                                            &sh->best_key, &visited);
             if (!done) {                                                    // even the bound cannot reach the seeded best
                 if (lane == 0) sh->group_ub[g] = -1;
                 continue;
@@ -741,7 +1031,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             if (lane == 0) sh->group_ub[g] = sc;
         }
     }
+    MT_WCLK(11, wclk)
+    if (lane == 0 && !slice_out) atomicAdd(&c.stats->match_clk[14], (unsigned long long)(visited - visited_seed));
+    visited_seed = visited;
     __syncthreads();
+    MT_CLK(4)
     if (warp == 0 && sh->ok) {                                              // rank the groups by decreasing bound
         for (int me = lane; me < ngroups; me += 32) {
             const int mine = sh->group_ub[me];
@@ -754,6 +1048,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         }
     }
     __syncthreads();
+    MT_CLK(5)
+    wclk = clock64();
 
     // ---- 3b. score member rotations while their group's bound can still win -----
     if (sh->ok) {
@@ -771,11 +1067,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             const unsigned long long cur = *vbest;
             if (ub < (int)(cur >> 32)) break;                               // groups are sorted: nothing left can win
             if (mt_key(ub, 0, 0, k) < cur) continue;                        // this rotation cannot beat the best key
-            __syncwarp();
-            mt_rasterise(c, sh, ccx, ccy, k, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
-            __syncwarp();
             uint32_t pl[MT_PLANES];
-            const bool done = mt_accumulate<true>(bm, pts, M, lane_off, pl, lane < nrows ? colmask : 0u, vbest, &visited);
+            const bool done = mt_pass<true>(c, sh, ccx, ccy, ccf, k, nx, ny, bm_lane, pts, M, lane, pl, lane < nrows ? colmask : 0u, vbest,
+                                            &visited);
             if (lane == 0) atomicAdd(&sh->evals, 1);
             if (!done) continue;                                            // cannot reach the best score any more
             unsigned long long key = 0ull;
@@ -784,10 +1078,20 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 if (other > key) key = other;
             }
-            if (lane == 0) atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
+            unsigned long long old = 0ull;
+            if (lane == 0) old = atomicMax(const_cast<unsigned long long *>(&sh->best_key), key);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (key > old) {
+                saved_key = key;
+#pragma unroll
+                for (int pb = 0; pb < MT_PLANES; pb++) slot[pb * 32 + lane] = pl[pb];
+            }
         }
     }
+    MT_WCLK(12, wclk)
+    if (lane == 0 && !slice_out) atomicAdd(&c.stats->match_clk[15], (unsigned long long)(visited - visited_seed));
     __syncthreads();
+    MT_CLK(6)
     if (lane == 0 && visited) atomicAdd(&sh->visits, visited);
     int bs, bi, bj, bk;
     mt_key_decode(sh->best_key, bs, bi, bj, bk);
@@ -799,44 +1103,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
 
     // ---- 5. covariance --------------------------------------------------------
     if (valid || slice_out) {
-        if (warp == 0) {                                                    // translation slice at the best rotation
-            mt_rasterise(c, sh, ccx, ccy, bk, pts, lane, -nx, -ny, 2 * nx, 2 * ny);
-            __syncwarp();
-            uint32_t pl[MT_PLANES];
-            mt_accumulate<false>(bm, pts, M, lane_off, pl);
-            long long W0 = 0, Wx = 0, Wy = 0, Wxx = 0, Wyy = 0, Wxy = 0;
-            if (lane < nrows) {
-                const int j = lane - ny;
-                for (int b = 0; b < ncols; b++) {
-                    const int s = mt_decode(pl, b), i = b - nx, d = bs - s;
-                    if (slice_out) slice_out[(j + RB_NT_MAX) * RB_SLICE_W + (i + RB_NT_MAX)] = s;
-                    if (d > 40) continue;
-                    const long long w = 1ll << (40 - d);
-                    W0 += w; Wx += w * i; Wy += w * j; Wxx += w * i * i; Wyy += w * j * j; Wxy += w * i * j;
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                W0 += __shfl_xor_sync(0xffffffffu, W0, o);
-                Wx += __shfl_xor_sync(0xffffffffu, Wx, o);
-                Wy += __shfl_xor_sync(0xffffffffu, Wy, o);
-                Wxx += __shfl_xor_sync(0xffffffffu, Wxx, o);
-                Wyy += __shfl_xor_sync(0xffffffffu, Wyy, o);
-                Wxy += __shfl_xor_sync(0xffffffffu, Wxy, o);
-            }
-            if (lane == 0) {
-                sh->mom[0] = W0; sh->mom[1] = Wx; sh->mom[2] = Wy; sh->mom[3] = Wxx; sh->mom[4] = Wyy; sh->mom[5] = Wxy;
-            }
-        } else {                                                            // rotation line at the best translation
+        if (sh->ok && saved_key == sh->best_key && lane == 0) sh->slot_warp = warp;    // this warp holds the slice of the best rotation
+        if (sh->ok) {                                                       // rotation line at the best translation (all warps)
             long long T0 = 0, T1 = 0, T2 = 0;
             const int klo = max(bk - MT_ROT_LINE_HALF, -c.nk), khi = min(bk + MT_ROT_LINE_HALF, c.nk);
-            for (int k = klo + (warp - 1); k <= khi; k += MT_WARPS - 1) {
+            for (int k = klo + warp; k <= khi; k += MT_WARPS) {
                 __syncwarp();
-                mt_rasterise(c, sh, ccx, ccy, k, pts, lane, bi, bj, 0, 0);
+                mt_rasterise(c, sh, ccx, ccy, ccf, k, pts, lane, bi, bj, 0, 0);
                 __syncwarp();
                 int s = 0;
                 for (int q = lane; q < M; q += 32) {
                     const uint32_t pk = pts[q];
-                    s += (int)((bm[pk >> 5] >> (pk & 31)) & 1u);
+                    s += (int)((bm[pk >> MT_PT_WORD_SHIFT] >> (pk & 31)) & 1u);
                 }
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 const int d = bs - s;
@@ -851,8 +1129,30 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                 atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[8]), (unsigned long long)T2);
             }
         }
+        __syncthreads();
+        if (sh->ok && sh->slot_warp >= 0) {                                 // translation slice at the best rotation: every thread decodes a few cells
+            const uint32_t *best_slot = raw + MT_WARPS * RB_MAXB + sh->slot_warp * (MT_PLANES * 32);
+            long long mo[6] = {0, 0, 0, 0, 0, 0};
+            for (int cell = tid; cell < nrows * ncols; cell += MT_THREADS) {
+                const int jr = cell / ncols, b = cell - jr * ncols;
+                int sc = 0;
+#pragma unroll
+                for (int pb = 0; pb < MT_PLANES; pb++) sc |= (int)((best_slot[pb * 32 + jr] >> b) & 1u) << pb;
+                const int i = b - nx, j = jr - ny, d = bs - sc;
+                if (slice_out) slice_out[(j + RB_NT_MAX) * RB_SLICE_W + (i + RB_NT_MAX)] = sc;
+                if (d > 40) continue;
+                const long long w = 1ll << (40 - d);
+                mo[0] += w; mo[1] += w * i; mo[2] += w * j; mo[3] += w * (i * i); mo[4] += w * (j * j); mo[5] += w * (i * j);
+            }
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                for (int o = 16; o > 0; o >>= 1) mo[e] += __shfl_xor_sync(0xffffffffu, mo[e], o);
+                if (lane == 0 && mo[e]) atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[e]), (unsigned long long)mo[e]);
+            }
+        }
     }
     __syncthreads();
+    MT_CLK(7)
 
     // ---- 5b. NDT refinement, matchScanCustom.m:32-50 ---------------------------------
     static_assert(MT_THREADS >= RB_MAXB && MT_WARPS % 2 == 0, "NDT stage: one thread per beam, two halves of warps");
@@ -861,7 +1161,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     bool nd_accept = false;
     if (c.refine && valid) {
         double qx = 0.0, qy = 0.0;
-        const bool has = tid < c.B && mt_curr_point(c, sh, exists, tid, adj, qx, qy);
+        const bool has = has_beam && mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy);
         double *red = reinterpret_cast<double *>(bmg), *ctl = red + MT_WARPS * NDT_TERMS;   // bmg is dead after phase A
         ndt_refine(bm, red, ctl, sh->g0xu - sh->x0, sh->fx, sh->fy, has, qx, qy, nd_p[0], nd_p[1], nd_p[2]);
         nd_p[0] = ctl[1]; nd_p[1] = ctl[2]; nd_p[2] = ctl[3]; nd_S = ctl[4]; nd_evals = (int)ctl[5];
@@ -871,6 +1171,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     }
 
     // ---- 6. result --------------------------------------------------------------
+    MT_CLK(8)
     if (tid == 0) {
         double *op = c.m_pose + 3 * (size_t)p, *oc = c.m_cov + 9 * (size_t)p;
         op[0] = sh->gx + (double)bi * RB_CS;                                // hybridmap.py:253-255
@@ -949,11 +1250,11 @@ void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)
     if (c.use_dup) match_copy_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
 }
 
-// Debug/test entry: re-run the matcher for one particle and dump the score slice
-// at its best rotation (29x29 int32).  Overwrites that particle's match outputs
-// with identical values.
-void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, cudaStream_t s)
+// Debug/test entry: re-run the last match (same mode) for one particle and dump the
+// score slice at its best rotation (29x29 int32).  Overwrites that particle's match
+// outputs with identical values.
+void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, int adj, cudaStream_t s)
 {
     match_set_attr();
-    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev, 0);
+    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev, adj);
 }

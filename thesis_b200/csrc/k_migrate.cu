@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) migrate_adopt_tiles_kernel(RbCtx c, const
     if (i >= n_tiles) return;
     if (threadIdx.x == 0) {
         int idx = atomicSub(c.free_count, 1) - 1;
-        if (idx < 0) { atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
+        if (idx < 0) { atomicAdd(c.free_count, 1); atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
         else { s_t = c.free_list[idx]; c.refcnt[s_t] = 0u; }
         map[i] = s_t;
     }

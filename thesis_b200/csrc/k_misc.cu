@@ -24,7 +24,7 @@ __global__ void init_kernel(RbCtx c)
         *c.free_count = (int)c.pool_tiles;
         RbStats z = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         *c.stats = z;
-        RbFlags f = {0, 0, 0, 0, 0, {0, 0, 0}};
+        RbFlags f = {};
         *c.flags = f;
     }
 }

@@ -40,10 +40,12 @@ __global__ void __launch_bounds__(128) motion_kernel(RbCtx c, MotionArgs a)
         Q[0] = fabs(q0 * q0); Q[4] = fabs(q1 * q1); Q[8] = fabs(q2 * q2);
     } else {                                  // DefaultIMUData.py:25-54
         double t2 = th + dt * a.u[1];
-        np_[0] = x + dt * a.u[0] * cos(t2);
-        np_[1] = y + dt * a.u[0] * sin(t2);
+        double ct, st, cp, sp;
+        rb_sincos(t2, &st, &ct);
+        rb_sincos(th, &sp, &cp);
+        np_[0] = x + dt * a.u[0] * ct;
+        np_[1] = y + dt * a.u[0] * st;
         np_[2] = t2;
-        double cp = cos(th), sp = sin(th);
         F[2] = dt * a.u[0] * cp;
         F[5] = dt * a.u[0] * sp;
         double g0 = dt * cp, g1 = dt * sp, g2 = dt, m0 = 0.05 * 0.05, m1 = (PI / 180 / 2) * (PI / 180 / 2);

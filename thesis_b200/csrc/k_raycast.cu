@@ -111,8 +111,7 @@ __device__ __forceinline__ bool particle_frame(const RbCtx &c, int p, double &x,
     x = pose[0];
     y = pose[1];
     double th = pose[2];
-    cs_ = cos(th);
-    sn_ = sin(th);
+    rb_sincos(th, &sn_, &cs_);
     int tx, ty, ix, iy;
     rb_read_axis(x, tx, ix);
     rb_read_axis(y, ty, iy);
@@ -193,6 +192,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
                 if (action) {
                     int idx = atomicSub(c.free_count, 1) - 1;
                     if (idx < 0) {
+                        atomicAdd(c.free_count, 1);                        // keep the stack pointer valid for the pushes of resample_refs
                         atomicExch(&c.flags->pool_exhausted, 1);
                         if (action == 2) atomicAdd(&c.refcnt[told], 1u);   // undo: stay a sharer
                         action = 0;

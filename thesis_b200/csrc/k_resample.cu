@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
     if (tid == 0) {
         for (int k = 1; k < RS_THREADS / 32; k++) { mx = fmax(mx, red_mx[k]); mn = fmin(mn, red_mn[k]); }
         s_do = (mx - mn > RB_RESAMPLE_TRIGGER) ? 1 : 0;
+        if (c.flags->pool_exhausted) s_do = 0;                               // maps missed a scan: freeze the set until the caller reacts
         c.flags->did_resample = s_do;
         c.flags->resample_error = 0;
         c.flags->remote_needed = 0;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
         if (e1 > NG) { e1 = NG; }
         for (long long s = e0; s < e1; s++) c.ancestors[s] = i;
     }
-    if (bad) c.flags->resample_error = 1;
+    if (bad) { c.flags->resample_error = 1; c.flags->resample_error_sticky = 1; }
 }
 
 // Local slot j of this rank is global slot rank*N + j.
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(256) resample_refs_kernel(RbCtx c)
         if (t == RB_NONE) continue;
         if (m == 0) {
             if (atomicSub(&c.refcnt[t], 1u) == 1u) {                          // last reference: back to the free list
-                int idx = atomicAdd(c.free_count, 1);
-                c.free_list[idx] = t;
+                const int idx = atomicAdd(c.free_count, 1);
+                if (idx >= 0 && (uint32_t)idx < c.pool_tiles) c.free_list[idx] = t;
+                else atomicExch(&c.flags->world_overflow, 3);                 // cannot happen: the counter is kept in [0, pool_tiles]
             }
         } else {
             atomicAdd(&c.refcnt[t], (unsigned)(m - 1));

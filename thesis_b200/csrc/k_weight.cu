@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
     if (fallback_phase) {
         if (valid) return;
         const double *pose = c.pose + 3 * (size_t)p;
-        double x = pose[0], y = pose[1], cs_ = cos(pose[2]), sn_ = sin(pose[2]);
+        double x = pose[0], y = pose[1], cs_, sn_;
+        rb_sincos(pose[2], &sn_, &cs_);
         int S = 0;
         for (int j = lane; j < c.B; j += 32) {
             double d = c.dist[j];
@@ -93,9 +94,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
         double y1 = (d1 - l10 * y0) / l11;
         double y2 = ((d2 - l20 * y0) - l21 * y1) / l22;
         double maha = (y0 * y0 + y1 * y1) + y2 * y2;
-        double pr = exp(-0.5 * maha) / nrm * 10.0;                            // robot.py:87
+        double pr = rb_exp(-0.5 * maha) / nrm * 10.0;                            // robot.py:87
         // observation weight of this sample, robot.py:118-139
-        double cs_ = cos(g2), sn_ = sin(g2);
+        double cs_, sn_;
+        rb_sincos(g2, &sn_, &cs_);
         int S = 0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
         // WT_INFLIGHT beams in flight: locate (ALU) -> page-table entries -> cells

@@ -213,6 +213,10 @@ class ShardedParticleSet(MigratingSet):
 
         self._dist = dist
         self.group = group
+        if kw.get("stream", 0):
+            # the collectives below are ordered against the handle's work through the legacy default
+            # stream; a private stream would let peers read tiles that finish_resample() is freeing
+            raise ValueError("ShardedParticleSet runs on the default stream (stream=0)")
         super().__init__(n_local, n_beams, dist.get_rank(group), dist.get_world_size(group), device=device, **kw)
         self._w_all = self._torch.empty(self.n_global, dtype=self._torch.float64, device=self._dev)
         self._tev = None
@@ -282,10 +286,16 @@ class ShardedParticleSet(MigratingSet):
         return did, (self._anc.copy() if want_ancestors else None)
 
     def resample(self, u01=None, want_ancestors=True):
+        # NCCL work is enqueued on torch's CURRENT stream: pin it to the default stream, which is the
+        # handle's, whatever torch.cuda.stream(...) context the caller is in
+        with self._torch.cuda.stream(self._torch.cuda.default_stream(self._dev)):
+            if self.transport == "peer":
+                return self._resample_peer(u01, want_ancestors)
+            return self._resample_nccl(u01, want_ancestors)
+
+    def _resample_nccl(self, u01, want_ancestors):
         import time
 
-        if self.transport == "peer":
-            return self._resample_peer(u01, want_ancestors)
         torch, dist = self._torch, self._dist
         prof = self._prof
         t0 = time.perf_counter()

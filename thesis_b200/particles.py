@@ -73,6 +73,10 @@ class ParticleSet:
     def synchronize(self):
         self._ck(self._lib.rbpf_synchronize(self._h))
 
+    def clear_errors(self):
+        """Reset the sticky device-side error flags (pool exhausted, resample assertion, internal bound)."""
+        self._ck(self._lib.rbpf_clear_errors(self._h))
+
     # -- stages (include/rbpf_b200.h)
     def set_scan(self, ranges, angles):
         r, rp = _d(ranges)
@@ -239,6 +243,20 @@ class ParticleSet:
         s = _lib.RbpfStats()
         self._ck(self._lib.rbpf_stats(self._h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    MATCH_PHASES = ("frame_points", "gather", "dilate3", "dilate_group", "seeds_bounds", "rank", "members",
+                    "covariance", "ndt")
+
+    def match_phase_clocks(self):
+        """SM clocks of the matcher kernel by phase (rbpf_match_phase_clocks): CTA-level split, per-warp
+        busy clocks of the three search phases and the points they visited."""
+        out = (C.c_uint64 * 16)()
+        self._ck(self._lib.rbpf_match_phase_clocks(self._h, out))
+        v = [int(x) for x in out]
+        d = {"cta_" + n: v[i] for i, n in enumerate(self.MATCH_PHASES)}
+        d.update(warp_seeds=v[10], warp_bounds=v[11], warp_members=v[12],
+                 visits_seeds=v[13], visits_bounds=v[14], visits_members=v[15])
+        return d
 
     def weights_device_ptr(self):
         p = C.c_uint64(0)
