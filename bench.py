@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-particles", type=int, default=0, help="CPU baseline sample (0 = 4 per core)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-parity", type=int, default=1024,
+                    help="N > 1: particles per rank of the untimed sharded-vs-single-set identity check (0 = skip)")
     ap.add_argument("--refine", type=int, default=REFINE_DEFAULT, choices=[0, 1],
                     help="NDT refinement stage of the reference matcher (matchScanCustom.m:32-50) after the grid search")
     return ap.parse_args()
@@ -101,9 +103,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(work, n_particles, max_seconds, beams, refine):
+def port_baseline(work, n_particles, max_seconds, beams, refine):
     """The oracle (C port of the reference path, OpenMP over particles) on a
-    bounded sample of the same workload.  Returns (updates/s, description)."""
+    bounded sample of the same workload.  Returns (updates/s, cores, description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
@@ -137,10 +139,35 @@ def cpu_baseline(work, n_particles, max_seconds, beams, refine):
     return val, cores, desc
 
 
+def cpu_baseline(work, args):
+    """The reference's CPU path on the box's host cores, on a bounded sample of the bench workload:
+    the UNMODIFIED Python reference (oracle/_ref, vendored by oracle/vendor_ref.py; MATLAB's
+    matchScanCustom answered by the oracle's restated matcher) on one core -- the reference is
+    single-threaded, main.py:144,157 -- and fanned over all cores, and beside it the oracle's C port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_baseline as RB
+
+    cores = os.cpu_count() or 1
+    pv, pc, pd = port_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams, args.refine)
+    port = {"value": pv, "unit": UNIT, "cores": pc, "kind": "port", "sample": pd}
+    if not RB.available() or args.refine:
+        return port
+    one = RB.run(work.ranges, work.angles, work.odom, work.dt, 2, 3, workers=1)
+    allc = RB.run(work.ranges, work.angles, work.odom, work.dt, 2 * cores, 3, workers=cores)
+    return {"value": allc["updates_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "unmodified Python reference: %d particles x %d scans of the same workload in %d processes, %.1f s "
+                      "(every process its own small filter; MATLAB matchScanCustom answered by the oracle's C matcher)"
+                      % (allc["particles"], allc["scans"], cores, allc["seconds"]),
+            "single_core": {"value": one["updates_per_s"], "cores": 1,
+                            "sample": "%d particles x %d scans, %.1f s" % (one["particles"], one["scans"], one["seconds"])},
+            "port": port}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The
-    reference is Python + a MATLAB engine and cannot travel to the GPU box, so
-    this arm times the oracle port (oracle/rbpf_oracle.c) on all host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores --
+    the unmodified Python reference (oracle/_ref) fanned over all cores, one particle per core and step
+    (a bounded sample: the reference needs about a second per particle-scan); the oracle's C port when
+    the reference has not been vendored (or with --refine, which the Python reference run does not have)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,43 +175,52 @@ def run_reference(args):
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
+    import ref_baseline as RB
 
-    cores = O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
-    O.set_refine(bool(args.refine))
-    n_cpu = args.cpu_particles if args.cpu_particles > 0 else 8 * cores
+    cores = os.cpu_count() or 1
     n_scans_total = 2 + args.warmup + args.steps
     work = synth.Workload(n_scans_total + 1, args.beams)
+    if RB.available() and not args.refine:
+        per = max(1, args.cpu_particles // cores) if args.cpu_particles > 0 else 1
+        dt, n_cpu = RB.run_steps(work.ranges, work.angles, work.odom, work.dt, per, args.warmup, args.steps, cores)
+        kind = "reference"
+        sample = ("each step = %d particles x 1 scan (%d beams) of the same synthetic workload: the unmodified Python reference in "
+                  "%d processes (one small filter each; MATLAB matchScanCustom answered by the oracle's C matcher)" % (n_cpu, args.beams, cores))
+    else:
+        cores = O.set_threads(cores)                  # torchrun exports OMP_NUM_THREADS=1
+        O.set_refine(bool(args.refine))
+        n_cpu = args.cpu_particles if args.cpu_particles > 0 else 8 * cores
+        f = O.Filter(n_cpu, args.beams, 30)
+        rng = np.random.default_rng(5)
+        f.set_scan(work.ranges[0], work.angles)
+        f.integrate()
+        f.integrate()
 
-    f = O.Filter(n_cpu, args.beams, 30)
-    rng = np.random.default_rng(5)
-    f.set_scan(work.ranges[0], work.angles)
-    f.integrate()
-    f.integrate()
+        def one(s):
+            f.motion(1, work.odom[s - 1], work.dt, work.par)
+            f.set_scan(work.ranges[s], work.angles)
+            f.map_update(rng.standard_normal((n_cpu, 30, 3)))
+            f.resample(float(rng.random()))
 
-    def one(s):
-        f.motion(1, work.odom[s - 1], work.dt, work.par)
-        f.set_scan(work.ranges[s], work.angles)
-        f.map_update(rng.standard_normal((n_cpu, 30, 3)))
-        f.resample(float(rng.random()))
-
-    s = 1
-    for _ in range(args.warmup):
-        one(s)
-        s += 1
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one(s)
-        s += 1
-    dt = time.perf_counter() - t0
+        s = 1
+        for _ in range(args.warmup):
+            one(s)
+            s += 1
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one(s)
+            s += 1
+        dt = time.perf_counter() - t0
+        kind = "port"
+        sample = "each step = %d particles x 1 scan (%d beams) of the same synthetic workload, oracle C port with OpenMP" % (n_cpu, args.beams)
     val = n_cpu * args.steps / dt
-    sample = "each step = %d particles x 1 scan (%d beams) of the same synthetic workload" % (n_cpu, args.beams)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -198,6 +234,12 @@ def workload_config(args, world):
         "samples_per_particle": 30, "cell_m": 0.05, "parallelism": "particles sharded x%d" % world,
         "cell_dtype": "int8 log-odds tenths", "state_dtype": "f64 poses / covariances / weights",
         "l2_policy": "per-step working set (page tables + touched sub-tiles of all particles) exceeds the 126 MB L2; no flush",
+        # where the workload departs from SURVEY 8d config 5 (thesis_b200/synth.py): 5 % clutter would leave no free
+        # space to range over, so 0.05 %; odometry = truth + N(0, (3 cm, 3 cm, 0.02 rad)) per scan, enough that the
+        # zero correction isValidPose rejects is rarely the optimum; a 40 m loop through the door centres
+        "world": "200 m x 200 m, walls every 10 m with 1 m doors, clutter fraction 0.0005",
+        "odometry_noise": "N(0, (0.03 m, 0.03 m, 0.02 rad)) per scan on the velocity-family increments",
+        "trajectory": "closed 40 m x 40 m loop, 0.35 m or pi/10 per scan (the reference's update gate is 0.33 m / pi/9)",
     }
 
 
@@ -229,9 +271,13 @@ def run_b200(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-        from thesis_b200.dist import ShardedParticleSet
+        from thesis_b200.dist import ShardedParticleSet, dist_parity_check
+    # untimed, before anything else: is the sharded run the same computation as a single set?
+    dist_parity = None
+    if world > 1 and args.dist_parity > 0:
+        dist_parity = dist_parity_check(args.dist_parity, args.beams, frames=8, device=local_rank)
     n_local = args.particles // world
-    n_scans = 1 + args.burnin + args.warmup + 2 * args.steps + 2
+    n_scans = 1 + args.burnin + args.warmup + args.steps + 2
     work = synth.Workload(n_scans, args.beams)
     pool = int(n_local * 26 + 4096)
     if world > 1:
@@ -256,6 +302,11 @@ def run_b200(args):
         one(s)
         s += 1
     ps.synchronize()
+    st0 = ps.stats()
+    # The timed loop and the end-to-end loop run the SAME scans from the same state: the whole particle
+    # set is snapshotted on the device here and rewound in between (rbpf_snapshot / rbpf_restore).
+    ps.snapshot()
+    s0 = s
     # ---- timed region: device-resident inputs apart from the 360-double sweep ----
     ps.timing_enable(args.steps)
     ph0 = ps.match_phase_clocks() if hasattr(ps, "match_phase_clocks") else None
@@ -276,7 +327,10 @@ def run_b200(args):
     ph1 = ps.match_phase_clocks() if ph0 is not None else None
     ps.timing_enable(0)
     ps.synchronize()
-    # ---- end-to-end through the public API with host buffers ----
+    st1 = ps.stats()
+    # ---- end-to-end through the public API with host buffers, same scans ----
+    ps.restore()
+    s = s0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -311,15 +365,36 @@ def run_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json, sustained copy)" if peaks else "fallback 6.65 TB/s"
     value = args.particles * args.steps / (ms / 1e3)
     e2e = args.particles * args.steps / (ms_e2e / 1e3)
-    match_ms = stage_ms["match"] / max(nst, 1)
-    achieved = MATCH_BYTES_PER_UPDATE * n_local / (match_ms / 1e3) / 1e9
-    a_r = float(np.mean([work.ray_cells(i) for i in range(1, n_scans)]))
+    # ---- roofline entries: ALGORITHMIC bytes per update x updates per launch
+    #      / the launch's CUDA-event duration on the handle's stream, against the measured copy bandwidth
+    a_r = float(np.mean([work.ray_cells(i) for i in range(s0, s0 + args.steps)]))
+    cow = (st1["cow_copies"] - st0["cow_copies"]) / max(args.steps, 1)
+    fresh = (st1["fresh_allocs"] - st0["fresh_allocs"]) / max(args.steps, 1)
+    per_update = {
+        "match_kernel": ("match", MATCH_BYTES_PER_UPDATE, "int8 cells of the 240-degree sector of radius 11.7 m the search can reach",
+                         MATCH_DRAM_BYTES_PER_UPDATE_NCU),
+        "raycast_cast_kernel": ("raycast_cast", 2.0 * a_r, "read + write of the int8 cells under the rays (A_r = sum min(r, 15 m) / 5 cm)", None),
+        "raycast_prepare_kernel": ("raycast_prepare", (2.0 * cow + fresh) * 25600.0 / n_local,
+                                   "copy-on-write: 2 x 25,600 B per shared sub-tile made private, 25,600 B per fresh one", None),
+        "weight_kernel": ("weight", 32.0 * args.beams, "one 32-byte sector per beam (the 30 samples of a beam fall into the same cells)", None),
+    }
+    rooflines = {}
+    for kname, (stage, bpu, what, dram) in per_update.items():
+        ms_k = stage_ms[stage] / max(nst, 1)
+        ach = bpu * n_local / (ms_k / 1e3) / 1e9 if ms_k > 0 else 0.0
+        rooflines[kname] = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": dram * n_local if dram else None, "algorithmic_bytes_per_update": bpu, "what": what,
+                            "updates_per_launch": n_local, "launch_ms": ms_k, "peak_source": peak_src}
+    dominant = max(rooflines.values(), key=lambda r: r["launch_ms"])
+    rooflines["match_kernel"]["traffic_source"] = "ncu --set full on an 8,192-particle launch (profiles/), scaled per update"
+    rooflines["match_kernel"]["note"] = ("the correlative search is bound by shared-memory wavefronts and the ALU pipe (ncu: 71 % / 72 % "
+                                         "of peak), not by HBM; see DESIGN.md")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "i8", "data": "synthetic",
         "config": dict(workload_config(args, world), burnin_scans=args.burnin,
-                       ray_cells_per_scan=a_r, pool_subtiles=pool,
+                       ray_cells_per_scan=a_r, pool_subtiles=pool, cow_copies_per_scan=cow, fresh_subtiles_per_scan=fresh,
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),
                        pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
                        match_searches_run_fraction=st["match_runs"] / max(1, n_local * (s - 1)),
@@ -331,20 +406,18 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h),
-                "note": "the K scans that follow the device-timed ones on the same trajectory (the state cannot be rewound); "
-                        "work per scan varies with the ray lengths, so e2e and value are not the same scans"},
+                "note": "the same K scans as the device-timed loop, from the same device-side snapshot of the particle set; every step "
+                        "copies the sweep from pinned host memory and reads all poses and weights back"},
         # kernels of _librbpf.so per step (ncu launch list in profiles/): motion, match, match_copy_dups, weight x2
         # (samples + fallback), raycast prepare + cast, resample plan, mult, gather, refs, dups = 12; sharded runs add
         # the four pull kernels (claim, tiles, place, release); NCCL's own kernels are not counted
         "gpu_launches": int(args.steps * (12 if world == 1 else 16)),
-        "roofline": {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": MATCH_DRAM_BYTES_PER_UPDATE_NCU * n_local,
-                     "traffic_source": "ncu --set full on an 8,192-particle launch, scaled per update", "peak_source": peak_src,
-                     "algorithmic_bytes_per_update": MATCH_BYTES_PER_UPDATE, "updates_per_launch": n_local,
-                     "launch_ms": match_ms,
-                     "note": "the correlative search is shared-memory-lookup bound, not HBM bound; see DESIGN.md"},
+        "roofline": dominant,                               # the kernel with the longest launch
+        "rooflines": rooflines,
         "stage_ms_per_step": {k: v / max(nst, 1) for k, v in stage_ms.items()},
     }
+    if dist_parity is not None:
+        line["dist_parity"] = dist_parity
     if ph1 is not None:
         d = {k: ph1[k] - ph0[k] for k in ph1}
         cta = sum(v for k, v in d.items() if k.startswith("cta_")) or 1
@@ -354,8 +427,7 @@ def run_b200(args):
         line["match_visits_share"] = {k[7:]: round(d[k] / (sum(d[q] for q in d if q.startswith("visits_")) or 1), 4)
                                       for k in d if k.startswith("visits_")}
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, desc = cpu_baseline(work, args.cpu_particles, args.cpu_seconds, args.beams, args.refine)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        line["cpu_baseline"] = cpu_baseline(work, args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

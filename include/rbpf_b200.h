@@ -125,6 +125,12 @@ int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, int32_t n_poi
  * device Philox draws.  Particles whose match failed are left for
  * rbpf_integrate (their weight needs the updated map, robot.py:75-77). */
 int rbpf_weight(rbpf_handle h, const double *z);
+/* The same stage with the proposal samples themselves supplied by the caller: guesses = N*K*3 (host,
+ * particle-major; rows of particles whose match failed are ignored).  This is the parity seam for
+ * `guesses = np.random.multivariate_normal(scan_pose, scan_cov, 30)` (robot.py:81): the Python side draws
+ * with NumPy itself, from the matcher results of rbpf_get_match, so the run consumes the global RNG stream
+ * exactly like the reference and sees bit-identical samples. */
+int rbpf_weight_guesses(rbpf_handle h, const double *guesses);
 
 /* Replaces HybridMap.update (hybridmap.py:95-145) at every particle's current
  * pose, then the NaN-covariance weight fallback (robot.py:76-77) for particles
@@ -192,6 +198,13 @@ int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out_xy, int64_
  * reading handle must have the same configuration. */
 int rbpf_checkpoint_write(rbpf_handle h, const char *path);
 int rbpf_checkpoint_read(rbpf_handle h, const char *path);
+
+/* The same on the device: rbpf_snapshot copies the complete mutable state (pool, reference counts, page
+ * tables, poses, covariances, weights) into shadow buffers -- allocated on first use, doubling the handle's
+ * memory -- and rbpf_restore copies it back, both stream-ordered.  Lets a caller rewind the filter, e.g. to
+ * run the same scans twice (bench.py: device-resident loop and host-buffer loop on identical work). */
+int rbpf_snapshot(rbpf_handle h);
+int rbpf_restore(rbpf_handle h);
 
 /* Device-side errors are sticky and deferred: the kernels set a flag (pool exhausted -> RBPF_ERR_POOL, the
  * reference's resample assertion main.py:66-67 -> RBPF_ERR_RESAMPLE, internal bound -> RBPF_ERR_WORLD) and go

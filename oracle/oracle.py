@@ -80,6 +80,8 @@ def lib():
         L.orc_filter_motion.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, _dp]
         L.orc_filter_integrate.argtypes = [C.c_void_p]
         L.orc_filter_map_update.argtypes = [C.c_void_p, _dp]
+        L.orc_filter_map_update_guesses.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int]
+        L.orc_propose_pdf.argtypes = [_dp, _dp, _dp, C.c_int, _dp]
         L.orc_filter_resample.argtypes = [C.c_void_p, C.c_double, _ip]
         _LIB = L
     return _LIB
@@ -239,6 +241,15 @@ def propose(mean, cov, z):
     return g, prs
 
 
+def propose_numpy(mean, cov, K=30):
+    """robot.py:81 with NumPy itself -- `np.random.multivariate_normal(scan_pose, scan_cov, 30)` on the
+    global legacy stream -- and robot.py:87's densities for those samples (orc_propose_pdf)."""
+    g = np.ascontiguousarray(np.random.multivariate_normal(np.asarray(mean, dtype=np.float64), np.asarray(cov, dtype=np.float64), K))
+    prs = np.empty(K)
+    lib().orc_propose_pdf(_d(mean)[1], _d(np.asarray(cov).reshape(9))[1], _d(g)[1], K, _d(prs)[1])
+    return g, prs
+
+
 def moments(guesses, w):
     g, gp = _d(guesses)
     w, wp = _d(w)
@@ -328,10 +339,19 @@ class Filter:
     def integrate(self):
         lib().orc_filter_integrate(self._h)
 
-    def map_update(self, z, prev_xy=None):
+    def map_update(self, z, prev_xy=None, guesses=False):
+        """z: N*K*3 standard normals for the mean + chol(cov) z transform, or -- guesses=True -- the
+        proposal samples themselves, drawn by the caller like robot.py:81 (see propose_numpy)."""
         z, zp = _d(z)
         assert z.size == self.N * self.K * 3
-        if prev_xy is None:
+        if guesses:
+            if prev_xy is None:
+                lib().orc_filter_map_update_guesses(self._h, zp, None, None, 0)
+            else:
+                prev = np.ascontiguousarray(prev_xy, dtype=np.float64)
+                px, py = np.ascontiguousarray(prev[:, 0]), np.ascontiguousarray(prev[:, 1])
+                lib().orc_filter_map_update_guesses(self._h, zp, _d(px)[1], _d(py)[1], len(px))
+        elif prev_xy is None:
             lib().orc_filter_map_update(self._h, zp)
         else:
             prev = np.ascontiguousarray(prev_xy, dtype=np.float64)

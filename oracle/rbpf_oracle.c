@@ -411,6 +411,24 @@ void orc_propose(const double *mean, const double *cov, const double *z, int K,
     }
 }
 
+/* prs = N(guess; mean, cov) * 10 (robot.py:87) for samples the caller drew itself -- with
+ * np.random.multivariate_normal like the reference (robot.py:81). */
+void orc_propose_pdf(const double *mean, const double *cov, const double *guesses, int K, double *prs)
+{
+    double l[6];
+    chol3(cov, l);
+    double nrm = (2.0 * M_PI) * sqrt(2.0 * M_PI) * ((l[0] * l[3]) * l[5]);
+    for (int k = 0; k < K; k++) {
+        const double *g = guesses + 3 * k;
+        double d0 = g[0] - mean[0], d1 = g[1] - mean[1], d2 = g[2] - mean[2];
+        double y0 = d0 / l[0];
+        double y1 = (d1 - l[1] * y0) / l[3];
+        double y2 = ((d2 - l[2] * y0) - l[4] * y1) / l[5];
+        double maha = (y0 * y0 + y1 * y1) + y2 * y2;
+        prs[k] = rb_exp(-0.5 * maha) / nrm * 10.0;
+    }
+}
+
 /* Weight normalisation and weighted moments, robot.py:88-108.  Returns norm. */
 double orc_moments(const double *guesses, const double *w, int K, double *mean, double *sigma)
 {
@@ -1153,8 +1171,10 @@ void orc_filter_integrate(orc_filter *f)
 }
 
 /* One particle of Robot.map_update robot.py:59-115 (scan-to-map branch), z = K*3 normals. */
+/* z_is_guesses: z holds the K proposal samples themselves (drawn by the caller with NumPy, robot.py:81)
+ * instead of standard normals for our mean + chol(cov) z transform. */
 static void particle_map_update(orc_filter *f, int i, const double *z, const double *prev_x, const double *prev_y,
-                                int n_prev)
+                                int n_prev, int z_is_guesses)
 {
     double *pose = f->pose + 3 * i, *cov = f->cov + 9 * i;
     orc_map *m = f->map[i];
@@ -1173,7 +1193,12 @@ static void particle_map_update(orc_filter *f, int i, const double *z, const dou
     int K = f->K;
     double *g = (double *)malloc(sizeof(double) * (size_t)K * 5), *prs = g + 3 * K, *w = g + 4 * K;
     double mean[3], sigma[9];
-    orc_propose(mp, mc, z, K, g, prs);                                     /* :80-87 */
+    if (z_is_guesses) {                                                    /* :80-87 */
+        memcpy(g, z, sizeof(double) * 3 * (size_t)K);
+        orc_propose_pdf(mp, mc, g, K, prs);
+    } else {
+        orc_propose(mp, mc, z, K, g, prs);
+    }
     orc_sample_weight(m, g, K, f->px, f->py, f->dist, f->B, prs, w);       /* :88 */
     double norm = orc_moments(g, w, K, mean, sigma);                       /* :89-108 */
     for (int a = 0; a < 3; a++) pose[a] = mean[a];                         /* :109-113 */
@@ -1188,7 +1213,7 @@ static void particle_map_update(orc_filter *f, int i, const double *z, const dou
 void orc_filter_map_update(orc_filter *f, const double *z)
 {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, NULL, NULL, 0);
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, NULL, NULL, 0, 0);
 }
 
 /* [p.map_update(scan, last_scan, True) for p in particles] main.py:159 : every
@@ -1196,7 +1221,15 @@ void orc_filter_map_update(orc_filter *f, const double *z)
 void orc_filter_map_update_adj(orc_filter *f, const double *z, const double *prev_x, const double *prev_y, int n_prev)
 {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, prev_x, prev_y, n_prev);
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, z + (size_t)3 * f->K * i, prev_x, prev_y, n_prev, 0);
+}
+
+/* The same two calls with the proposal samples supplied (N*K*3, rows of particles whose match fails are
+ * ignored): the caller drew them with np.random.multivariate_normal from the matcher result, robot.py:81. */
+void orc_filter_map_update_guesses(orc_filter *f, const double *g, const double *prev_x, const double *prev_y, int n_prev)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < f->N; i++) particle_map_update(f, i, g + (size_t)3 * f->K * i, prev_x, prev_y, n_prev, 1);
 }
 
 /* particles = resample(particles) main.py:160 with Robot.copy robot.py:141-149. */

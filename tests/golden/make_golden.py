@@ -153,30 +153,16 @@ r._cov = np.diag([1e-4, 1e-4, 1e-6])
 G["upd_prior_cov"] = np.array(r._cov)
 G["upd_match_corr"] = m_corr
 G["upd_match_cov"] = m_cov
-z = rng.standard_normal((30, 3))
-G["upd_z"] = z
-
-# The reference draws with np.random.multivariate_normal (robot.py:81); our declared
-# sampling transform is mean + chol(cov) z, injected here so the rest runs verbatim.
-Lc = np.linalg.cholesky(m_cov)
-injected = {}
-
-
-def fake_mvn(mean, cov, K):
-    # must equal oracle.propose(); recomputed in the test from upd_z
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-
-    gs, _ = O.propose(np.array(mean, dtype=np.float64), np.array(cov, dtype=np.float64), z)
-    injected["g"] = gs
-    return gs
-
-
-_orig = np.random.multivariate_normal
-np.random.multivariate_normal = fake_mvn
+# The reference draws its proposal samples with np.random.multivariate_normal on the global legacy stream
+# (robot.py:81).  Nothing is patched: the stream is seeded, Robot.map_update runs as it is, and the samples
+# it drew are reproduced afterwards by seeding again and making the same call.
+UPD_SEED = 20261018
+G["upd_seed"] = np.int64(UPD_SEED)
+np.random.seed(UPD_SEED)
 r.map_update(LD[4], None, False)
-np.random.multivariate_normal = _orig
-G["upd_guesses"] = injected["g"]
+upd_mean = [m_corr[0] + 0.6, m_corr[1] + 0.15, m_corr[2] + 0.1]          # hybridmap.py:253-255
+np.random.seed(UPD_SEED)
+G["upd_guesses"] = np.array(np.random.multivariate_normal(upd_mean, np.array(m_cov.tolist()), 30))
 G["upd_curr"] = eng.curr                     # valid_curr_points, hybridmap.py:240
 G["upd_ref"] = eng.ref                       # valid_ref_points,  hybridmap.py:239
 G["upd_prange"] = eng.prange
@@ -233,15 +219,14 @@ for n, scale, shift in ((8, 50.0, 0.0), (64, 1e3, -500.0), (257, 1e6, -9e5), (10
     w = rng.normal(0, 1, n) * scale + shift
     if n == 64:
         w[5] = -np.inf
-    u = float(rng.random())
+    seed = int(rng.integers(1, 2 ** 31))
+    u = float(np.random.RandomState(seed).random_sample())          # what main.py:59 will draw
     ps = [W(np.float64(x)) for x in w]
     for i, p in enumerate(ps):
         p.tag = i
-    _r = np.random.random
-    np.random.random = lambda: u
+    np.random.seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         out = refmain.resample(ps)
-    np.random.random = _r
     anc = np.array([p.tag for p in out], dtype=np.int32)
     did = len(out[0]._weight) == 2
     cases.append((w, u, anc, did))

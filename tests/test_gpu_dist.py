@@ -84,3 +84,49 @@ def test_two_rank_emulation_equals_single_set(mods, golden, transport, world):
     for ps in ranks:
         st = ps.stats()
         assert st["pool_in_use"] <= st["total_refs"]
+
+
+def test_sharded_drop_in_api_world_of_one(mods, tmp_path):
+    """`new_filter(sharded=True)` + `[Robot(eng) ...]` + the headless loop + `resample` under a real
+    (one-rank) NCCL process group: the sharded path of the drop-in API -- all-gathered poses for
+    particle 0's gate, global resample -- gives the same result as the plain single set.
+    (profiles/ holds the multi-rank runs of thesis_b200.dist.dist_parity_check.)"""
+    torch, D, P = mods
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        r = D.dist_parity_check(particles_per_rank=96, n_beams=360, frames=6, device=0, tmp_dir=str(tmp_path))
+        assert r["identical"] and r["ranks"] == 1 and r["particles"] == 96 and r["migrated"] == 0
+        with pytest.raises(P.RbpfError):
+            P.new_filter(rng="numpy", sharded=True)                # host draws cannot be sharded
+    finally:
+        dist.destroy_process_group()
+
+
+def test_snapshot_restore_rewinds_the_filter(mods, golden):
+    """rbpf_snapshot / rbpf_restore: the same scans from the same snapshot give the same particles
+    (device draws are keyed by the step counter, which is restored too)."""
+    torch, D, P = mods
+    ps = P.ParticleSet(64, 180, pool_subtiles=6000, seed=9)
+    r, a = golden["intel_ranges"], golden["intel_angles"]
+    ps.set_scan(r[0], a); ps.integrate(); ps.integrate()
+    par = (0.002, 0.05, 0.01 * np.pi / 180, 0.05)
+    for s in range(1, 4):
+        ps.motion(1, (0.05, 0.0, -0.3), 1.0, par); ps.step(r[s], a)
+    ps.snapshot()
+
+    def run():
+        for s in range(4, 9):
+            ps.motion(1, (0.05, 0.0, -0.3), 1.0, par); ps.step(r[s], a)
+        ps.synchronize()
+        return ps.poses.copy(), ps.weights.copy(), ps.export_tile(5, 0, 0).copy(), ps.stats()
+
+    p1, w1, t1, s1 = run()
+    ps.restore()
+    p2, w2, t2, s2 = run()
+    assert np.array_equal(p1, p2) and np.array_equal(w1, w2) and np.array_equal(t1, t2)
+    assert s1["pool_in_use"] == s2["pool_in_use"] and s2["refcount_sum"] == s2["total_refs"]

@@ -83,8 +83,8 @@ def test_motion_families(PS, golden, name, family, par):
     pose, cov = ps.poses, ps.covs
     op, oc = O.motion(family, golden["mot_%s_u" % name], dt, par, golden["mot_pose0"], golden["mot_cov0"])
     for i in range(5):
-        assert np.allclose(pose[i], op, rtol=0, atol=1e-13)          # CUDA cos/sin vs glibc (unicycle only)
-        assert np.allclose(cov[i], oc, rtol=1e-12, atol=1e-20)
+        assert np.array_equal(pose[i], op)                           # same sin / cos on both sides (rb_math.h)
+        assert np.array_equal(cov[i], oc)
         assert np.allclose(pose[i], golden["mot_%s_pose" % name], rtol=0, atol=1e-13)
         assert np.allclose(cov[i], golden["mot_%s_cov" % name], rtol=1e-12, atol=1e-18)
 
@@ -179,7 +179,8 @@ def seeded(PS, G, N, pool=400):
 
 
 def test_weight_stage_against_reference_map_update(PS, golden):
-    """robot.py:73-115 with the matcher answer injected at the MATLAB seam."""
+    """robot.py:73-115 with the matcher answer injected at the MATLAB seam; the proposal samples are the
+    ones the unmodified reference drew with np.random.multivariate_normal (robot.py:81)."""
     N = 4
     ps, m = seeded(PS, golden, N)
     assert_map_equal(ps, 0, m, "seed")
@@ -188,8 +189,10 @@ def test_weight_stage_against_reference_map_update(PS, golden):
     ps.covs = golden["upd_prior_cov"]
     ps.set_scan(*scan_of(golden, 4))
     ps.set_match(pose0 + golden["upd_match_corr"], golden["upd_match_cov"], 1)
-    z = np.tile(golden["upd_z"][None], (N, 1, 1))
-    ps.weight(z)
+    np.random.seed(int(golden["upd_seed"]))                  # the same NumPy call on the same stream reproduces them
+    assert np.array_equal(np.random.multivariate_normal(pose0 + golden["upd_match_corr"], golden["upd_match_cov"], 30),
+                          golden["upd_guesses"])
+    ps.weight_guesses(np.tile(golden["upd_guesses"][None], (N, 1, 1)))
     ps.integrate(fallback_weights=True)
     pose, cov, w = ps.poses, ps.covs, ps.weights
     for i in range(N):
@@ -246,9 +249,9 @@ def test_weight_stage_random_matches_vs_oracle(PS, golden):
         g, prs = O.propose(mposes[i], mcovs[i], z[i])
         ww = m.sample_weight(g, s, prs)
         op, oc, norm = O.moments(g, ww)
-        assert np.allclose(pose[i], op, rtol=0, atol=POSE_ATOL)
-        assert np.allclose(cov[i], oc, rtol=1e-7, atol=1e-18)       # cancellation in sum w (g - mean)^2
-        assert np.isclose(w[i], norm + w0[i], rtol=REL_TOL)
+        assert np.array_equal(pose[i], op)                           # bit for bit: same exp / sin / cos, same order
+        assert np.array_equal(cov[i], oc)
+        assert w[i] == norm + w0[i]
 
 
 # ----------------------------------------------------------------- matcher --
@@ -559,12 +562,12 @@ def test_filter_steps_against_oracle(PS, golden):
         f.map_update(z)
         res = ps.match_result()
         assert np.array_equal(res["valid"], f.valid.astype(bool)), "step %d" % step
-        assert np.allclose(ps.weights, f.weight, rtol=1e-9), "step %d" % step
+        assert np.array_equal(ps.weights, f.weight), "step %d" % step
         did, anc = ps.resample(u01)
         odid, oanc = f.resample(u01)
         assert did == odid and np.array_equal(anc, oanc), "step %d" % step
-        assert np.allclose(ps.poses, f.pose, rtol=0, atol=1e-9), "step %d" % step
-        assert np.allclose(ps.covs, f.cov, rtol=1e-6, atol=1e-16), "step %d" % step
+        assert np.array_equal(ps.poses, f.pose), "step %d" % step
+        assert np.array_equal(ps.covs, f.cov), "step %d" % step
     for i in range(N):
         assert_map_equal(ps, i, f.map(i), "final %d" % i)
 

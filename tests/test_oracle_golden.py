@@ -112,7 +112,8 @@ def test_full_map_update(golden):
     rx, ry = O.pose_range(golden["upd_prior_cov"])
     assert np.allclose([rx, ry], golden["upd_prange"][:2], rtol=0, atol=0)
     mean = np.array([0.6, 0.15, 0.1]) + golden["upd_match_corr"]
-    g, prs = O.propose(mean, golden["upd_match_cov"], golden["upd_z"])
+    np.random.seed(int(golden["upd_seed"]))                  # robot.py:81 with NumPy itself, same stream as the reference run
+    g, prs = O.propose_numpy(mean, golden["upd_match_cov"], 30)
     assert np.array_equal(g, golden["upd_guesses"])
     w = m.sample_weight(g, s, prs)
     pose, cov, norm = O.moments(g, w)
@@ -127,8 +128,13 @@ def test_pdf_against_scipy(golden):
     import scipy.stats
 
     mean = np.array([0.62, 0.12, 0.11])
-    g, prs = O.propose(mean, golden["upd_match_cov"], golden["upd_z"])
+    z = np.random.default_rng(5).standard_normal((30, 3))
+    g, prs = O.propose(mean, golden["upd_match_cov"], z)
     ref = scipy.stats.multivariate_normal.pdf(g, mean, golden["upd_match_cov"]) * 10   # robot.py:87
+    assert np.allclose(prs, ref, rtol=1e-12)
+    np.random.seed(3)
+    g, prs = O.propose_numpy(mean, golden["upd_match_cov"], 30)
+    ref = scipy.stats.multivariate_normal.pdf(g, mean, golden["upd_match_cov"]) * 10
     assert np.allclose(prs, ref, rtol=1e-12)
 
 

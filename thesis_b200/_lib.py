@@ -56,6 +56,7 @@ SIGNATURES = {
     "rbpf_scan_match": (C.c_int, [_H]),
     "rbpf_scan_match_adj": (C.c_int, [_H, _dp, C.c_int32]),
     "rbpf_weight": (C.c_int, [_H, _dp]),
+    "rbpf_weight_guesses": (C.c_int, [_H, _dp]),
     "rbpf_integrate": (C.c_int, [_H, C.c_int32]),
     "rbpf_resample": (C.c_int, [_H, _dp, _ip, _ip]),
     "rbpf_step": (C.c_int, [_H, _dp, _dp, C.c_int32]),
@@ -79,6 +80,8 @@ SIGNATURES = {
     "rbpf_checkpoint_write": (C.c_int, [_H, C.c_char_p]),
     "rbpf_checkpoint_read": (C.c_int, [_H, C.c_char_p]),
     "rbpf_clear_errors": (C.c_int, [_H]),
+    "rbpf_snapshot": (C.c_int, [_H]),
+    "rbpf_restore": (C.c_int, [_H]),
     "rbpf_stats": (C.c_int, [_H, C.POINTER(RbpfStats)]),
     "rbpf_match_phase_clocks": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "rbpf_synchronize": (C.c_int, [_H]),

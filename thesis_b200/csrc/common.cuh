@@ -249,7 +249,7 @@ __device__ __forceinline__ double rb_u01(uint32_t hi, uint32_t lo)   // (0,1), 5
 void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, const double *par, cudaStream_t s);
 void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s);
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, int adj, cudaStream_t s);
-void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s);
+void rb_launch_weight(const RbCtx &c, const double *z_dev, const double *guesses_dev, int fallback_phase, cudaStream_t s);
 void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);
 void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s);
 void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s);

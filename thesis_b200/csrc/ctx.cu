@@ -53,6 +53,11 @@ struct rbpf_ctx {
     int flag_pending[2] = {0, 0};
     int last_adj = 0;              // mode of the last match (rbpf_get_match_slice re-runs it)
     void *ckpt_host = nullptr;     // pinned bounce buffer of the checkpoint calls, allocated on first use
+    // device-side snapshot (rbpf_snapshot / rbpf_restore): shadow copies of every mutable buffer
+    struct Snap { void *live, *shadow; size_t bytes; };
+    std::vector<Snap> snap;
+    int snap_parity = 0, snap_use_dup = 0, snap_valid = 0;
+    unsigned long long snap_step_no = 0;
 };
 
 #define RB_NSTAGES 8               // set_scan, match, weight, raycast_prepare, raycast_cast, weight_fallback, resample_plan, resample_apply
@@ -132,6 +137,7 @@ extern "C" int rbpf_destroy(rbpf_handle h)
         if (pm.attached && pm.ipc)
             for (void *b : pm.base) cudaIpcCloseMemHandle(b);
     for (void *p : h->allocs) cudaFree(p);
+    for (auto &s2 : h->snap) cudaFree(s2.shadow);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) cudaEventDestroy(h->stage_ev[i]);
     if (h->h_scan) cudaFreeHost(h->h_scan);
@@ -382,7 +388,18 @@ extern "C" int rbpf_weight(rbpf_handle h, const double *z)
         CK(cudaMemcpyAsync(h->d_z, z, (size_t)h->d.N * h->d.K * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         zd = h->d_z;
     }
-    rb_launch_weight(h->d, zd, 0, h->stream);
+    rb_launch_weight(h->d, zd, nullptr, 0, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_weight_guesses(rbpf_handle h, const double *guesses)
+{
+    if (h) h->d.use_dup = 0;
+    if (!h || !h->have_scan || !guesses) { if (h) h->err = "weight_guesses: no scan set or no samples"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->d_z, guesses, (size_t)h->d.N * h->d.K * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rb_launch_weight(h->d, nullptr, h->d_z, 0, h->stream);
     CK(cudaGetLastError());
     return RBPF_OK;
 }
@@ -394,7 +411,7 @@ extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
     CK(cudaSetDevice(h->cfg.device));
     rb_launch_raycast_prepare(h->d, h->stream);
     rb_launch_raycast_cast(h->d, h->stream);
-    if (fallback_weights) rb_launch_weight(h->d, nullptr, 1, h->stream);
+    if (fallback_weights) rb_launch_weight(h->d, nullptr, nullptr, 1, h->stream);
     CK(cudaGetLastError());
     return RBPF_OK;
 }
@@ -475,13 +492,13 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     h->last_adj = 0;
     MARK(2);
     h->d.use_dup = 0;
-    rb_launch_weight(h->d, nullptr, 0, h->stream);
+    rb_launch_weight(h->d, nullptr, nullptr, 0, h->stream);
     MARK(3);
     rb_launch_raycast_prepare(h->d, h->stream);
     MARK(4);
     rb_launch_raycast_cast(h->d, h->stream);
     MARK(5);
-    rb_launch_weight(h->d, nullptr, 1, h->stream);
+    rb_launch_weight(h->d, nullptr, nullptr, 1, h->stream);
     MARK(6);
     rb_launch_resample(h->d, h->d.weight, nullptr, h->stream);
     MARK(7);
@@ -898,6 +915,62 @@ extern "C" int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out
     if (dev) cudaFree(dev);
     if (e != cudaSuccess) { h->err = std::string("occupied_points: ") + cudaGetErrorString(e); return RBPF_ERR_CUDA; }
     *n = (int64_t)cnt;
+    return RBPF_OK;
+}
+
+// ---- device-side snapshot -----------------------------------------------------------
+// The whole mutable state copied device-to-device into shadow buffers (allocated on first use: it
+// doubles the handle's memory), and back.  bench.py uses it to time the device-resident loop and the
+// host-buffer loop on the SAME scans; it is also the cheap way to branch a filter.
+extern "C" int rbpf_snapshot(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    RbCtx &d = h->d;
+    const size_t N = d.N;
+    if (h->snap.empty()) {
+        // double-buffered arrays by their physical allocation (h->phys), so that a restore is independent of the parity
+        const std::pair<void *, size_t> bufs[] = {
+            {h->phys[0], (size_t)d.pool_tiles * RB_SUB_BYTES}, {d.refcnt, sizeof(uint32_t) * d.pool_tiles},
+            {d.free_list, sizeof(uint32_t) * d.pool_tiles}, {d.free_count, sizeof(int) * 4},
+            {h->phys[1], sizeof(uint32_t) * N * d.nsub}, {h->phys[2], sizeof(uint32_t) * N * d.nsub},
+            {h->phys[3], sizeof(double) * 3 * N}, {h->phys[4], sizeof(double) * 3 * N},
+            {h->phys[5], sizeof(double) * 9 * N}, {h->phys[6], sizeof(double) * 9 * N},
+            {h->phys[7], sizeof(unsigned long long) * N}, {h->phys[8], sizeof(unsigned long long) * N},
+            {d.weight, sizeof(double) * N}, {d.dup_of, sizeof(int) * N}, {d.ancestors, sizeof(int) * (size_t)d.n_global},
+            {d.stats, sizeof(RbStats)}, {d.flags, sizeof(RbFlags)},
+        };
+        for (const auto &b : bufs) {
+            void *sh = nullptr;
+            cudaError_t e = cudaMalloc(&sh, b.second ? b.second : 16);
+            if (e != cudaSuccess) {
+                for (auto &s2 : h->snap) cudaFree(s2.shadow);
+                h->snap.clear();
+                h->err = std::string("snapshot: cudaMalloc: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                return RBPF_ERR_CUDA;
+            }
+            h->snap.push_back({b.first, sh, b.second});
+        }
+    }
+    for (const auto &s2 : h->snap) CK(cudaMemcpyAsync(s2.shadow, s2.live, s2.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    h->snap_parity = h->parity;
+    h->snap_use_dup = d.use_dup;
+    h->snap_step_no = d.step_no;
+    h->snap_valid = 1;
+    return RBPF_OK;
+}
+
+extern "C" int rbpf_restore(rbpf_handle h)
+{
+    if (!h) return RBPF_ERR_ARG;
+    if (!h->snap_valid) { h->err = "restore: no snapshot"; return RBPF_ERR_ARG; }
+    CK(cudaSetDevice(h->cfg.device));
+    for (const auto &s2 : h->snap) CK(cudaMemcpyAsync(s2.live, s2.shadow, s2.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->parity != h->snap_parity) swap_buffers(h);
+    h->d.use_dup = h->snap_use_dup;
+    h->d.step_no = h->snap_step_no;
+    h->flag_pending[0] = h->flag_pending[1] = 0;
     return RBPF_OK;
 }
 

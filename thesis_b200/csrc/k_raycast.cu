@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
                 if (told == RB_NONE) action = 1;
                 else if (atomicAdd(&c.refcnt[told], 0u) > 1u) {
                     uint32_t old = atomicSub(&c.refcnt[told], 1u);
-                    if (old == 1u) atomicExch(&c.refcnt[told], 1u);   // last holder: keep it
+                    if (old == 1u) atomicAdd(&c.refcnt[told], 1u);    // last holder: keep it (an add, not a store: a sharer that
+                                                                      // ran out of pool may be putting its own reference back)
                     else action = 2;
                 }
                 if (action) {

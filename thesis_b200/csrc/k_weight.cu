@@ -27,7 +27,11 @@
 #ifndef WT_MINBLOCKS
 #define WT_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbCtx c, const double *__restrict__ z, int fallback_phase)
+// z: N*K*3 standard normals (our transform mean + chol(cov) z), or guesses: N*K*3 proposal samples drawn by
+// the caller exactly as the reference draws them (np.random.multivariate_normal, robot.py:81), or neither
+// (Philox normals on the device).
+__global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbCtx c, const double *__restrict__ z,
+                                                                             const double *__restrict__ guesses, int fallback_phase)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * WT_WARPS + warp;
@@ -70,8 +74,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
 
     double g0 = m0, g1 = m1, g2 = m2, w = 0.0;
     if (lane < K) {
-        double z0, z1, z2;
-        if (z) {
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+        if (guesses) {
+        } else if (z) {
             const double *zz = z + ((size_t)p * K + lane) * 3;
             z0 = zz[0]; z1 = zz[1]; z2 = zz[2];
         } else {
@@ -86,9 +91,14 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
             z1 = ra * sin(TWO_PI * u2);
             z2 = rb2 * cos(TWO_PI * u4);
         }
-        g0 = m0 + l00 * z0;
-        g1 = m1 + (l10 * z0 + l11 * z1);
-        g2 = m2 + ((l20 * z0 + l21 * z1) + l22 * z2);
+        if (guesses) {
+            const double *gg = guesses + ((size_t)p * K + lane) * 3;
+            g0 = gg[0]; g1 = gg[1]; g2 = gg[2];
+        } else {
+            g0 = m0 + l00 * z0;
+            g1 = m1 + (l10 * z0 + l11 * z1);
+            g2 = m2 + ((l20 * z0 + l21 * z1) + l22 * z2);
+        }
         double d0 = g0 - m0, d1 = g1 - m1, d2 = g2 - m2;
         double y0 = d0 / l00;
         double y1 = (d1 - l10 * y0) / l11;
@@ -160,8 +170,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
     }
 }
 
-void rb_launch_weight(const RbCtx &c, const double *z_dev, int fallback_phase, cudaStream_t s)
+void rb_launch_weight(const RbCtx &c, const double *z_dev, const double *guesses_dev, int fallback_phase, cudaStream_t s)
 {
     int blocks = (c.N + WT_WARPS - 1) / WT_WARPS;
-    weight_kernel<<<blocks, WT_WARPS * 32, 0, s>>>(c, z_dev, fallback_phase);
+    weight_kernel<<<blocks, WT_WARPS * 32, 0, s>>>(c, z_dev, guesses_dev, fallback_phase);
 }

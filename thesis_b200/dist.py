@@ -382,3 +382,76 @@ class ShardedParticleSet(MigratingSet):
         if self._tev is not None:
             self._tev = []
         return out, n
+
+
+def dist_parity_check(particles_per_rank=1024, n_beams=360, frames=8, device=0, seed=5, tmp_dir=None):
+    """configs[3] in small: a Freiburg-shaped CARMEN log (360 beams; the real fr.log is missing from the
+    reference tree, so thesis_b200.synth writes a stand-in), `particles_per_rank` particles on every rank,
+    driven through the drop-in API -- `[Robot(eng) ...]`, the headless main.py loop, `resample` -- once
+    sharded over all ranks of the job (NCCL all-gather of the weights, NVLink migration) and once as a
+    single set on this rank's GPU.  Every rank compares its slice: poses, covariances, weights and the
+    maps of a few of its particles must be identical bit for bit.  Collective: call on every rank.
+    Returns {ranks, particles, particles_per_rank, frames, migrated, identical}."""
+    import tempfile
+
+    import torch
+    import torch.distributed as dist
+
+    from . import harness, loaders, particles as P, sensors, synth
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = particles_per_rank * world
+    dev = torch.device("cuda", device)
+    own_tmp = None
+    if tmp_dir is None:
+        own_tmp = tempfile.TemporaryDirectory(prefix="rbpf_parity_r%d_" % rank)
+        tmp_dir = own_tmp.name
+    w = synth.Workload(frames + 1, n_beams=n_beams)                 # every rank writes its own copy of the same log
+    synth.write_carmen_log(os.path.join(tmp_dir, "fr.txt"), w)
+    synth.write_carmen_log(os.path.join(tmp_dir, "fr.log"), w)
+
+    def run(sharded):
+        ld = sensors.Lidar(loaders.FreidLidarData(tmp_dir))
+        im = sensors.IMU(loaders.FreidIMUData(tmp_dir))
+        sh = P.new_filter(rng="device", keep_history=False, sharded=sharded, device=device, seed=seed, world_tiles=(5, 5),
+                          pool_subtiles=40 * (particles_per_rank if sharded else n) + 4096)
+        parts = [P.Robot("eng") for _ in range(n)]                   # main.py:87 on every rank
+        migrated = 0
+
+        def resample(ps):
+            nonlocal migrated
+            out = P.resample(ps)
+            anc = ps[0]._shared.last_ancestors
+            if sharded:
+                lo = rank * particles_per_rank
+                mine = anc[lo:lo + particles_per_rank] // particles_per_rank
+                migrated += int(np.count_nonzero(mine != rank))
+            return out
+
+        harness.run_log(parts, ld, im, resample, seed_fn=P.seed_map, max_frames=frames)
+        sh.ps.synchronize()
+        return sh, migrated
+
+    sh_a, migrated = run(True)
+    sh_b, _ = run(False)
+    a, b = sh_a.ps, sh_b.ps
+    lo, hi = rank * particles_per_rank, (rank + 1) * particles_per_rank
+    same = (np.array_equal(a.poses, b.poses[lo:hi]) and np.array_equal(a.covs, b.covs[lo:hi]) and
+            np.array_equal(a.weights, b.weights[lo:hi]))
+    for j in (0, particles_per_rank // 2, particles_per_rank - 1):
+        same = same and sorted(a.list_tiles(j)) == sorted(b.list_tiles(lo + j))
+        for c in a.list_tiles(j):
+            same = same and bool(np.array_equal(a.export_tile(j, *c), b.export_tile(lo + j, *c)))
+    t = torch.tensor([1 if same else 0, -migrated], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ok = bool(int(t[0]))
+    t2 = torch.tensor([migrated], dtype=torch.int64, device=dev)
+    dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+    a.close()
+    b.close()
+    P._DEFAULT_SET = None
+    if own_tmp is not None:
+        own_tmp.cleanup()
+    return {"ranks": world, "particles": n, "particles_per_rank": particles_per_rank, "beams": n_beams, "frames": frames,
+            "log": "synthetic CARMEN log through FreidLidarData / FreidIMUData, drop-in Robot / resample API",
+            "migrated": int(t2[0]), "identical": ok, "transport": a.transport}

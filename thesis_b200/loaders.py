@@ -97,8 +97,22 @@ class Freid101LidarData(_CarmenLidar):
     FILE, BEAMS = "fr101.log", 360
 
 
-class OberoLidarData(_CarmenLidar):          # the committed orebro.log has 181 beams; the reference asks for 360
+class OberoLidarData(_CarmenLidar):
+    """OberoLidarData.py:8,16 asks for 360 readings per FLASER record, but the committed data/orebro.log
+    holds 181 (a 180-degree SICK at 1 degree): the reference's loader runs into the record's trailing
+    fields and dies on float('pippo').  Every FLASER record of that file is stamped 0 and the ODOM
+    stamps are not times either, so the reference's np.unique would keep one sweep.  Declared
+    deviations: the beam count is the one the record states and records are ordered by line number,
+    0.1 s apart (like the CSAIL loader)."""
     FILE, BEAMS = "orebro.log", 360
+
+    def load_and_format(self):
+        rows = _carmen_rows(os.path.join(self._dir, self.FILE), "FLASER", with_lineno=True)
+        self.BEAMS = int(rows[0][1])
+        scans = np.array([[float(v) for v in r[2:self.BEAMS + 2]] for r in rows])
+        times = np.array([int(r[-1]) * 1000 for r in rows])
+        angles = np.array([-pi / 2 + i * pi / (self.BEAMS - 1) for i in range(self.BEAMS)])
+        return times, scans, angles
 
 
 class BeleLidarData(_CarmenLidar):
@@ -244,7 +258,6 @@ AcesIMUData = _velocity_loader("AcesIMUData", "aces.txt", calib=1)
 FreidIMUData = _velocity_loader("FreidIMUData", "fr.log", flip_x=True)
 FreidCorrectIMUData = _velocity_loader("FreidCorrectIMUData", "fr_correct.log", flip_x=True)
 Freid101IMUData = _velocity_loader("Freid101IMUData", "fr101.log")
-OberoIMUData = _velocity_loader("OberoIMUData", "orebro.log")
 BeleIMUData = _velocity_loader("BeleIMUData", "bele.log", rel_time=True)
 
 
@@ -264,6 +277,16 @@ class CsailIMUData(_VelocityIMU):
     @staticmethod
     def get_cov_input_uncertainty(prev_pose, reading):
         return CsailIMUData._noise(reading)
+
+
+class OberoIMUData(CsailIMUData):
+    """Odometry of data/orebro.log (OberoIMUData.py): its ODOM stamps are not times (6.979, 1.961,
+    3.4e-86, ...), so records are ordered by line number like OberoLidarData (declared)."""
+    FILE = "orebro.log"
+
+    @staticmethod
+    def get_cov_input_uncertainty(prev_pose, reading):
+        return OberoIMUData._noise(reading)
 
 
 class DefaultIMUData(IMUData):

@@ -73,6 +73,14 @@ class ParticleSet:
     def synchronize(self):
         self._ck(self._lib.rbpf_synchronize(self._h))
 
+    def snapshot(self):
+        """Copy the whole mutable state into device-side shadow buffers (doubles the memory on first use)."""
+        self._ck(self._lib.rbpf_snapshot(self._h))
+
+    def restore(self):
+        """Rewind to the last snapshot()."""
+        self._ck(self._lib.rbpf_restore(self._h))
+
     def clear_errors(self):
         """Reset the sticky device-side error flags (pool exhausted, resample assertion, internal bound)."""
         self._ck(self._lib.rbpf_clear_errors(self._h))
@@ -106,6 +114,13 @@ class ParticleSet:
             if z.size != self.N * self.K * 3:
                 raise ValueError("z must hold N*K*3 standard normals")
             self._ck(self._lib.rbpf_weight(self._h, zp))
+
+    def weight_guesses(self, guesses):
+        """Weight stage on caller-drawn proposal samples [N, K, 3] (robot.py:81 drawn with NumPy itself)."""
+        g, gp = _d(guesses)
+        if g.size != self.N * self.K * 3:
+            raise ValueError("guesses must hold N*K*3 values")
+        self._ck(self._lib.rbpf_weight_guesses(self._h, gp))
 
     def integrate(self, fallback_weights=False):
         self._ck(self._lib.rbpf_integrate(self._h, 1 if fallback_weights else 0))
@@ -271,12 +286,26 @@ class ParticleSet:
 class _SharedSet:
     """State shared by all Robot views of one filter."""
 
-    def __init__(self, rng="numpy", keep_history=True, **set_kwargs):
+    def __init__(self, rng="numpy", keep_history=True, sharded=False, group=None, **set_kwargs):
         self.views = []
         self.ps = None
         self.rng = rng                    # "numpy": draws from np.random like the reference; "device": Philox
         self.keep_history = keep_history
         self.set_kwargs = set_kwargs
+        # sharded: one process per GPU (torch.distributed, NCCL); every rank builds the SAME list of
+        # Robot views -- main.py:87 unchanged -- and owns the slice [rank * n, (rank + 1) * n) of it
+        self.sharded = bool(sharded)
+        self.group = group
+        self.rank, self.world, self.n_local = 0, 1, None
+        if self.sharded:
+            if rng != "device" or keep_history:
+                raise RbpfError("a sharded filter draws on the device and keeps no per-view histories: "
+                                "new_filter(rng='device', keep_history=False, sharded=True)")
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RbpfError("sharded=True needs an initialised torch.distributed process group (torchrun)")
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.motion_rounds = 0
         self.update_rounds = 0
         self._poses = None                # host cache of poses / weights, refreshed lazily
@@ -288,25 +317,59 @@ class _SharedSet:
         if self.ps is None:
             kw = dict(self.set_kwargs)
             kw.setdefault("n_beams", n_beams)
-            self.ps = ParticleSet(len(self.views), **kw)
+            if self.sharded:
+                from .dist import ShardedParticleSet
+
+                if len(self.views) % self.world:
+                    raise RbpfError("%d particles do not divide over %d ranks" % (len(self.views), self.world))
+                self.n_local = len(self.views) // self.world
+                nb = kw.pop("n_beams")
+                self.ps = ShardedParticleSet(self.n_local, nb, group=self.group, **kw)
+            else:
+                self.n_local = len(self.views)
+                self.ps = ParticleSet(len(self.views), **kw)
         return self.ps
 
     def invalidate(self):
         self._poses = self._weights = self._covs = None
 
+    def _global(self, local):
+        """Sharded: all-gather a per-particle array so that every rank sees every particle (main.py reads
+        particle 0's pose on every frame, main.py:152-155,168).  A collective: every rank runs the same
+        loop and therefore asks at the same point."""
+        if not self.sharded:
+            return local
+        import torch
+        import torch.distributed as dist
+
+        ps = self.ps
+        mine = torch.as_tensor(np.ascontiguousarray(local)).to(ps._dev)
+        out = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=ps._dev)
+        with torch.cuda.stream(torch.cuda.default_stream(ps._dev)):
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.reshape((-1,) + tuple(mine.shape[1:])).cpu().numpy()
+
+    def is_local(self, slot):
+        return not self.sharded or self.n_local is None or self.rank * self.n_local <= slot < (self.rank + 1) * self.n_local
+
+    def local_slot(self, slot):
+        if not self.is_local(slot):
+            raise RbpfError("particle %d lives on rank %d" % (slot, slot // self.n_local))
+        return slot - self.rank * self.n_local if self.sharded else slot
+
     def poses(self):
         if self._poses is None:
-            self._poses = self.materialise().poses
+            self._poses = self._global(self.materialise().poses)
         return self._poses
 
     def weights(self):
         if self._weights is None:
-            self._weights = self.materialise().weights
+            self._weights = self._global(self.materialise().weights)
         return self._weights
 
     def covs(self):
         if self._covs is None:
-            self._covs = self.materialise().covs
+            self._covs = self._global(self.materialise().covs)
         return self._covs
 
     def record_history(self):
@@ -324,11 +387,17 @@ class _SharedSet:
 _DEFAULT_SET = None
 
 
-def new_filter(rng="numpy", keep_history=True, **set_kwargs):
+def new_filter(rng="numpy", keep_history=True, sharded=False, group=None, **set_kwargs):
     """Start a new particle set; the Robot(...) constructions that follow join it.
-    set_kwargs go to ParticleSet (world_tiles, pool_subtiles, device, seed, ...)."""
+    set_kwargs go to ParticleSet (world_tiles, pool_subtiles, device, seed, ...).
+
+    sharded=True (under torchrun, one process per GPU, after torch.distributed.init_process_group("nccl")):
+    the same `particles = [Robot(eng) for _ in range(NUM_PARTICLES)]` on every rank, but each rank's GPU
+    holds NUM_PARTICLES / world of them (thesis_b200.dist.ShardedParticleSet); `resample(particles)` is
+    the global systematic resample with NVLink migration.  Every rank sees every particle's pose and
+    weight (all-gathered on demand), maps only of its own particles."""
     global _DEFAULT_SET
-    _DEFAULT_SET = _SharedSet(rng=rng, keep_history=keep_history, **set_kwargs)
+    _DEFAULT_SET = _SharedSet(rng=rng, keep_history=keep_history, sharded=sharded, group=group, **set_kwargs)
     return _DEFAULT_SET
 
 
@@ -342,13 +411,15 @@ class _MapView:
         self._map_len_m = 40
 
     def _tiles(self):
-        ps = self._robot._shared.materialise()
-        return {c: ps.export_tile(self._robot._slot, c[0], c[1]) for c in ps.list_tiles(self._robot._slot)}
+        sh = self._robot._shared
+        ps, j = sh.materialise(), sh.local_slot(self._robot._slot)
+        return {c: ps.export_tile(j, c[0], c[1]) for c in ps.list_tiles(j)}
 
     def get_occupied_points(self):
         """Cell coordinates of cells with log-odds > 1.0 (hybridmap.py:303-313), thresholded and
         compacted on the device (the reference's O(tiles * 800^2) Python loop dominates its frame time)."""
-        pts = self._robot._shared.materialise().occupied_points(self._robot._slot)
+        sh = self._robot._shared
+        pts = sh.materialise().occupied_points(sh.local_slot(self._robot._slot))
         return list(pts[:, 0]), list(pts[:, 1])
 
     def get_odds_at(self, pos):
@@ -365,7 +436,8 @@ class _MapView:
         return o / (1 + o)
 
     def __str__(self):
-        return "Hybrid Map: %d maps" % len(self._robot._shared.materialise().list_tiles(self._robot._slot))
+        sh = self._robot._shared
+        return "Hybrid Map: %d maps" % len(sh.materialise().list_tiles(sh.local_slot(self._robot._slot)))
 
 
 class Robot:
@@ -451,11 +523,14 @@ class Robot:
             else:                    # robot.py:68-69 -> HybridMap.get_scan_match hybridmap.py:210-261
                 ps.scan_match()
             if sh.rng == "numpy":
-                valid = ps.match_result()["valid"]
-                z = np.zeros((ps.N, ps.K, 3))
-                for i in np.flatnonzero(valid):          # draw order: particle-major, skipped for failed matches
-                    z[i] = np.random.standard_normal((ps.K, 3))
-                ps.weight(z)
+                # robot.py:81 verbatim, with NumPy itself and in the reference's order (particle-major, no
+                # draw for a failed match, robot.py:73-78): the global RNG stream is consumed exactly as
+                # the reference consumes it and the samples are bit-identical to its samples
+                m = ps.match_result()
+                g = np.zeros((ps.N, ps.K, 3))
+                for i in np.flatnonzero(m["valid"]):
+                    g[i] = np.random.multivariate_normal(m["pose"][i], m["cov"][i], ps.K)
+                ps.weight_guesses(g)
             else:
                 ps.weight(None)
             ps.integrate(fallback_weights=True)
