@@ -40,6 +40,10 @@
 // exhaustive search of the oracle; ~31 full-pass equivalents instead of 231.
 #include "common.cuh"
 
+#ifdef WT_LIBM   // experiment only
+#define rb_sincos(a, s, c) sincos(a, s, c)
+#endif
+
 #ifndef MT_GROUP
 #define MT_GROUP 8                      // rotations per group
 #endif

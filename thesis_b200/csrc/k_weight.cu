@@ -12,6 +12,11 @@
 // in the reference's sequential order so that results are run-to-run identical.
 #include "common.cuh"
 
+#ifdef WT_LIBM   // experiment only: CUDA libm instead of the shared IEEE routines (breaks bit parity with the oracle)
+#define rb_sincos(a, s, c) sincos(a, s, c)
+#define rb_exp(x) exp(x)
+#endif
+
 #ifndef WT_WARPS
 #define WT_WARPS 4
 #endif
