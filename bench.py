@@ -409,9 +409,9 @@ def run_b200(args):
                 "note": "the same K scans as the device-timed loop, from the same device-side snapshot of the particle set; every step "
                         "copies the sweep from pinned host memory and reads all poses and weights back"},
         # kernels of _librbpf.so per step (ncu launch list in profiles/): motion, match, match_copy_dups, weight x2
-        # (samples + fallback), raycast prepare + cast, resample plan, mult, gather, refs, dups = 12; sharded runs add
+        # (samples + fallback), raycast prepare + cast, resample plan + ancestors, gather, refs = 10; sharded runs add
         # the four pull kernels (claim, tiles, place, release); NCCL's own kernels are not counted
-        "gpu_launches": int(args.steps * (12 if world == 1 else 16)),
+        "gpu_launches": int(args.steps * (10 if world == 1 else 14)),
         "roofline": dominant,                               # the kernel with the longest launch
         "rooflines": rooflines,
         "stage_ms_per_step": {k: v / max(nst, 1) for k, v in stage_ms.items()},

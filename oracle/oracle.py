@@ -50,6 +50,7 @@ def lib():
         L.orc_bresenham.argtypes = [C.c_int] * 4 + [_ip, C.c_int]
         L.orc_map_update.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int]
         L.orc_nearby_occ.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int]
+        L.orc_match_ref.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int]
         L.orc_sample_weight.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp]
         L.orc_propose.argtypes = [_dp, _dp, _dp, C.c_int, _dp, _dp]
         L.orc_moments.restype = C.c_double
@@ -144,6 +145,12 @@ class Map:
     def update(self, pose, scan):
         p, pp = _d(pose)
         lib().orc_map_update(self._h, pp, *scan.ptrs(), scan.B)
+
+    def match_ref(self, guess, scan, cap=40000):
+        """valid_ref_points of hybridmap.py:230-239 (relative to the guess) as the restated matcher masks them."""
+        out = np.empty((cap, 2))
+        n = lib().orc_match_ref(self._h, _d(guess)[1], _d(scan.px)[1], _d(scan.py)[1], _d(scan.dist)[1], len(scan.px), _d(out)[1], cap)
+        return out[:n]
 
     def nearby_occ(self, x, y, cap=20000):
         out = np.empty((cap, 2))

@@ -559,6 +559,39 @@ int orc_match_curr(const orc_map *m, const double *guess, const double *px, cons
     return M;
 }
 
+static void match_ref_mask(const orc_map *m, const double *guess, const double *px, const double *py, const double *dist,
+                           int B, int G0x, int G0y, int R1, unsigned char *mask);
+
+/* The `valid_ref_points` of hybridmap.py:230-239 as the restated matcher sees them: occupied cells under
+ * match_ref_mask, as (x, y) relative to the guess, in the lexicographic order of np.unique.  Returns the
+ * count (out_xy may be NULL). */
+int orc_match_ref(const orc_map *m, const double *guess, const double *px, const double *py, const double *dist, int B,
+                  double *out_xy, int cap)
+{
+    int t0x = (int)floor(guess[0] / TILE_LEN + 0.5), t0y = (int)floor(guess[1] / TILE_LEN + 0.5);
+    if (guess[0] < t0x * TILE_LEN - 20.0) t0x--; else if (guess[0] >= t0x * TILE_LEN + 20.0) t0x++;
+    if (guess[1] < t0y * TILE_LEN - 20.0) t0y--; else if (guess[1] >= t0y * TILE_LEN + 20.0) t0y++;
+    const int i0x = (int)((guess[0] - t0x * TILE_LEN) / TILE_LEN * DIM + DIM / 2.0);
+    const int i0y = (int)((guess[1] - t0y * TILE_LEN) / TILE_LEN * DIM + DIM / 2.0);
+    const int G0x = 800 * t0x + i0x - 400, G0y = 800 * t0y + i0y - 400, R1 = 300, S1 = 2 * R1 + 1;
+    unsigned char *mask = (unsigned char *)malloc((size_t)S1 * S1);
+    match_ref_mask(m, guess, px, py, dist, B, G0x, G0y, R1, mask);
+    int n = 0;
+    for (int a = -R1; a <= R1; a++)                                            /* x-major = lexicographic */
+        for (int b = -R1; b <= R1; b++) {
+            if (!mask[(size_t)(b + R1) * S1 + (a + R1)] || !occ_cell(m, G0x + a, G0y + b)) continue;
+            const int Gx = G0x + a, Gy = G0y + b;
+            const int tx = (int)floor((Gx + 400) / 800.0), ty = (int)floor((Gy + 400) / 800.0);
+            if (out_xy && n < cap) {
+                out_xy[2 * n] = (index_to_distance(Gx + 400 - 800 * tx) + tx * TILE_LEN) - guess[0];
+                out_xy[2 * n + 1] = (index_to_distance(Gy + 400 - 800 * ty) + ty * TILE_LEN) - guess[1];
+            }
+            n++;
+        }
+    free(mask);
+    return n;
+}
+
 /* ---------------------------------------------------- NDT refinement stage -- */
 
 /*
@@ -828,9 +861,54 @@ void orc_ndt_probe(const double *p, double *out16) { g_probe_p = p; g_probe_out 
  * scan-to-map, hybridmap.py:210-261) or from the previous scan's endpoints
  * rasterised on the same lattice (ref_x/ref_y, n_ref; scan-to-scan,
  * hybridmap.py:147-191). */
+/* The reference's `ref` set (hybridmap.py:230-239): occupied cells are handed to the matcher only when they
+ * lie in the 72 x 72-cell window [j - 36, j + 36) of some curr point in some tile (GridMap._get_rel_cell and
+ * get_nearby_occ_points, gridmap.py:130-155, float expressions and the dec_x / dec_y quirk replayed) and
+ * within 11.5 m of the guess (:239).  Windows come from EVERY curr point of :216-228, also those the
+ * 11.0 m filter of :240 drops afterwards.  mask covers global read-lattice cells G0 + [-R1, R1]^2, row b. */
+static void match_ref_mask(const orc_map *m, const double *guess, const double *px, const double *py, const double *dist,
+                           int B, int G0x, int G0y, int R1, unsigned char *mask)
+{
+    const int S1 = 2 * R1 + 1, pr = (int)(1.8 / CS);
+    memset(mask, 0, (size_t)S1 * S1);
+    double c0, s0;
+    rb_sincos(guess[2], &s0, &c0);
+    for (int j = 0; j < B; j++) {
+        if (!(dist[j] < MATCH_MAX_R && dist[j] > MATCH_MIN_R)) continue;      /* :217-218 */
+        double gx, gy;
+        xform(c0, s0, guess[0], guess[1], px[j], py[j], &gx, &gy);
+        orc_tile *t0 = map_with_pos(m, gx, gy);                               /* :220-221 */
+        int ix, iy;
+        if (!t0 || !get_cell(gx - t0->cx, gy - t0->cy, &ix, &iy)) continue;
+        const double cpx = index_to_distance(ix) + t0->cx, cpy = index_to_distance(iy) + t0->cy;   /* :226-228 */
+        for (int i = 0; i < m->n; i++) {                                      /* :231-234 every tile */
+            const orc_tile *t = &m->tiles[i];
+            const double x = cpx - t->cx, y = cpy - t->cy;
+            int decx = 0, decy = 0;
+            if (y < -TILE_LEN / 2.0) decy = 1; else if (x < -TILE_LEN / 2.0) decx = 1;            /* gridmap.py:131-136 */
+            const int jx = (int)(x / TILE_LEN * DIM + DIM / 2.0) - decx, jy = (int)(y / TILE_LEN * DIM + DIM / 2.0) - decy;
+            const int x0 = jx - pr > 0 ? jx - pr : 0, y0 = jy - pr > 0 ? jy - pr : 0;
+            const int x1 = jx + pr < DIM ? jx + pr : DIM, y1 = jy + pr < DIM ? jy + pr : DIM;
+            const int tx = t->cx / TILE_LEN, ty = t->cy / TILE_LEN;
+            for (int a = x0; a < x1; a++) {
+                const int ra = 800 * tx + a - 400 - G0x;
+                if (ra < -R1 || ra > R1) continue;
+                const double rx_ = (index_to_distance(a) + t->cx) - guess[0];                     /* :237 */
+                for (int b = y0; b < y1; b++) {
+                    const int rb = 800 * ty + b - 400 - G0y;
+                    if (rb < -R1 || rb > R1) continue;
+                    const double ry_ = (index_to_distance(b) + t->cy) - guess[1];
+                    if (sqrt(rx_ * rx_ + ry_ * ry_) < MATCH_MAX_R + 0.5) mask[(size_t)(rb + R1) * S1 + (ra + R1)] = 1;   /* :239 */
+                }
+            }
+        }
+    }
+}
+
 static int match_core(const orc_map *m, const double *ref_x, const double *ref_y, int n_ref,
                       const double *guess, double *cx, double *cy, const int *cj, int M, double rx, double ry,
-                      double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice)
+                      double *out_pose, double *out_cov, double *out_score, int *dbg, int *slice,
+                      const double *px, const double *py, const double *dist, int B)
 {
     /* cell of the guess position and the guess's offset inside it */
     int t0x = (int)floor(guess[0] / TILE_LEN + 0.5), t0y = (int)floor(guess[1] / TILE_LEN + 0.5);
@@ -851,9 +929,15 @@ static int match_core(const orc_map *m, const double *ref_x, const double *ref_y
     unsigned char *win = (unsigned char *)malloc((size_t)S * S);
     unsigned char *raw = (unsigned char *)calloc((size_t)(S + 2) * (S + 2), 1);
     if (m) {
+        /* occupied cells of the particle's tiles that the reference would pass on as `ref` (hybridmap.py:230-239) */
+        unsigned char *mask = (unsigned char *)malloc((size_t)(S + 2) * (S + 2));
+        match_ref_mask(m, guess, px, py, dist, B, G0x, G0y, R + 1, mask);
         for (int b = -R - 1; b <= R + 1; b++)
-            for (int a = -R - 1; a <= R + 1; a++)
-                raw[(size_t)(b + R + 1) * (S + 2) + (a + R + 1)] = (unsigned char)occ_cell(m, G0x + a, G0y + b);
+            for (int a = -R - 1; a <= R + 1; a++) {
+                const size_t o = (size_t)(b + R + 1) * (S + 2) + (a + R + 1);
+                raw[o] = mask[o] ? (unsigned char)occ_cell(m, G0x + a, G0y + b) : 0;
+            }
+        free(mask);
     } else {
         /* previous-scan endpoints relative to the guess, |r| < 11 (hybridmap.py:170-171),
          * rasterised like the curr points at rotation 0 */
@@ -971,7 +1055,7 @@ int orc_match(const orc_map *m, const double *guess, const double *px, const dou
     double *cx = (double *)malloc(sizeof(double) * (size_t)B), *cy = (double *)malloc(sizeof(double) * (size_t)B);
     int *cj = (int *)malloc(sizeof(int) * (size_t)B);
     int M = match_curr(m, guess, px, py, dist, B, cx, cy, cj);
-    int v = match_core(m, NULL, NULL, 0, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    int v = match_core(m, NULL, NULL, 0, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice, px, py, dist, B);
     free(cx); free(cy); free(cj);
     return v;
 }
@@ -996,7 +1080,7 @@ int orc_match_adj(const double *guess, const double *px, const double *py, int B
         if (!(sqrt(qx * qx + qy * qy) < MATCH_MAX_R)) continue;
         cx[M] = qx; cy[M] = qy; cj[M] = j; M++;
     }
-    int v = match_core(NULL, prev_x, prev_y, n_prev, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice);
+    int v = match_core(NULL, prev_x, prev_y, n_prev, guess, cx, cy, cj, M, rx, ry, out_pose, out_cov, out_score, dbg, slice, px, py, NULL, B);
     free(cx); free(cy); free(cj);
     return v;
 }

@@ -96,7 +96,11 @@ def test_matcher_front_end_points(golden):
     curr = m.match_curr(guess, s)
     assert curr.shape == golden["upd_curr"].shape
     assert np.array_equal(curr, golden["upd_curr"])
-    # ref = unique occupied cells within the 72x72 windows of the curr points, < 11.5 m
+    # ref = unique occupied cells within the 72x72 windows of the curr points, < 11.5 m: the set the restated
+    # matcher scores on (orc_match masks the occupancy with it) is the reference's valid_ref_points, in np.unique order
+    ref = m.match_ref(guess, s)
+    assert ref.shape == golden["upd_ref"].shape
+    assert np.array_equal(ref, golden["upd_ref"])
     pts = []
     for cx, cy in curr + guess[:2]:
         pts.append(m.nearby_occ(cx, cy))

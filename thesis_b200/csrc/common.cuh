@@ -119,6 +119,7 @@ struct RbCtx {
     const uint32_t *lutx, *luty;            // per axis, packed (RB_LUT_*)
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch
+    double *plan_scal;                      // slice, start of the last plan (main.py:57,59)
     int *ancestors;                         // n_global
     int *mult;                              // N  local descendants of each old local particle
     // Duplicates made by the last resample are bit-identical (pose, covariance, shared

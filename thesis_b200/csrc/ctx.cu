@@ -214,7 +214,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
-    A(d.w_all, d.n_global); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
+    A(d.w_all, d.n_global); A(d.plan_scal, 4); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);
     A(h->d_z, N * d.K * 3);
     A(h->d_u01, 2);
@@ -267,6 +267,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     h->mg_n = h->mg_tiles = 0;
     cudaMemsetAsync(h->d_mg_mark, 0xFF, sizeof(uint32_t) * (size_t)d.pool_tiles, h->stream);
     cudaMemsetAsync(d.m_refine, 0, sizeof(int) * 2 * (size_t)N, h->stream);
+    cudaMemsetAsync(d.mult, 0, sizeof(int) * (size_t)N, h->stream);      // zero between resamples (resample_refs_kernel resets it)
     rb_launch_init(d, h->stream);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, std::string("init: ") + cudaGetErrorString(e));

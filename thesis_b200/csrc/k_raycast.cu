@@ -148,25 +148,36 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
     for (int j = lane; j < c.B; j += 32) {
         const Ray r = ray_of_beam(c, j, x, y, cs_, sn_, sx, sy);
         const RayStep st = ray_step(sx, sy, r);
+        // sub-tile coordinates of the cells at n = 0, 32, 64, ... and of the last cell: consecutive
+        // segments share an end, and most of them stay inside the sub-tile that is already marked
+        int pax = 0, pay = 0, last = -1;
         for (int n0 = 0; n0 < r.len; n0 += 32) {
-            int n1 = min(n0 + 31, r.len - 1), ax, ay, bx, by;
-            ray_cell(sx, sy, st, n0, ax, ay);
+            const int n1 = min(n0 + 32, r.len - 1);
+            int ax, ay, bx, by;
+            if (n0 == 0) {
+                ray_cell(sx, sy, st, 0, ax, ay);
+                const uint32_t qx = rb_write_lut(c.lutx, ax, c.txh), qy = rb_write_lut(c.luty, ay, c.tyh);
+                // when one end is outside the world, the cells of the segment that are inside still lie
+                // between the inside end and the world border: use the border sub-tile of that axis
+                pax = qx == RB_NONE ? (ax < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(qx);
+                pay = qy == RB_NONE ? (ay < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(qy);
+            }
             ray_cell(sx, sy, st, n1, bx, by);
-            const uint32_t pax = rb_write_lut(c.lutx, ax, c.txh), pay = rb_write_lut(c.luty, ay, c.tyh);
             const uint32_t pbx = rb_write_lut(c.lutx, bx, c.txh), pby = rb_write_lut(c.luty, by, c.tyh);
-            // when one end is outside the world, the cells of the segment that are
-            // inside still lie between the inside end and the world border: use the
-            // border sub-tile of that axis
-            int sax = pax == RB_NONE ? (ax < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(pax);
-            int sbx = pbx == RB_NONE ? (bx < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(pbx);
-            int say = pay == RB_NONE ? (ay < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(pay);
-            int sby = pby == RB_NONE ? (by < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(pby);
-            int s0 = say * c.subs_x + sax, s1 = sby * c.subs_x + sbx, s2 = say * c.subs_x + sbx,
-                s3 = sby * c.subs_x + sax;
-            atomicOr(&mask[s0 >> 5], 1u << (s0 & 31));
-            atomicOr(&mask[s1 >> 5], 1u << (s1 & 31));
-            atomicOr(&mask[s2 >> 5], 1u << (s2 & 31));
-            atomicOr(&mask[s3 >> 5], 1u << (s3 & 31));
+            const int sbx = pbx == RB_NONE ? (bx < 0 ? 0 : c.subs_x - 1) : (int)RB_LUT_SUB(pbx);
+            const int sby = pby == RB_NONE ? (by < 0 ? 0 : c.subs_y - 1) : (int)RB_LUT_SUB(pby);
+            const int s0 = pay * c.subs_x + pax, s1 = sby * c.subs_x + sbx;
+            if (s0 != s1 || s0 != last) {
+                const int s2 = pay * c.subs_x + sbx, s3 = sby * c.subs_x + pax;
+                atomicOr(&mask[s0 >> 5], 1u << (s0 & 31));
+                if (s1 != s0) {
+                    atomicOr(&mask[s1 >> 5], 1u << (s1 & 31));
+                    if (s2 != s0 && s2 != s1) atomicOr(&mask[s2 >> 5], 1u << (s2 & 31));
+                    if (s3 != s0 && s3 != s1) atomicOr(&mask[s3 >> 5], 1u << (s3 & 31));
+                }
+                last = s1;
+            }
+            pax = sbx; pay = sby;
         }
     }
     __syncwarp();

@@ -21,16 +21,18 @@
 //                 descendants contributes m - 1 (or releases its tiles if m = 0).
 #include "common.cuh"
 
-#define RS_THREADS 1024
-static_assert(RS_THREADS == 1024, "the block scan assumes 32 warps");
+#define RS_THREADS 256                  // 8 warps: the kernel is a chain of dependent chunk scans, not throughput work
+#define RS_EPT 4                        // consecutive elements per thread
+#define RS_CHUNK (RS_THREADS * RS_EPT)  // 1,024
+static_assert(RS_THREADS == 256, "the block scan assumes 8 warps");
 
 __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, const double *__restrict__ w_in,
                                                                    const double *__restrict__ u01_in)
 {
-    __shared__ double red_mx[32], red_mn[32];
-    __shared__ double chunk[RS_THREADS];
-    __shared__ long long scan_tot[32];
-    __shared__ double s_mn2, s_carry, s_slice, s_start;
+    __shared__ double red_mx[RS_THREADS / 32], red_mn[RS_THREADS / 32];
+    __shared__ double chunk[RS_CHUNK];
+    __shared__ long long scan_tot[RS_THREADS / 32];
+    __shared__ double s_mn2, s_carry;
     __shared__ int s_do;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NG = c.n_global;
@@ -56,10 +58,7 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
         if (s_do) c.stats->resamples += 1ull;
     }
     __syncthreads();
-    if (!s_do) {                                                             // particles unchanged
-        for (int i = tid; i < NG; i += RS_THREADS) c.ancestors[i] = i;
-        return;
-    }
+    if (!s_do) return;                                                       // particles unchanged (identity ancestors)
     // -inf -> 0, then min of the result (main.py:53-54)
     mn = INF;
     for (int i = tid; i < NG; i += RS_THREADS) {
@@ -86,9 +85,9 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
     // (an integer in [2^52, 2^53)) and v = (m + f) u, m integer, 0 <= f < 1:
     //     S' = S + m + [f > 1/2]          (f == 1/2, a tie, depends on the parity of S + m)
     // so a chunk without ties that does not leave the binade is an exact INTEGER prefix sum,
-    // done in parallel (one element per thread, two barriers).  Chunks with a tie, a
-    // binade crossing, a denormal or the very first chunk take the sequential chain.
-    const int n_chunks = (NG + RS_THREADS - 1) / RS_THREADS;
+    // done in parallel (RS_EPT consecutive elements per thread, two barriers).  Chunks with a tie,
+    // a binade crossing, a denormal or the very first chunk take the sequential chain.
+    const int n_chunks = (NG + RS_CHUNK - 1) / RS_CHUNK;
     const unsigned long long MANT = (1ull << 52) - 1ull;
     double carry = 0.0;                                                      // uniform over the block
     auto load = [&](int i) {
@@ -99,37 +98,45 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
         }
         return v;
     };
-    double v_next = load(tid);
+    double v_next[RS_EPT];
+#pragma unroll
+    for (int e = 0; e < RS_EPT; e++) v_next[e] = load(RS_EPT * tid + e);
     for (int k = 0; k < n_chunks; k++) {
-        const int i = k * RS_THREADS + tid;
-        const bool active = i < NG;
-        const double v = v_next;
-        v_next = load(i + RS_THREADS);
+        const int i0 = k * RS_CHUNK + RS_EPT * tid;
+        double v[RS_EPT];
+#pragma unroll
+        for (int e = 0; e < RS_EPT; e++) { v[e] = v_next[e]; v_next[e] = load(i0 + RS_CHUNK + e); }
         const unsigned long long cb = (unsigned long long)__double_as_longlong(carry);
         const int kexp = (int)((cb >> 52) & 0x7ffull);
         const bool fast_ok = !(cb >> 63) && kexp >= 54 && kexp < 0x7ff;      // carry > 0, normal, u normal
-        long long a = 0;
+        long long a[RS_EPT];
         bool slow = !fast_ok;
-        if (active && fast_ok && v != 0.0) {
-            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
-            const int ve = (int)((vb >> 52) & 0x7ffull);
-            if ((vb >> 63) || ve == 0x7ff || ve == 0) slow = true;           // negative, inf / nan, denormal
-            else {
-                const unsigned long long M = (vb & MANT) | (1ull << 52);
-                const int sft = kexp - ve;
-                if (sft < 1) slow = true;                                    // v >= 2^k: the sum leaves the binade
-                else if (sft <= 54) {
-                    const unsigned long long r = M & ((1ull << sft) - 1ull), half = 1ull << (sft - 1);
-                    a = (long long)(M >> sft);
-                    if (r > half) a += 1;
-                    else if (r == half) slow = true;                         // tie
-                }                                                            // sft > 54: v < u/4, rounds away
+#pragma unroll
+        for (int e = 0; e < RS_EPT; e++) {
+            a[e] = 0;
+            if (i0 + e < NG && fast_ok && v[e] != 0.0) {
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(v[e]);
+                const int ve = (int)((vb >> 52) & 0x7ffull);
+                if ((vb >> 63) || ve == 0x7ff || ve == 0) slow = true;       // negative, inf / nan, denormal
+                else {
+                    const unsigned long long M = (vb & MANT) | (1ull << 52);
+                    const int sft = kexp - ve;
+                    if (sft < 1) slow = true;                                // v >= 2^k: the sum leaves the binade
+                    else if (sft <= 54) {
+                        const unsigned long long r = M & ((1ull << sft) - 1ull), half = 1ull << (sft - 1);
+                        a[e] = (long long)(M >> sft);
+                        if (r > half) a[e] += 1;
+                        else if (r == half) slow = true;                     // tie
+                    }                                                        // sft > 54: v < u/4, rounds away
+                }
             }
         }
         bool done = false;
         if (!__syncthreads_or(slow)) {
-            // inclusive integer scan over the block
-            long long p = a;
+            // inclusive integer scan: inside the thread, across the warp, across the 8 warps
+#pragma unroll
+            for (int e = 1; e < RS_EPT; e++) a[e] += a[e - 1];
+            long long p = a[RS_EPT - 1];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long q = __shfl_up_sync(0xffffffffu, p, o);
@@ -137,28 +144,31 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
             }
             if (lane == 31) scan_tot[warp] = p;
             __syncthreads();
-            long long t = scan_tot[lane];                                    // RS_THREADS / 32 == 32 warps
+            long long before = p - a[RS_EPT - 1], total = 0;                 // exclusive prefix of this thread inside the warp
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long q = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += q;
+            for (int q = 0; q < RS_THREADS / 32; q++) {
+                const long long t = scan_tot[q];
+                if (q < warp) before += t;
+                total += t;
             }
-            const long long total = __shfl_sync(0xffffffffu, t, 31);
-            const long long before = warp ? __shfl_sync(0xffffffffu, t, warp - 1) : 0ll;
             const unsigned long long S_in = (cb & MANT) | (1ull << 52);
             if (S_in + (unsigned long long)total < (1ull << 53)) {            // stays in the binade
                 const unsigned long long hi = (unsigned long long)kexp << 52;
-                if (active) w[i] = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)(before + p)) & MANT)));
+#pragma unroll
+                for (int e = 0; e < RS_EPT; e++)
+                    if (i0 + e < NG) w[i0 + e] = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)(before + a[e])) & MANT)));
                 carry = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)total) & MANT)));
                 done = true;
             }
             __syncthreads();                                                 // scan_tot is reused by the next chunk
         }
         if (!done) {                                                         // sequential chain for this chunk
-            chunk[tid] = v;
+            // (a[] may hold partial prefix sums here; the chain works on the values themselves)
+#pragma unroll
+            for (int e = 0; e < RS_EPT; e++) chunk[RS_EPT * tid + e] = v[e];
             __syncthreads();
             if (tid == 0) {
-                const int n = min(RS_THREADS, NG - k * RS_THREADS);
+                const int n = min(RS_CHUNK, NG - k * RS_CHUNK);
                 double cur = carry;
                 int e0 = 0;
                 for (; e0 + 8 <= n; e0 += 8) {
@@ -174,7 +184,9 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
                 s_carry = cur;
             }
             __syncthreads();
-            if (active) w[i] = chunk[tid];
+#pragma unroll
+            for (int e = 0; e < RS_EPT; e++)
+                if (i0 + e < NG) w[i0 + e] = chunk[RS_EPT * tid + e];
             carry = s_carry;
             __syncthreads();
         }
@@ -190,18 +202,26 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
             rb_philox(0x5eedu, 0u, (uint32_t)c.step_no, 0x52u, c.seed, r);
             u = rb_u01(r[0], r[1]);
         }
-        s_slice = slice;
-        s_start = u * slice;                                                 // main.py:59
+        c.plan_scal[0] = slice;
+        c.plan_scal[1] = u * slice;                                          // main.py:59
     }
-    __syncthreads();
-    const double slice = s_slice, start = s_start;
-    // emitted-after-i = max(0, floor((c_i - start)/slice) + 1)  (main.py:63-64;
-    // the running sum is non-decreasing because all adjusted weights are >= 0)
+}
+
+// Ancestors from the running sum, in parallel over all SMs (every rank runs it on identical input):
+// emitted-after-i = max(0, floor((c_i - start)/slice) + 1)  (main.py:63-64; the running sum is
+// non-decreasing because all adjusted weights are >= 0).  Identity when nothing triggered.
+__global__ void __launch_bounds__(256) resample_ancestors_kernel(RbCtx c)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, NG = c.n_global;
+    if (i >= NG) return;
+    if (!c.flags->did_resample) { c.ancestors[i] = i; return; }
+    const double *w = c.w_all;
+    const double slice = c.plan_scal[0], start = c.plan_scal[1];
     bool bad = false;
-    for (int i = tid; i < NG; i += RS_THREADS) {
-        double f = floor((w[i] - start) / slice);
-        double fp = i ? floor((w[i - 1] - start) / slice) : -1.0;
-        if (!(f > -4e18 && f < 4e18)) { bad = true; continue; }             // math.floor would raise
+    const double f = floor((w[i] - start) / slice);
+    const double fp = i ? floor((w[i - 1] - start) / slice) : -1.0;
+    if (!(f > -4e18 && f < 4e18)) bad = true;                                // math.floor would raise
+    else {
         long long e1 = (long long)f + 1, e0 = i ? (long long)fp + 1 : 0;
         if (e0 < 0) e0 = 0;
         if (e1 < 0) e1 = 0;
@@ -212,14 +232,31 @@ __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, cons
     if (bad) { c.flags->resample_error = 1; c.flags->resample_error_sticky = 1; }
 }
 
-// Local slot j of this rank is global slot rank*N + j.
+// Local slot j of this rank is global slot rank*N + j.  One warp per new slot: copies the ancestor's
+// state and page table, counts the ancestor's local descendants (mult, zero between resamples) and
+// finds dup_of[j] = first local slot with the same ancestor (the ancestor vector is non-decreasing, so
+// that is a lower bound found by bisection).
 __global__ void __launch_bounds__(256) resample_gather_kernel(RbCtx c)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= c.N) return;
     const int j = warp;
     const int err = c.flags->resample_error;                                  // on error: particles unchanged
-    const int a = err ? j : c.ancestors[c.rank * c.N + j] - c.rank * c.N;
+    const int base = c.rank * c.N;
+    const int ag = err ? base + j : c.ancestors[base + j];
+    const int a = ag - base;
+    if (lane == 1) {
+        int rep = j;
+        if (!err && c.flags->did_resample) {
+            int lo = base, hi = base + j;                 // first index in [base, base + j] with ancestors[idx] >= ag
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (c.ancestors[mid] < ag) lo = mid + 1; else hi = mid;
+            }
+            rep = lo - base;
+        }
+        c.dup_of[j] = rep;
+    }
     if (a < 0 || a >= c.N) {                                                  // remote ancestor: migration fills it
         if (lane == 0) atomicAdd(&c.flags->remote_needed, 1);
         return;
@@ -228,6 +265,7 @@ __global__ void __launch_bounds__(256) resample_gather_kernel(RbCtx c)
     if (lane < 3) c.pose2[3 * (size_t)j + lane] = c.pose[3 * (size_t)a + lane];
     if (lane < 9) c.cov2[9 * (size_t)j + lane] = c.cov[9 * (size_t)a + lane];
     if (lane == 0) {
+        atomicAdd(&c.mult[a], 1);
         c.exists2[j] = c.exists[a];
         if (did) c.weight[j] = 1.0;                                           // main.py:77-78 (a == j when !did)
     }
@@ -236,20 +274,15 @@ __global__ void __launch_bounds__(256) resample_gather_kernel(RbCtx c)
     for (int e = lane; e < c.nsub; e += 32) dst[e] = src[e];
 }
 
-// Number of local descendants of every old local particle.
-__global__ void __launch_bounds__(256) resample_mult_kernel(RbCtx c)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c.N) return;
-    const int a = c.flags->resample_error ? j : c.ancestors[c.rank * c.N + j] - c.rank * c.N;
-    if (a >= 0 && a < c.N) atomicAdd(&c.mult[a], 1);
-}
-
+// Reference counts: an old particle with m local descendants contributes m - 1, or releases its
+// sub-tiles when m = 0.  Leaves mult zero for the next resample.
 __global__ void __launch_bounds__(256) resample_refs_kernel(RbCtx c)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= c.N) return;
     const int m = c.mult[warp];
+    __syncwarp();
+    if (lane == 0) c.mult[warp] = 0;
     if (m == 1) return;
     const uint32_t *src = c.pt + (size_t)warp * c.nsub;
     for (int e = lane; e < c.nsub; e += 32) {
@@ -270,35 +303,13 @@ __global__ void __launch_bounds__(256) resample_refs_kernel(RbCtx c)
 void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s)
 {
     resample_plan_kernel<<<1, RS_THREADS, 0, s>>>(c, weights_all, u01_dev);
-}
-
-// dup_of[j] = first local slot whose ancestor equals slot j's (ancestors are non-decreasing,
-// so that is a lower bound found by bisection).
-__global__ void __launch_bounds__(256) resample_dups_kernel(RbCtx c)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c.N) return;
-    int rep = j;
-    if (!c.flags->resample_error && c.flags->did_resample) {
-        const int base = c.rank * c.N;
-        const int a = c.ancestors[base + j];
-        int lo = base, hi = base + j;                 // first index in [base, base + j] with ancestors[idx] >= a
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (c.ancestors[mid] < a) lo = mid + 1; else hi = mid;
-        }
-        rep = lo - base;
-    }
-    c.dup_of[j] = rep;
+    resample_ancestors_kernel<<<(c.n_global + 255) / 256, 256, 0, s>>>(c);
 }
 
 // Applies the planned ancestors to this rank's particles (local part).
 void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s)
 {
-    cudaMemsetAsync(c.mult, 0, sizeof(int) * (size_t)c.N, s);
-    resample_mult_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
     int blocks = (c.N * 32 + 255) / 256;
     resample_gather_kernel<<<blocks, 256, 0, s>>>(c);
     resample_refs_kernel<<<blocks, 256, 0, s>>>(c);
-    resample_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
 }
