@@ -66,10 +66,6 @@
 #define MT_RAW_ROWS 484
 #define MT_NRB ((MT_RAW_ROWS + 31) / 32) // 16 bands of 32 rows
 #define MT_NBLK (MT_NRB * RB_RAW_STRIDE) // 288 blocks of 32 rows x 32 cells
-#define MT_NBINS 64                     // polar bins of the curr points (which blocks can a lookup reach?)
-#define MT_REACH 60.0f                  // cells: half diagonal of a block (22.7) + lookup reach around a rotated point
-                                        // (14 translation + 5 group dilation + 1 proximity + rounding, as a Euclidean
-                                        // distance: 29.7) + the guess inside its cell (1.4) + slack
 #ifndef MT_GATHER_U
 #define MT_GATHER_U 4                   // blocks (= 32-byte sectors per lane) in flight per warp and round of the gather
 #endif
@@ -92,7 +88,7 @@ struct MatchShared {
     int slot_warp;                      // warp whose slot holds the counters of the best rotation
     int a0, dy0;                        // first staged row (storage coordinates, multiple of 4); y0 - 1 - a0
     int nblk;                           // blocks to gather
-    int rbin[MT_NBINS], rdil[MT_NBINS]; // farthest curr point per polar bin [cells]; the same over +-30 degrees of rotation
+    unsigned short row_lo[RB_BM_ROWS], row_hi[RB_BM_ROWS];   // columns of a bitmap row within 11.5 m of the guess (:239)
     uint32_t need[MT_NRB];              // per band: which 32-cell words a lookup can reach
     unsigned short blist[MT_NBLK];      // compacted list of those blocks
     int ord_cnt[4 * MT_WARPS];          // far-first ordering of the points: per range class and warp
@@ -370,22 +366,27 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
 }
 
 // curr point of beam j relative to the guess position (hybridmap.py:216-228,236,240; adj: :165-172)
-__device__ __forceinline__ bool mt_curr_point(const RbCtx &c, const MatchShared *sh, unsigned long long exists, double d, double bpx,
-                                              double bpy, int adj, double &qx, double &qy)
+// Returns bit 1 when the beam is a curr point of the matcher (|c| < 11 m, :240) and bit 0 when it is a
+// curr point of hybridmap.py:216-228 at all -- those span the 72 x 72-cell windows of the reference set
+// (:230-234), also the ones the 11 m filter drops.  (ax, ay) = its cell corner in map coordinates.
+__device__ __forceinline__ int mt_curr_point(const RbCtx &c, const MatchShared *sh, unsigned long long exists, double d, double bpx,
+                                             double bpy, int adj, double &qx, double &qy, double &ax, double &ay)
 {
     double gx, gy;
     rb_xform(sh->cs0, sh->sn0, sh->gx, sh->gy, bpx, bpy, gx, gy);
+    ax = ay = 0.0;
     if (adj) {                                                             // hybridmap.py:165-172
         qx = gx - sh->gx; qy = gy - sh->gy;
-        return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R;
+        return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R ? 2 : 0;
     }
-    if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) return false;
+    if (!(d < RB_MATCH_MAX_R && d > RB_MATCH_MIN_R)) return 0;
     int tx, ty, ix, iy;
     rb_read_axis(gx, tx, ix);
     rb_read_axis(gy, ty, iy);
-    if (!rb_tile_exists(c, exists, tx, ty)) return false;
-    qx = rb_cell_corner(ix, tx) - sh->gx; qy = rb_cell_corner(iy, ty) - sh->gy;
-    return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R;
+    if (!rb_tile_exists(c, exists, tx, ty)) return 0;
+    ax = rb_cell_corner(ix, tx); ay = rb_cell_corner(iy, ty);
+    qx = ax - sh->gx; qy = ay - sh->gy;
+    return sqrt(qx * qx + qy * qy) < RB_MATCH_MAX_R ? 3 : 1;
 }
 
 // ---- NDT refinement stage (matchScanCustom.m:32-50) --------------------------------
@@ -675,7 +676,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     if (c.use_dup && !slice_out && c.dup_of[p] != p) return;                // a bit-identical duplicate: result copied afterwards
     const double *pose = c.pose + 3 * (size_t)p, *cov = c.cov + 9 * (size_t)p;
     long long clk_prev = clock64();
-    if (tid < MT_NBINS) sh->rbin[tid] = 0;
     if (tid < MT_NRB) sh->need[tid] = 0u;
     // this thread's beam (one per thread) and the tile mask are on their way while thread 0 sets up the frame
     const bool has_beam = tid < c.B;
@@ -722,15 +722,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     __syncthreads();
 
     // ---- 1. curr points, hybridmap.py:216-228,236,240 ----------------------
-    const bool gate = !adj && !c.refine;                                    // gather only the blocks a lookup can reach
     if (tid < 25 && !adj) {                                                 // page-table entries under the window
         const int sxb = sh->sxb0 + tid % 5, syb = sh->syb0 + tid / 5;
         sh->ptw[tid] = (sxb >= 0 && sxb < c.subs_x && syb >= 0 && syb < c.subs_y) ? c.pt[(size_t)p * c.nsub + syb * c.subs_x + sxb] : RB_NONE;
     }
     static_assert(MT_THREADS >= RB_MAXB, "one thread per beam");
+    double cp_x = 0.0, cp_y = 0.0;                                          // this thread's beam: cell corner in map coordinates
+    int cp_kind = 0;
     {
         double qx = 0.0, qy = 0.0;
-        const bool is_pt = has_beam && mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy);
+        cp_kind = has_beam ? mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy, cp_x, cp_y) : 0;
+        const bool is_pt = cp_kind & 2;
         const unsigned bal = __ballot_sync(0xffffffffu, is_pt);
         int base = 0;
         if (bal && lane == 0) base = atomicAdd(&sh->M, __popc(bal));        // one slot range per warp
@@ -739,12 +741,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             const int slot = base + __popc(bal & ((1u << lane) - 1u));
             ccx[slot] = qx;
             ccy[slot] = qy;
-            if (gate) {                                                     // farthest point per polar bin, in cells
-                const float fx_ = (float)qx, fy_ = (float)qy;
-                int bin = (int)((atan2f(fy_, fx_) + 3.14159265f) * (MT_NBINS / 6.28318531f));
-                bin = min(max(bin, 0), MT_NBINS - 1);
-                atomicMax(&sh->rbin[bin], (int)(sqrtf(fx_ * fx_ + fy_ * fy_) * 20.0f) + 2);
-            }
         }
     }
     __syncthreads();
@@ -758,13 +754,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         const int Mp = sh->M;
         const int s_ = Mp % 37 ? 37 : (Mp % 41 ? 41 : 43);                      // a prime that does not divide M
         for (int q = tid; q < Mp; q += MT_THREADS) { tx_[q] = ccx[q]; ty_[q] = ccy[q]; }
-        // the rotation search turns every point by up to +-30 degrees (5.33 bins) around the guess
-        if (tid < MT_NBINS) {
-            int m = 0;
-#pragma unroll
-            for (int d = -7; d <= 7; d++) m = max(m, sh->rbin[(tid + d) & (MT_NBINS - 1)]);
-            sh->rdil[tid] = m;
-        }
         __syncthreads();
         // ... and far points first (stable within four range classes): a wrong rotation moves a
         // point by range x angle, so the far points are the ones that miss, and the passes that
@@ -797,47 +786,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         }
         __syncthreads();
     }
-#else
-    if (tid < MT_NBINS) {
-        int m = 0;
-        for (int d = -7; d <= 7; d++) m = max(m, sh->rbin[(tid + d) & (MT_NBINS - 1)]);
-        sh->rdil[tid] = m;
-    }
-    __syncthreads();
 #endif
     if (tid < sh->M) ccf[tid] = make_float2((float)(ccx[tid] * 20.0), (float)(ccy[tid] * 20.0));
     MT_CLK(0)
-    // Which 32 x 32-cell blocks of the window can a lookup touch?  A lookup lies within
-    // MT_REACH - 22.7 cells of a point turned by at most 30 degrees, so a block matters only if
-    // the disc of radius MT_REACH around its centre reaches the polar region the points
-    // sweep (conservative: float slack on the angles, two cells on the radii).
     const int a0 = sh->a0, dy0 = sh->dy0;
-    if (tid < MT_NBLK) {
-        const int rb = tid / RB_RAW_STRIDE, wc = tid - rb * RB_RAW_STRIDE;
-        bool needed = !gate;
-        if (gate && sh->M > 0) {
-            const float bx = (float)(sh->x0 - 32 + 32 * wc + 16 - sh->g0xu), by = (float)(a0 + 32 * rb + 16 - sh->g0yu);
-            const float d = sqrtf(bx * bx + by * by);
-            if (d <= MT_REACH + 1.0f) {
-                needed = true;
-            } else {
-                const float al = asinf(MT_REACH / d) + 0.02f, ac = atan2f(by, bx) + 3.14159265f;
-                const int lo = (int)floorf((ac - al) * (MT_NBINS / 6.28318531f)), hi = (int)floorf((ac + al) * (MT_NBINS / 6.28318531f));
-                const int far = (int)(d - MT_REACH);
-                for (int bb = lo; bb <= hi && bb < lo + MT_NBINS; bb++) needed |= sh->rdil[bb & (MT_NBINS - 1)] >= far;
-            }
-        }
-        if (needed) {
-            atomicOr(&sh->need[rb], 1u << wc);
-            sh->blist[atomicAdd(&sh->nblk, 1)] = (unsigned short)tid;
-        }
-    }
 
     // ---- 2. occupancy bitmap around the guess cell ---------------------------
-    MT_CLK(3)
     if (adj) {
         // previous scan rasterised relative to the guess cell, like curr points at rotation 0
         for (int idx = tid; idx < MT_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
+        if (tid < MT_NRB) sh->need[tid] = 0xffffffffu;
         __syncthreads();
         const int xb = sh->g0xu - sh->x0 + 32, yb = RB_WIN_R + 1 + dy0;
         for (int q = tid; q < c.n_prev; q += MT_THREADS) {
@@ -848,16 +806,111 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             atomicOr(&raw[b * RB_RAW_STRIDE + (a >> 5)], 1u << (a & 31));
         }
     } else {
-        __syncthreads();                                                    // need[], blist[] complete
-        const int x0 = sh->x0, nblk = sh->nblk;
-        unsigned char *rawb = reinterpret_cast<unsigned char *>(raw);
-        // blocks no lookup can reach stay empty
-        for (int b = warp; b < MT_NBLK; b += MT_WARPS) {
-            const int rb = b / RB_RAW_STRIDE, wc = b - rb * RB_RAW_STRIDE;
-            if ((sh->need[rb] >> wc) & 1u) continue;
-            const int row = 32 * rb + lane;
-            if (row < MT_RAW_ROWS) raw[row * RB_RAW_STRIDE + wc] = 0u;
+        // ---- 2a. the reference's `ref` set, hybridmap.py:230-239 -------------------------------
+        // Occupied cells reach the matcher only when they lie in the 72 x 72-cell window
+        // [j - 36, j + 36) of some curr point in some tile (GridMap._get_rel_cell /
+        // get_nearby_occ_points, gridmap.py:130-155: float expression and dec quirk replayed per point
+        // and tile) and within 11.5 m of the guess.  Union of equal squares = dilation of their centres:
+        // every point marks its 72-bit row span at its (per tile) centre row, a running OR over 72 rows
+        // (prefix / suffix ORs over blocks of 72 rows) does the rest; tile extents clip both ways.  The
+        // mask is built in `raw`; the gather then fetches only 32 x 32-cell blocks whose mask is not empty.
+        const int x0 = sh->x0, y0 = sh->y0;
+        uint32_t *H = bm, *Gp = bmg;                                        // both free until the dilation pass
+        for (int idx = tid; idx < MT_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
+        // rows: |ref| < 11.5 m (:239) as a column interval [lo, hi) per bitmap row, float64 predicate as in the oracle
+        for (int r = tid; r < RB_BM_ROWS; r += MT_THREADS) {
+            const int uy = y0 + r;
+            const int tY = (uy + 800 * 1024) / 800 - 1024, iy = uy - 800 * tY;
+            const double dyr = rb_cell_corner(iy, tY - c.tyh) - sh->gy;
+            int lo = 0, hi = 0;
+            const double lim = RB_MATCH_MAX_R + 0.5;
+            if (fabs(dyr) < lim) {
+                auto inside = [&](int cbit) {
+                    const int ux = x0 + cbit;
+                    const int tX = (ux + 800 * 1024) / 800 - 1024, ix = ux - 800 * tX;
+                    const double dxr = rb_cell_corner(ix, tX - c.txh) - sh->gx;
+                    return sqrt(dxr * dxr + dyr * dyr) < lim;
+                };
+                const double half = sqrt(lim * lim - dyr * dyr);
+                const int cg = sh->g0xu - x0;
+                lo = cg - (int)(half * 20.0) - 2;
+                hi = cg + (int)(half * 20.0) + 3;
+                while (lo < hi && !inside(lo)) lo++;
+                while (hi > lo && !inside(hi - 1)) hi--;
+                lo = max(lo, 0); hi = min(hi, 512);
+                if (hi < lo) hi = lo;
+            }
+            sh->row_lo[r] = (unsigned short)lo;
+            sh->row_hi[r] = (unsigned short)hi;
         }
+        // tiles under the bitmap window (storage tile indices), at most 2 x 2
+        const int TXa = max(x0 / 800, 0), TXb = min((x0 + 511) / 800, c.tiles_x - 1);
+        const int TYa = max(y0 < 0 ? -1 : y0 / 800, 0), TYb = min((y0 + RB_BM_ROWS - 1) / 800, c.tiles_y - 1);
+        for (int TY = TYa; TY <= TYb; TY++) {
+            for (int idx = tid; idx < RB_BM_ROWS * RB_BM_STRIDE; idx += MT_THREADS) H[idx] = 0u;
+            __syncthreads();
+            if (cp_kind & 1) {
+                for (int TX = (x0 < 0 ? 0 : TXa); TX <= TXb; TX++) {
+                    if (!((exists >> (TY * c.tiles_x + TX)) & 1ull)) continue;   // the reference walks its own tile list
+                    const double xr = cp_x - RB_TILE_LEN * (double)(TX - c.txh), yr = cp_y - RB_TILE_LEN * (double)(TY - c.tyh);
+                    int decx = 0, decy = 0;
+                    if (yr < -20.0) decy = 1; else if (xr < -20.0) decx = 1;         // gridmap.py:131-136
+                    const int jx = rb_trunc(xr / RB_TILE_LEN * 800.0 + 400.0) - decx, jy = rb_trunc(yr / RB_TILE_LEN * 800.0 + 400.0) - decy;
+                    if (jy - 36 >= 800 || jy + 36 <= 0) continue;                    // window misses the tile (rows)
+                    const int xa = max(jx - 36, 0), xb = min(jx + 36, 800);
+                    if (xa >= xb) continue;
+                    const int row = 800 * TY + jy - y0;                              // centre row in the bitmap (always inside: |c| < 11.1 m)
+                    int ca = 800 * TX + xa - x0, cb = 800 * TX + xb - x0;            // columns [ca, cb)
+                    ca = max(ca, 0); cb = min(cb, 512);
+                    if (row < 0 || row >= RB_BM_ROWS || ca >= cb) continue;
+                    uint32_t *hr = H + row * RB_BM_STRIDE;
+                    for (int wq = ca >> 5; wq <= (cb - 1) >> 5; wq++) {
+                        const int b0 = max(ca - 32 * wq, 0), b1 = min(cb - 32 * wq, 32);
+                        const uint32_t bits = (b1 >= 32 ? 0xffffffffu : ((1u << b1) - 1u)) & ~((1u << b0) - 1u);
+                        atomicOr(&hr[wq], bits);
+                    }
+                }
+            }
+            __syncthreads();
+            // prefix ORs of every block of 72 rows into Gp, suffix ORs in place (one thread per word column and block)
+            if (tid < 16 * 7) {
+                const int wq = tid & 15, blk = tid >> 4;
+                const int ra = 72 * blk, rb_ = min(ra + 72, RB_BM_ROWS);
+                uint32_t acc = 0u;
+                for (int r = ra; r < rb_; r++) { acc |= H[r * RB_BM_STRIDE + wq]; Gp[r * RB_BM_STRIDE + wq] = acc; }
+                acc = 0u;
+                for (int r = rb_ - 1; r >= ra; r--) { acc |= H[r * RB_BM_STRIDE + wq]; H[r * RB_BM_STRIDE + wq] = acc; }
+            }
+            __syncthreads();
+            // rows of this tile row: window [r - 35, r + 36] of centre rows, clipped to 11.5 m; into raw (+ block list)
+            const int rlo = max(800 * TY - y0, 0), rhi = min(800 * TY + 800 - y0, RB_BM_ROWS);
+            for (int idx = tid; idx < (rhi - rlo) * 16; idx += MT_THREADS) {
+                const int r = rlo + (idx >> 4), wq = idx & 15;
+                const int a_ = r - 35, b_ = min(r + 36, RB_BM_ROWS - 1);
+                uint32_t v;
+                if (a_ <= 0) v = Gp[b_ * RB_BM_STRIDE + wq];
+                else if (a_ / 72 == b_ / 72) v = H[a_ * RB_BM_STRIDE + wq];
+                else v = H[a_ * RB_BM_STRIDE + wq] | Gp[b_ * RB_BM_STRIDE + wq];
+                const int lo = (int)sh->row_lo[r] - 32 * wq, hi = (int)sh->row_hi[r] - 32 * wq;
+                uint32_t keep = 0u;
+                if (hi > 0 && lo < 32) keep = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << max(lo, 0)) - 1u);
+                v &= keep;
+                if (v) {
+                    const int rho = r + dy0 + 1;
+                    raw[rho * RB_RAW_STRIDE + wq + 1] = v;
+                    atomicOr(&sh->need[rho >> 5], 1u << (wq + 1));
+                }
+            }
+            __syncthreads();
+        }
+        if (tid < MT_NBLK) {
+            const int rb = tid / RB_RAW_STRIDE, wc = tid - rb * RB_RAW_STRIDE;
+            if ((sh->need[rb] >> wc) & 1u) sh->blist[atomicAdd(&sh->nblk, 1)] = (unsigned short)tid;
+        }
+        MT_CLK(3)
+        __syncthreads();
+        const int nblk = sh->nblk;
+        unsigned char *rawb = reinterpret_cast<unsigned char *>(raw);
         // One warp per block, one lane per 32-byte sector (8 cells of 4 rows): whole sectors
         // in flight, MT_GATHER_U blocks per round, page-table entries from shared memory (one
         // global-memory latency per round).  Thresholded bytes go straight to their place.
@@ -892,10 +945,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             for (int u = 0; u < MT_GATHER_U; u++) {
                 if (row0[u] < 0) continue;
                 unsigned char *dst = rawb + ((size_t)row0[u] * RB_RAW_STRIDE + wcs[u]) * 4 + sx;
-                dst[0] = (unsigned char)(mt_pack4(v[u][0].x) | (mt_pack4(v[u][0].y) << 4));
-                dst[RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][0].z) | (mt_pack4(v[u][0].w) << 4));
-                dst[2 * RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][1].x) | (mt_pack4(v[u][1].y) << 4));
-                dst[3 * RB_RAW_STRIDE * 4] = (unsigned char)(mt_pack4(v[u][1].z) | (mt_pack4(v[u][1].w) << 4));
+                dst[0] &= (unsigned char)(mt_pack4(v[u][0].x) | (mt_pack4(v[u][0].y) << 4));
+                dst[RB_RAW_STRIDE * 4] &= (unsigned char)(mt_pack4(v[u][0].z) | (mt_pack4(v[u][0].w) << 4));
+                dst[2 * RB_RAW_STRIDE * 4] &= (unsigned char)(mt_pack4(v[u][1].x) | (mt_pack4(v[u][1].y) << 4));
+                dst[3 * RB_RAW_STRIDE * 4] &= (unsigned char)(mt_pack4(v[u][1].z) | (mt_pack4(v[u][1].w) << 4));
             }
         }
     }
@@ -1165,7 +1218,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     bool nd_accept = false;
     if (c.refine && valid) {
         double qx = 0.0, qy = 0.0;
-        const bool has = has_beam && mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy);
+        double ax_, ay_;
+        const bool has = has_beam && (mt_curr_point(c, sh, exists, b_d, b_px, b_py, adj, qx, qy, ax_, ay_) & 2);
         double *red = reinterpret_cast<double *>(bmg), *ctl = red + MT_WARPS * NDT_TERMS;   // bmg is dead after phase A
         ndt_refine(bm, red, ctl, sh->g0xu - sh->x0, sh->fx, sh->fy, has, qx, qy, nd_p[0], nd_p[1], nd_p[2]);
         nd_p[0] = ctl[1]; nd_p[1] = ctl[2]; nd_p[2] = ctl[3]; nd_S = ctl[4]; nd_evals = (int)ctl[5];
