@@ -215,8 +215,9 @@ int rbpf_clear_errors(rbpf_handle h);
 int rbpf_stats(rbpf_handle h, rbpf_stats_t *out);
 /* Where the matcher kernel (the MATLAB matchScanCustom call of hybridmap.py:244-251) spends its time:
  * SM clocks since creation, out[16].  Slots 0-8 are summed over CTAs (one search each, thread 0 between
- * barriers): 0 frame + curr points, 1 map gather + threshold, 2 3x3 dilation, 3 group-bound dilation,
- * 4 seed rotations + group bounds, 5 group ranking, 6 member rotations, 7 covariance, 8 NDT stage.
+ * barriers): 0 frame + curr points, 1 map gather + threshold, 2 both dilations, 3 reference-set mask
+ * (hybridmap.py:230-239), 4 seed rotations + group bounds, 5 group ranking, 6 member rotations, 7 covariance,
+ * 8 NDT stage.
  * Slots 10-12 are summed over warps (busy time, without barrier waits): seeds, group bounds, member
  * rotations; 13-15 are the points those three phases visited. */
 int rbpf_match_phase_clocks(rbpf_handle h, uint64_t *out16);

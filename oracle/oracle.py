@@ -80,6 +80,8 @@ def lib():
         L.orc_filter_set_scan.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_filter_motion.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, _dp]
         L.orc_filter_integrate.argtypes = [C.c_void_p]
+        L.orc_rb_sincos.argtypes = [_dp, C.c_int, _dp, _dp]
+        L.orc_rb_exp.argtypes = [_dp, C.c_int, _dp]
         L.orc_filter_map_update.argtypes = [C.c_void_p, _dp]
         L.orc_filter_map_update_guesses.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int]
         L.orc_propose_pdf.argtypes = [_dp, _dp, _dp, C.c_int, _dp]
@@ -246,6 +248,21 @@ def propose(mean, cov, z):
     prs = np.empty(K)
     lib().orc_propose(_d(mean)[1], _d(np.asarray(cov).reshape(9))[1], zp, K, _d(g)[1], _d(prs)[1])
     return g, prs
+
+
+def rb_sincos(a):
+    """csrc/rb_math.h rb_sincos over an array (the routine the CUDA kernels and this oracle share)."""
+    a, ap = _d(a)
+    s, c = np.empty_like(a), np.empty_like(a)
+    lib().orc_rb_sincos(ap, a.size, _d(s)[1], _d(c)[1])
+    return s, c
+
+
+def rb_exp(x):
+    x, xp = _d(x)
+    out = np.empty_like(x)
+    lib().orc_rb_exp(xp, x.size, _d(out)[1])
+    return out
 
 
 def propose_numpy(mean, cov, K=30):

@@ -45,6 +45,10 @@
  * arguments (tests/test_rb_math.py). */
 #include "../thesis_b200/csrc/rb_math.h"
 
+/* the shared routines, exported for tests/test_rb_math.py */
+void orc_rb_sincos(const double *a, int n, double *sn, double *cs) { for (int i = 0; i < n; i++) rb_sincos(a[i], &sn[i], &cs[i]); }
+void orc_rb_exp(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = rb_exp(x[i]); }
+
 #define CS 0.05            /* hybridmap.py:67  cell size, metres */
 #define TILE_LEN 40        /* hybridmap.py:68  tile side, metres (an int in the reference) */
 #define DIM 800            /* gridmap.py:31    round(40/0.05) */

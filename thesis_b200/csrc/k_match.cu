@@ -825,17 +825,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             int lo = 0, hi = 0;
             const double lim = RB_MATCH_MAX_R + 0.5;
             if (fabs(dyr) < lim) {
+                const double dy2 = dyr * dyr;
                 auto inside = [&](int cbit) {
                     const int ux = x0 + cbit;
                     const int tX = (ux + 800 * 1024) / 800 - 1024, ix = ux - 800 * tX;
                     const double dxr = rb_cell_corner(ix, tX - c.txh) - sh->gx;
-                    return sqrt(dxr * dxr + dyr * dyr) < lim;
+                    return sqrt(dxr * dxr + dy2) < lim;
                 };
-                const double half = sqrt(lim * lim - dyr * dyr);
+                // column c is dx = (c - cg) * 0.05 - fx away from the guess (0 <= fx < 0.05): the interval ends lie
+                // within one column of these estimates; the float64 predicate of the oracle decides
+                const double half = sqrt(lim * lim - dy2) * 20.0;
                 const int cg = sh->g0xu - x0;
-                lo = cg - (int)(half * 20.0) - 2;
-                hi = cg + (int)(half * 20.0) + 3;
+                lo = cg - (int)half;
+                hi = cg + (int)half + 2;
+                if (inside(lo - 1)) lo--;
                 while (lo < hi && !inside(lo)) lo++;
+                if (inside(hi)) hi++;
                 while (hi > lo && !inside(hi - 1)) hi--;
                 lo = max(lo, 0); hi = min(hi, 512);
                 if (hi < lo) hi = lo;
@@ -877,9 +882,21 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                 const int wq = tid & 15, blk = tid >> 4;
                 const int ra = 72 * blk, rb_ = min(ra + 72, RB_BM_ROWS);
                 uint32_t acc = 0u;
-                for (int r = ra; r < rb_; r++) { acc |= H[r * RB_BM_STRIDE + wq]; Gp[r * RB_BM_STRIDE + wq] = acc; }
+                for (int r = ra; r < rb_; r += 8) {                         // eight loads in flight, then the OR chain
+                    uint32_t v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = r + e < rb_ ? H[(r + e) * RB_BM_STRIDE + wq] : 0u;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { acc |= v[e]; if (r + e < rb_) Gp[(r + e) * RB_BM_STRIDE + wq] = acc; }
+                }
                 acc = 0u;
-                for (int r = rb_ - 1; r >= ra; r--) { acc |= H[r * RB_BM_STRIDE + wq]; H[r * RB_BM_STRIDE + wq] = acc; }
+                for (int r = rb_ - 1; r >= ra; r -= 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = r - e >= ra ? H[(r - e) * RB_BM_STRIDE + wq] : 0u;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { acc |= v[e]; if (r - e >= ra) H[(r - e) * RB_BM_STRIDE + wq] = acc; }
+                }
             }
             __syncthreads();
             // rows of this tile row: window [r - 35, r + 36] of centre rows, clipped to 11.5 m; into raw (+ block list)

@@ -176,13 +176,23 @@ __global__ void pull_claim_kernel(RbCtx c, RbPeers peers, uint32_t *mark, uint32
     if (!pull_source(c, warp, r, s)) return;
     const uint32_t *pt = peers.p[r].pt + (size_t)s * c.nsub;
     uint32_t *mk = mark + (size_t)r * c.pool_tiles;
-    for (int e = lane; e < c.nsub; e += 32) {
-        const uint32_t t = pt[e];
-        if (t == RB_NONE || t >= c.pool_tiles) continue;
-        if (atomicCAS(&mk[t], RB_NONE, 0xFFFFFFFEu) == RB_NONE) {
-            const int idx = atomicAdd(count, 1);
-            if ((uint32_t)idx < c.pool_tiles) { list[idx] = t; list_rank[idx] = (unsigned char)r; }
-            else atomicExch(&c.flags->pool_exhausted, 1);
+    uint32_t *raw_local = c.pt2 + (size_t)warp * c.nsub;                     // the slot's page table: remote indices for now
+    // eight remote loads in flight per lane (a load over NVLink takes microseconds), then the claims
+    for (int e0 = 0; e0 < c.nsub; e0 += 32 * 8) {
+        uint32_t t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int e = e0 + 32 * k + lane; t[k] = e < c.nsub ? pt[e] : RB_NONE; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int e = e0 + 32 * k + lane;
+            if (e >= c.nsub) continue;
+            raw_local[e] = t[k];
+            if (t[k] == RB_NONE || t[k] >= c.pool_tiles) continue;
+            if (atomicCAS(&mk[t[k]], RB_NONE, 0xFFFFFFFEu) == RB_NONE) {
+                const int idx = atomicAdd(count, 1);
+                if ((uint32_t)idx < c.pool_tiles) { list[idx] = t[k]; list_rank[idx] = (unsigned char)r; }
+                else atomicExch(&c.flags->pool_exhausted, 1);
+            }
         }
     }
 }
@@ -208,7 +218,11 @@ __global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeers peers,
         if (t != RB_NONE) {
             const uint4 *src = reinterpret_cast<const uint4 *>(peers.p[r].pool + (size_t)rt * RB_SUB_BYTES);
             uint4 *dst = reinterpret_cast<uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES);
-            for (int q = threadIdx.x; q < RB_SUB_BYTES / 16; q += blockDim.x) dst[q] = src[q];
+            uint4 v[7];                                                      // 1,600 x 16 B over 256 threads: all loads first
+#pragma unroll
+            for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) v[k] = src[q]; }
+#pragma unroll
+            for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) dst[q] = v[k]; }
         }
         __syncthreads();
     }
@@ -229,11 +243,10 @@ __global__ void pull_place_kernel(RbCtx c, RbPeers peers, const uint32_t *__rest
         c.exists2[j] = peer.exists[s];
         c.weight[j] = 1.0;                                                   // main.py:77-78
     }
-    const uint32_t *src = peer.pt + (size_t)s * c.nsub;
     const uint32_t *mk = mark + (size_t)r * c.pool_tiles;
-    uint32_t *dst = c.pt2 + (size_t)j * c.nsub;
+    uint32_t *dst = c.pt2 + (size_t)j * c.nsub;                              // holds the remote indices (pull_claim_kernel)
     for (int e = lane; e < c.nsub; e += 32) {
-        const uint32_t rt = src[e];
+        const uint32_t rt = dst[e];
         uint32_t t = RB_NONE;
         if (rt != RB_NONE && rt < c.pool_tiles) {
             t = mk[rt];

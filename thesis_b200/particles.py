@@ -259,7 +259,7 @@ class ParticleSet:
         self._ck(self._lib.rbpf_stats(self._h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in s._fields_}
 
-    MATCH_PHASES = ("frame_points", "gather", "dilate3", "dilate_group", "seeds_bounds", "rank", "members",
+    MATCH_PHASES = ("frame_points", "gather", "dilations", "ref_mask", "seeds_bounds", "rank", "members",
                     "covariance", "ndt")
 
     def match_phase_clocks(self):
