@@ -32,10 +32,13 @@ UNIT = "updates/s"
 # compulsory cells of the matcher footprint for a 180-degree sweep,
 # (240/360) * pi * 11.7^2 / 0.0025 cells, 1 byte each (int8 tenths)
 MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
-# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch over 8,192 particles
-# (profiles/r1_full_8192p_final_raw.csv), per update; below the algorithmic figure because
-# particles that share sub-tiles after a resample hit in L2
-MATCH_DRAM_BYTES_PER_UPDATE_NCU = (853.2e6 + 5.4e6) / 8192
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 8,192 particles, per update (`ncu --set full`,
+# profiles/r2_*_raw.csv).  The matcher's is below its algorithmic figure: only blocks under the reference-set mask
+# are fetched and particles that share sub-tiles after a resample hit in L2.
+MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.79e6 + 5.21e6) / 8192
+CAST_DRAM_BYTES_PER_UPDATE_NCU = (473.00e6 + 318.49e6) / 8192
+WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.33e6 + 3.08e6) / 8192
+PREPARE_DRAM_BYTES_PER_UPDATE_NCU = (134.72e6 + 91.77e6) / 8192
 
 
 def parse():
@@ -373,10 +376,10 @@ def run_b200(args):
     per_update = {
         "match_kernel": ("match", MATCH_BYTES_PER_UPDATE, "int8 cells of the 240-degree sector of radius 11.7 m the search can reach",
                          MATCH_DRAM_BYTES_PER_UPDATE_NCU),
-        "raycast_cast_kernel": ("raycast_cast", 2.0 * a_r, "read + write of the int8 cells under the rays (A_r = sum min(r, 15 m) / 5 cm)", None),
+        "raycast_cast_kernel": ("raycast_cast", 2.0 * a_r, "read + write of the int8 cells under the rays (A_r = sum min(r, 15 m) / 5 cm)", CAST_DRAM_BYTES_PER_UPDATE_NCU),
         "raycast_prepare_kernel": ("raycast_prepare", (2.0 * cow + fresh) * 25600.0 / n_local,
-                                   "copy-on-write: 2 x 25,600 B per shared sub-tile made private, 25,600 B per fresh one", None),
-        "weight_kernel": ("weight", 32.0 * args.beams, "one 32-byte sector per beam (the 30 samples of a beam fall into the same cells)", None),
+                                   "copy-on-write: 2 x 25,600 B per shared sub-tile made private, 25,600 B per fresh one", PREPARE_DRAM_BYTES_PER_UPDATE_NCU),
+        "weight_kernel": ("weight", 32.0 * args.beams, "one 32-byte sector per beam (the 30 samples of a beam fall into the same cells)", WEIGHT_DRAM_BYTES_PER_UPDATE_NCU),
     }
     rooflines = {}
     for kname, (stage, bpu, what, dram) in per_update.items():
@@ -386,7 +389,8 @@ def run_b200(args):
                             "traffic": dram * n_local if dram else None, "algorithmic_bytes_per_update": bpu, "what": what,
                             "updates_per_launch": n_local, "launch_ms": ms_k, "peak_source": peak_src}
     dominant = max(rooflines.values(), key=lambda r: r["launch_ms"])
-    rooflines["match_kernel"]["traffic_source"] = "ncu --set full on an 8,192-particle launch (profiles/), scaled per update"
+    for r_ in rooflines.values():
+        r_["traffic_source"] = "ncu --set full on an 8,192-particle launch (profiles/r2_*_raw.csv), scaled per update"
     rooflines["match_kernel"]["note"] = ("the correlative search is bound by shared-memory wavefronts and the ALU pipe (ncu: 71 % / 72 % "
                                          "of peak), not by HBM; see DESIGN.md")
     line = {

@@ -20,6 +20,8 @@
 //                    lane-parallel (one beam per lane) and broadcast; chunks whose
 //                    cells are all plain "empty" updates take a fast path; a cell
 //                    whose clamped value does not change is not stored back.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #ifndef RC_WARPS
@@ -492,6 +494,70 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     }
 }
 
+// ------------------------------------------------------- atomics variant --
+// EXPERIMENT, not the product path (RBPF_CAST_ATOMICS=1): the variant BASELINE.json's north_star names.
+// The beams of a particle are split over the four warps of a CTA and every cell update is a
+// compare-and-swap on the 32-bit word that holds the byte (there are no byte atomics), in whatever
+// order the warps get there.  It measures the best case of an atomic formulation: it does NOT replay
+// the reference's beam order, so a cell that both saturates and is touched by several beams of one
+// sweep can end up different -- an exact version would add a membership test against
+// the <= 2 B order-sensitive cells to every update and a sequential replay of those.  Numbers in
+// profiles/README.md; the ordered kernel above stays the default because it is exact and not slower.
+__global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_atomic_kernel(RbCtx c)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x;
+    if (p >= c.N || c.flags->pool_exhausted) return;
+    double x, y, cs_, sn_;
+    int sx, sy;
+    if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) return;
+    const uint32_t *pt = c.pt + (size_t)p * c.nsub;
+    const unsigned long long ex_mask = c.exists[p];
+    unsigned long long ex_new = 0ull;
+    unsigned dropped = 0;
+    for (int j = warp; j < c.B; j += RC_WARPS) {
+        const Ray r = ray_of_beam(c, j, x, y, cs_, sn_, sx, sy);
+        if (r.len == 0) continue;
+        const RayStep st = ray_step(sx, sy, r);
+        const uint32_t pex = rb_write_lut(c.lutx, r.ex, c.txh), pey = rb_write_lut(c.luty, r.ey, c.tyh);
+        const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(RB_LUT_TILE(pey) * c.tiles_x + RB_LUT_TILE(pex));
+        for (int n = lane; n < r.len; n += 32) {
+            int kx, ky;
+            ray_cell(sx, sy, st, n, kx, ky);
+            const uint32_t px_ = rb_write_lut(c.lutx, kx, c.txh), py_ = rb_write_lut(c.luty, ky, c.tyh);
+            if (px_ == RB_NONE || py_ == RB_NONE) { dropped++; continue; }
+            const int sub = (int)RB_LUT_SUB(py_) * c.subs_x + (int)RB_LUT_SUB(px_);
+            const int tile = (int)(RB_LUT_TILE(py_) * c.tiles_x + RB_LUT_TILE(px_));
+            if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;
+            const uint32_t tt = pt[sub];
+            if (tt == RB_NONE) continue;
+            int ops = (r.occ && n == r.len - 1) ? 2 : 1;
+            if (r.occ && n == r.len - 2 && tile == end_tile) ops |= 4;
+            int8_t *a = c.pool + (size_t)tt * RB_SUB_BYTES + RB_LUT_OFF(py_) + RB_LUT_OFF(px_);
+            uint32_t *wp = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+            const int sh8 = (int)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
+            uint32_t old = *wp;
+            for (;;) {
+                const int t = (int)(int8_t)(old >> sh8);
+                const int v = apply_ops(t, ops);
+                if (v == t) break;                                           // saturated: nothing to write
+                const uint32_t want = (old & ~(0xffu << sh8)) | ((uint32_t)(uint8_t)(int8_t)v << sh8);
+                const uint32_t seen = atomicCAS(wp, old, want);
+                if (seen == old) break;
+                old = seen;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ex_new |= __shfl_xor_sync(0xffffffffu, ex_new, o);
+        dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+    }
+    if (lane == 0) {
+        if (ex_new) atomicOr(&c.exists[p], ex_new);
+        if (dropped) atomicAdd(&c.stats->cells_dropped, (unsigned long long)dropped);
+    }
+}
+
 void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s)
 {
     raycast_prepare_kernel<<<(c.N + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, s>>>(c);
@@ -499,6 +565,11 @@ void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s)
 
 void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
 {
+    static const int use_atomics = getenv("RBPF_CAST_ATOMICS") && atoi(getenv("RBPF_CAST_ATOMICS")) > 0;
+    if (use_atomics) {                                            // experiment only, see raycast_cast_atomic_kernel
+        raycast_cast_atomic_kernel<<<c.N, RC_WARPS * 32, 0, s>>>(c);
+        return;
+    }
     const int blocks = (c.N + RC_WARPS - 1) / RC_WARPS;
 #ifdef RC_SMEM_LUT   // measured slower on B200 (5.55 vs 4.02 ms at 16,384 particles): staging 32 KB per CTA costs more than the L1 hits it saves
     const size_t lut_bytes = sizeof(uint32_t) * 800 * (size_t)(c.tiles_x + c.tiles_y);

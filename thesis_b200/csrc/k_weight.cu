@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
                     if (d < RB_W_MAX_R && d > RB_W_MIN_R) {
                         double gx, gy;
                         rb_xform(cs_, sn_, g0, g1, c.px[jj], c.py[jj], gx, gy);
-                        rb_locate(c, gx, gy, sub[u], off[u]);
+                        rb_locate_fast(c, gx, gy, sub[u], off[u]);
                     }
                 }
             }
