@@ -400,7 +400,8 @@ def run_b200(args):
         "config": dict(workload_config(args, world), burnin_scans=args.burnin,
                        ray_cells_per_scan=a_r, pool_subtiles=pool, cow_copies_per_scan=cow, fresh_subtiles_per_scan=fresh,
                        unique_subtile_fraction=1.0 - st["shared_refs"] / max(st["total_refs"], 1),
-                       pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], resamples=st["resamples"],
+                       pool_in_use=st["pool_in_use"], match_failed=st["match_failed"], match_failed_zero_correction=st["match_failed_zero"],
+                       match_failed_fraction=st["match_failed"] / max(1, n_local * (s - 1)), resamples=st["resamples"],
                        match_searches_run_fraction=st["match_runs"] / max(1, n_local * (s - 1)),
                        match_scoring_passes_per_update=st["match_evals"] / max(1, st["match_runs"]),
                        match_exhaustive_passes_per_update=231, ndt_refine=bool(args.refine),

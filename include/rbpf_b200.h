@@ -92,6 +92,8 @@ typedef struct {
     uint64_t match_evals;     /* bitmap scoring passes of the matcher (group bounds + member rotations; exhaustive = 231 per match) */
     uint64_t ndt_evals;       /* NDT score evaluations of the refinement stage (cumulative, searches actually run) */
     uint64_t ndt_accepted;    /* searches whose refined pose replaced the grid pose (matchScanCustom.m:38-41) */
+    uint64_t match_failed_zero; /* of match_failed: the optimum was the zero correction, which isValidPose rejects
+                                   (matchScanCustom.m:55); the others sit on the border of the search window (:53-54) */
 } rbpf_stats_t;
 
 /* Replaces `particles = [Robot(eng) for _ in range(NUM_PARTICLES)]` (main.py:87,

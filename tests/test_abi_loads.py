@@ -56,4 +56,4 @@ def test_config_struct_matches_header(lib):
     from thesis_b200 import _lib
 
     assert C.sizeof(_lib.RbpfConfig) == 56
-    assert C.sizeof(_lib.RbpfStats) == 120
+    assert C.sizeof(_lib.RbpfStats) == 128

@@ -39,6 +39,7 @@ class RbpfStats(C.Structure):
         ("refcount_sum", C.c_uint64), ("match_visits", C.c_uint64), ("match_points", C.c_uint64),
         ("match_runs", C.c_uint64),
         ("match_evals", C.c_uint64), ("ndt_evals", C.c_uint64), ("ndt_accepted", C.c_uint64),
+        ("match_failed_zero", C.c_uint64),
     ]
 
 

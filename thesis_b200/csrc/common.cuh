@@ -62,6 +62,7 @@ struct RbStats {                            // device-side counters
         ndt_evals, ndt_accepted;
     // match_kernel phase split (SM clocks summed over CTAs resp. warps, see rbpf_match_phase_clocks)
     unsigned long long match_clk[16];
+    unsigned long long match_failed_zero;   // failed matches whose optimum is the zero correction (matchScanCustom.m:55)
 };
 
 struct RbFlags {                            // device-side status words

@@ -685,6 +685,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
     out->match_runs = s.match_runs;
     out->ndt_evals = s.ndt_evals;
     out->ndt_accepted = s.ndt_accepted;
+    out->match_failed_zero = s.match_failed_zero;
     return RBPF_OK;
 }
 

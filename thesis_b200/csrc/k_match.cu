@@ -1272,7 +1272,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             for (int q = 0; q < 9; q++) oc[q] = nan;
             c.m_score[p] = 0.0;
-            if (!slice_out) atomicAdd(&c.stats->match_failed, 1ull);
+            if (!slice_out) {
+                atomicAdd(&c.stats->match_failed, 1ull);
+                if (sh->ok && bi == 0 && bj == 0 && bk == 0) atomicAdd(&c.stats->match_failed_zero, 1ull);
+            }
         } else {
             const double W0 = (double)sh->mom[0], T0 = (double)sh->mom[6];
             const double mx = (double)sh->mom[1] / W0, my = (double)sh->mom[2] / W0, mt = (double)sh->mom[7] / T0;
@@ -1315,7 +1318,11 @@ __global__ void __launch_bounds__(256) match_copy_dups_kernel(RbCtx c)
     for (int q = 0; q < 2; q++) c.m_refine[2 * (size_t)p + q] = c.m_refine[2 * (size_t)r + q];
     c.m_score[p] = c.m_score[r];
     c.m_valid[p] = c.m_valid[r];
-    if (!c.m_valid[r]) atomicAdd(&c.stats->match_failed, 1ull);
+    if (!c.m_valid[r]) {
+        atomicAdd(&c.stats->match_failed, 1ull);
+        const int *ob = c.m_best + 4 * (size_t)r;
+        if (ob[0] == 0 && ob[1] == 0 && ob[2] == 0) atomicAdd(&c.stats->match_failed_zero, 1ull);
+    }
 }
 
 void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)

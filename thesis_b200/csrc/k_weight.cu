@@ -115,7 +115,13 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
         rb_sincos(g2, &sn_, &cs_);
         int S = 0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-        // WT_INFLIGHT beams in flight: locate (ALU) -> page-table entries -> cells
+        // WT_INFLIGHT beams in flight: locate (ALU) -> page-table entries -> cells.
+        // The cell of a beam end is floor(20 g) per axis (rb_locate_fast); here 20 g comes from two fused
+        // multiply-adds on the pre-scaled frame -- within 1e-11 of 20 x the reference's own float64 chain,
+        // so the floor is the same unless 20 g lies within 1e-6 of an integer, and then the reference's
+        // expressions are replayed (rb_xform + rb_locate).
+        const double c20 = cs_ * 20.0, s20 = sn_ * 20.0, x20 = g0 * 20.0, y20 = g1 * 20.0;
+        const int offx = 400 + 800 * c.txh, offy = 400 + 800 * c.tyh;
         for (int j = 0; j < c.B; j += WT_INFLIGHT) {
             int sub[WT_INFLIGHT], off[WT_INFLIGHT];
 #pragma unroll
@@ -125,9 +131,21 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
                 if (jj < c.B) {
                     const double d = c.dist[jj];
                     if (d < RB_W_MAX_R && d > RB_W_MIN_R) {
-                        double gx, gy;
-                        rb_xform(cs_, sn_, g0, g1, c.px[jj], c.py[jj], gx, gy);
-                        rb_locate_fast(c, gx, gy, sub[u], off[u]);
+                        const double bpx = c.px[jj], bpy = c.py[jj];
+                        const double vx = fma(c20, bpx, fma(-s20, bpy, x20)), vy = fma(s20, bpx, fma(c20, bpy, y20));
+                        const int kx = __double2int_rd(vx), ky = __double2int_rd(vy);
+                        const double dx = vx - (double)kx, dy = vy - (double)ky;
+                        if (dx > 1e-6 && dx < 1.0 - 1e-6 && dy > 1e-6 && dy < 1.0 - 1e-6 && fabs(vx) < 1e6 && fabs(vy) < 1e6) {
+                            const int ux = kx + offx, uy = ky + offy;
+                            if ((unsigned)ux < (unsigned)c.ux_max && (unsigned)uy < (unsigned)c.uy_max) {
+                                sub[u] = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
+                                off[u] = RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB);
+                            }
+                        } else {
+                            double gx, gy;
+                            rb_xform(cs_, sn_, g0, g1, bpx, bpy, gx, gy);
+                            rb_locate(c, gx, gy, sub[u], off[u]);
+                        }
                     }
                 }
             }
