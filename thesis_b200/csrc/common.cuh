@@ -118,6 +118,9 @@ struct RbCtx {
     int n_prev;
     // write-path LUT (lattice cell k -> storage coordinate)
     const uint32_t *lutx, *luty;            // per axis, packed (RB_LUT_*)
+    const uint32_t *clut;                   // cast LUT (k_raycast.cu, version 2): x entries then y entries, packed so that x + y is
+                                            // offset (0-14) | page-table slot (15-25) | aliasing flags (x: 30/31, y: 28/29)
+    int *cast_work;                         // particle counter of the persistent cast kernel (zeroed by raycast_prepare)
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch
     double *plan_scal;                      // slice, start of the last plan (main.py:57,59)

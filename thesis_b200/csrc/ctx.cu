@@ -21,7 +21,7 @@ struct rbpf_ctx {
     std::vector<void *> allocs;
     double *d_px, *d_py, *d_dist;  // scan
     double *d_rot;                 // rotation table
-    uint32_t *d_lutx, *d_luty;
+    uint32_t *d_lutx, *d_luty, *d_clut;
     double *d_prev;                // 2 * RB_MAXB: previous scan endpoints (x then y)
     double *h_prev;                // pinned staging
     double *d_z;                   // N*K*3 host-supplied normals
@@ -213,6 +213,8 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_rot, 2 * (2 * d.nk + 1));
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
+    A(h->d_clut, 800 * (d.tiles_x + d.tiles_y));
+    A(d.cast_work, 4);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
     A(d.w_all, d.n_global); A(d.plan_scal, 4); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);
@@ -251,6 +253,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     d.rot_cs = h->d_rot;
     d.lutx = h->d_lutx;
     d.luty = h->d_luty;
+    d.clut = h->d_clut;
 
     std::vector<double> rot(2 * (2 * d.nk + 1));
     for (int k = -d.nk; k <= d.nk; k++) {
@@ -260,7 +263,16 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     std::vector<uint32_t> lutx, luty;
     build_lut(d.txh, lutx, false);
     build_lut(d.tyh, luty, true);
+    // cast LUT: the same storage coordinates re-packed so that the entries of the two axes add up to one word
+    std::vector<uint32_t> clut(lutx.size() + luty.size());
+    for (size_t q = 0; q < lutx.size(); q++)
+        clut[q] = RB_LUT_OFF(lutx[q]) | (RB_LUT_SUB(lutx[q]) << 15) | (((lutx[q] >> RB_LUT_NEXT_BIT) & 1u) << 30) | (((lutx[q] >> RB_LUT_PREV_BIT) & 1u) << 31);
+    for (size_t q = 0; q < luty.size(); q++)
+        clut[lutx.size() + q] = RB_LUT_OFF(luty[q]) | ((RB_LUT_SUB(luty[q]) * (uint32_t)d.subs_x) << 15) |
+                                (((luty[q] >> RB_LUT_NEXT_BIT) & 1u) << 28) | (((luty[q] >> RB_LUT_PREV_BIT) & 1u) << 29);
+    if (d.nsub > 2048) return fail(RBPF_ERR_ARG, "world too large for the cast LUT (more than 2048 sub-tiles)");
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_clut, clut.data(), clut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_lutx, lutx.data(), lutx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_luty, luty.data(), luty.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "table upload failed");

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_prepare_kernel(RbCtx c)
     __shared__ uint32_t mask_s[RC_WARPS][52];                      // 64 tiles * 25 sub-tiles = 1600 bits
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * RC_WARPS + warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *c.cast_work = 0;      // work counter of raycast_cast2_kernel, which runs next
     if (p >= c.N) return;
     uint32_t *mask = mask_s[warp];
     const int nwords = (c.nsub + 31) >> 5;
@@ -494,6 +495,393 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
     }
 }
 
+// ------------------------------------------------------- cast, version 2 --
+// Same update order, a third of the instructions.  What changed against raycast_cast_kernel:
+//   * persistent CTAs (grid = resident CTAs), warps fetch particles from a work counter, so the
+//     two cast LUTs (rb_cast_lut: 800 entries per reference tile and axis) are staged in shared
+//     memory once per CTA instead of once per four particles;
+//   * the cast LUT entries of the two axes ADD UP to one word: bits 0-14 byte offset inside the
+//     sub-tile, bits 15-25 page-table slot, bits 28-31 the aliasing flags (x: 30/31, y: 28/29).
+//     One compare of (word & key mask) against the cached slot finds both a sub-tile change and
+//     an aliasing pair along the major axis -- the only two things the empty-cell path cares about;
+//   * the minor coordinate of cell n is the closed form floor((n d2 + D) / D2) by a magic
+//     multiply (exact: n <= 300 cells after the 15 m clip), no error term is carried;
+//   * a ray is ceil(len / 32) chunks: "empty" chunks over [0, len - 32) and ONE tail chunk
+//     [len - 32, len) that holds the end / nearby cells in lanes 31 / 30;
+//   * per-beam constants go through shared memory (two 16-byte broadcasts per beam).
+// Rays that leave the world take cast_general_ray (the old per-cell path).
+#ifndef RC2_WARPS
+#define RC2_WARPS 8
+#endif
+#ifndef RC2_MINBLOCKS
+#define RC2_MINBLOCKS 4
+#endif
+
+#define RC2_SUBMASK 0x03ff8000u
+#define RC2_OFFMASK 0x00007fffu
+
+struct CastRec {     // per-beam constants, 32 bytes
+    int w0;          // len (bits 0-11) | occ << 12 | steep << 13 | inside << 14 | (smaj < 0) << 15 | (smin + 1) << 16 | near_ok << 18
+    int d2;          // 2 * minor extent
+    int D2;          // 2 * major extent (>= 2)
+    unsigned magic;  // ceil(2^32 / D2)
+    int bmaj, bmin;  // index into the staged LUTs of the major / minor coordinate of cell 0
+    int end_tile;    // reference tile of the end cell or -1 (general path only)
+    int ex, ey;      // (general path only: end cell)  -- ey overlays the padding word
+};
+
+// The old per-cell path for rays with a cell outside the world (rare: the world is sized for the log).
+// Scalars in, the newly touched reference tiles out: nothing of the caller has its address taken.
+__device__ __noinline__ unsigned long long cast_general_ray(int8_t *pool, const uint32_t *pt, const uint32_t *lutx, const uint32_t *luty,
+                                                            RbFlags *flags, RbStats *stats, int txh, int tyh, int subs_x, int tiles_x,
+                                                            int lane, int sx, int sy, int len, int occ, int ex, int ey, int end_tile,
+                                                            unsigned long long ex_mask)
+{
+    unsigned long long ex_new = 0ull;
+    unsigned dropped = 0;
+    Ray r;
+    r.ex = ex; r.ey = ey; r.len = len; r.occ = occ;
+    const RayStep st = ray_step(sx, sy, r);
+    const int steep = st.steep, smaj = st.smaj, smin = st.smin;
+    const int D2 = (int)st.D2, d2 = (int)st.d2;
+    const int step_q = (int)((32u * st.d2) / st.D2), step_e = (int)(32u * st.d2 - (unsigned)step_q * st.D2);
+    const int n_occ = occ ? len - 1 : -1, n_near = occ ? len - 2 : -1;
+    const uint32_t *lmaj = steep ? luty : lutx, *lmin = steep ? lutx : luty;
+    const int hmaj = steep ? tyh : txh, hmin = steep ? txh : tyh;
+    int n = lane, e, kmaj, kmin;
+    {
+        const unsigned num = (unsigned)lane * st.d2 + st.D;
+        const unsigned m = num / st.D2;
+        e = (int)(num - m * st.D2);
+        kmaj = (steep ? sy : sx) + smaj * lane;
+        kmin = (steep ? sx : sy) + smin * (int)m;
+    }
+    int cached_sub = -1;
+    int8_t *cached_base = nullptr;
+    for (int n0 = 0; n0 < len; n0 += 32) {
+        int ops = 0;
+        int8_t *addr = nullptr;
+        if (n < len) {
+            const uint32_t pmaj = rb_write_lut(lmaj, kmaj, hmaj), pmin = rb_write_lut(lmin, kmin, hmin);
+            if (pmaj == RB_NONE || pmin == RB_NONE) {
+                dropped++;
+            } else {
+                const uint32_t px_ = steep ? pmin : pmaj, py_ = steep ? pmaj : pmin;
+                const int sub = (int)RB_LUT_SUB(py_) * subs_x + (int)RB_LUT_SUB(px_);
+                const int tile = (int)(RB_LUT_TILE(py_) * tiles_x + RB_LUT_TILE(px_));
+                if (sub != cached_sub) {
+                    const uint32_t tt = pt[sub];
+                    cached_sub = sub;
+                    cached_base = tt == RB_NONE ? nullptr : pool + (size_t)tt * RB_SUB_BYTES;
+                    if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;   // HybridMapEntry allocation :125-131
+                    if (!cached_base) atomicExch(&flags->world_overflow, 2);    // cannot happen after prepare
+                }
+                bool alias_prev = false, alias_next = false;
+                if (pmaj >> RB_LUT_NEXT_BIT) {
+                    const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                    alias_prev = n >= 1 && ((pmaj >> SH_MAJ_PREV) & 1u) && (!bump_prev || ((pmin >> SH_MIN_PREV) & 1u));
+                    alias_next = n + 1 < len && ((pmaj >> SH_MAJ_NEXT) & 1u) && (!bump_next || ((pmin >> SH_MIN_NEXT) & 1u));
+                }
+                if (cached_base && !alias_prev) {
+                    int o = n == n_occ ? 2 : 1;                                 // hybridmap.py:137-138 / :144
+                    if (n == n_near && tile == end_tile) o |= 4;                // hybridmap.py:139-142
+                    if (alias_next) {
+                        int o2 = n + 1 == n_occ ? 2 : 1;
+                        if (n + 1 == n_near && tile == end_tile) o2 |= 4;
+                        o |= o2 << 3;
+                    }
+                    ops = o;
+                    addr = cached_base + RB_LUT_OFF(py_) + RB_LUT_OFF(px_);
+                }
+            }
+        }
+        n += 32;
+        kmaj += 32 * smaj;
+        e += step_e;
+        int dq = step_q;
+        if (e >= D2) { e -= D2; dq++; }
+        kmin += smin * dq;
+        if (ops) {
+            const int t = (int)*addr;
+            int v = apply_ops(t, ops & 7);
+            if (ops >> 3) v = apply_ops(v, ops >> 3);
+            if (v != t) *addr = (int8_t)v;
+        }
+        __syncwarp();
+    }
+    if (dropped) atomicAdd(&stats->cells_dropped, (unsigned long long)dropped);
+    return ex_new;
+}
+
+struct CastLane {    // per-lane cache of the last page-table lookup
+    unsigned key;    // slot << 15 of the cached sub-tile (never matches when invalid)
+    int8_t *base;
+};
+
+// Sub-tile change: look the slot up, note a new reference tile (HybridMapEntry allocation, hybridmap.py:125-131).
+__device__ __forceinline__ void cast_new_sub(const RbCtx &c, const uint32_t *pt, const unsigned char *sub2tile, unsigned s,
+                                             CastLane &cl, unsigned long long ex_mask, unsigned long long &ex_new)
+{
+    const unsigned sub = (s & RC2_SUBMASK) >> 15;
+    const uint32_t tt = pt[sub];
+    const int tile = sub2tile[sub];
+    if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;
+    if (tt == RB_NONE) {                                             // cannot happen after prepare
+        atomicExch(&c.flags->world_overflow, 2);
+        cl.key = 0xffffffffu;
+        cl.base = c.pool;                                            // a valid address: the lane loads it and stores nothing
+    } else {
+        cl.key = s & RC2_SUBMASK;
+        cl.base = c.pool + (size_t)tt * RB_SUB_BYTES;
+    }
+}
+
+// NCH chunks of 32 consecutive "empty" cells each, loads of all chunks in flight together.
+template <int NCH>
+__device__ __forceinline__ void cast_empty_group(const RbCtx &c, const uint32_t *__restrict__ lut_s, const unsigned char *sub2tile,
+                                                 const uint32_t *pt, int &imaj, unsigned &num, int &n, int nf, int bmin,
+                                                 int smaj32, int smin, unsigned d2x32, unsigned magic, unsigned keymask,
+                                                 int d2, int D2, int sh_maj, int sh_min, int fwd, CastLane &cl,
+                                                 unsigned long long ex_mask, unsigned long long &ex_new)
+{
+    int8_t *addr[NCH];
+    int dec[NCH], t[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+        const unsigned m = __umulhi(num, magic);
+        const unsigned s = lut_s[imaj] + lut_s[bmin + smin * (int)m];
+        int d_ = n < nf ? RB_T_EMP : 0;                              // lanes past the last empty-only cell load and store nothing new
+        if ((s & keymask) != cl.key) {
+            if ((s & RC2_SUBMASK) != cl.key) cast_new_sub(c, pt, sub2tile, s, cl, ex_mask, ex_new);
+            const unsigned A = (s >> sh_maj) & 3u;                   // bit 0: shares storage with k + 1, bit 1: with k - 1
+            if (A) {
+                const unsigned Bm = (s >> sh_min) & 3u;
+                const int e = (int)(num - m * (unsigned)D2);
+                const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                const unsigned f = (unsigned)fwd, b = 3u - f;         // fwd: bit of the forward direction (1 or 2)
+                const unsigned fm = smin > 0 ? 1u : 2u, bm = 3u - fm;
+                const bool skip = n >= 1 && (A & b) && (!bump_prev || (Bm & bm));
+                const bool dbl = (A & f) && (!bump_next || (Bm & fm));
+                if (n < nf) d_ = skip ? 0 : dbl ? 2 * RB_T_EMP : RB_T_EMP;
+            }
+            if (cl.key == 0xffffffffu) d_ = 0;
+        }
+        addr[u] = cl.base + (s & RC2_OFFMASK);
+        dec[u] = d_;
+        n += 32;
+        imaj += smaj32;
+        num += d2x32;
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; u++) t[u] = (int)*addr[u];
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+        const int v = max(t[u] - dec[u], -RB_T_MAX);                 // dec 0: v == t (cells are never below the floor)
+        if (v != t[u]) *addr[u] = (int8_t)v;
+    }
+}
+
+// Per-beam constants of beams j0 .. j0 + 31 (one beam per lane) into the warp's record table.  Out of line:
+// the float64 frame and the per-beam geometry do not take registers away from the cell loop.
+__device__ __noinline__ void cast_setup_beams(const double *px, const double *py, const double *dist, const uint32_t *lutx,
+                                              const uint32_t *luty, int txh, int tyh, int tiles_x, int B, int j0, int lane,
+                                              const double *frame, int4 *recs, int nx, int ny)
+{
+    const int ox = 800 * txh + 400, oy = 800 * tyh + 400;
+    int4 ra = make_int4(0, 0, 2, 0), rb = make_int4(0, 0, -1, 0);
+    if (j0 + lane < B) {
+        const double x = frame[0], y = frame[1], cs_ = frame[2], sn_ = frame[3];
+        const int sx = reinterpret_cast<const int *>(frame + 4)[0], sy = reinterpret_cast<const int *>(frame + 4)[1];
+        const bool start_inside = (unsigned)(sx + ox) < (unsigned)nx && (unsigned)(sy + oy) < (unsigned)ny;
+        Ray r;
+        {
+            double gx, gy;
+            rb_xform(cs_, sn_, x, y, px[j0 + lane], py[j0 + lane], gx, gy);
+            r.ex = rb_trunc(gx / RB_CS);                              // hybridmap.py:106
+            r.ey = rb_trunc(gy / RB_CS);
+            r.occ = 1;
+            const double d = dist[j0 + lane];
+            if (d > RB_CLIP_R) {                                      // hybridmap.py:107-113
+                const double scale = 15.0 / d;
+                const int nex = rb_trunc((double)sx + scale * (double)(r.ex - sx));
+                const int ney = rb_trunc((double)sy + scale * (double)(r.ey - sy));
+                r.ex = nex;
+                r.ey = ney;
+                r.occ = 0;
+            }
+            const int dx = r.ex - sx, dy = r.ey - sy;
+            const int adx = abs(dx), ady = abs(dy);
+            if (adx == 0) r.len = dy >= 0 ? dy + 1 : 0;               // hybridmap.py:278-279
+            else if (ady == 0) r.len = dx >= 0 ? dx + 1 : 0;          // hybridmap.py:280-281
+            else r.len = max(adx, ady) + 1;
+        }
+        const RayStep st = ray_step(sx, sy, r);
+        const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
+        const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(RB_LUT_TILE(pey) * tiles_x + RB_LUT_TILE(pex));
+        int len = r.len;
+        if (len > 4095 || st.D > 4095u) len = 0;                       // cannot happen: rays are clipped at 15 m = 300 cells
+        // start and end cell inside the world => every cell of the ray is (bounding box)
+        // (and the magic quotient is exact for D <= 700; the 15 m clip keeps D at 300)
+        const int inside = pex != RB_NONE && pey != RB_NONE && start_inside && st.D <= 700u;
+        int near_ok = 0;
+        if (inside && r.occ && len >= 2) {                              // hybridmap.py:139-142: the cell before the end, if the end's tile holds it
+            int qx, qy;
+            ray_cell(sx, sy, st, len - 2, qx, qy);
+            const uint32_t pqx = rb_write_lut(lutx, qx, txh), pqy = rb_write_lut(luty, qy, tyh);
+            near_ok = (int)(RB_LUT_TILE(pqy) * tiles_x + RB_LUT_TILE(pqx)) == end_tile;
+        }
+        ra.x = len | (r.occ << 12) | (st.steep << 13) | (inside << 14) | ((st.smaj < 0) << 15) | ((st.smin + 1) << 16) | (near_ok << 18);
+        ra.y = (int)st.d2;
+        ra.z = (int)st.D2;
+        ra.w = (int)(unsigned)((0x100000000ull + st.D2 - 1) / st.D2);
+        rb.x = st.steep ? nx + sy + oy : sx + ox;
+        rb.y = st.steep ? sx + ox : nx + sy + oy;
+        rb.z = end_tile;
+        rb.w = (r.ex & 0xffff) | (r.ey << 16);                          // general path only; |cell| < 2^15: the world has at most 16 x 800 cells per axis
+    }
+    recs[2 * lane] = ra;
+    recs[2 * lane + 1] = rb;
+}
+
+#define RC2_WARP_WORDS (256 + 16)    // per warp: 32 records of 32 bytes, then the particle's frame (x, y, cos, sin, start cell)
+
+__global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_kernel(RbCtx c)
+{
+    extern __shared__ uint32_t smem2[];
+    const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nx = 800 * c.tiles_x, ny = 800 * c.tiles_y;
+    uint32_t *lut_s = smem2;                                         // x entries, then y entries
+    int4 *recs = reinterpret_cast<int4 *>(smem2 + nx + ny + warp * RC2_WARP_WORDS);
+    double *frame = reinterpret_cast<double *>(smem2 + nx + ny + warp * RC2_WARP_WORDS + 256);
+    unsigned char *sub2tile = reinterpret_cast<unsigned char *>(smem2 + nx + ny + RC2_WARPS * RC2_WARP_WORDS);
+    for (int i = threadIdx.x; i < nx + ny; i += RC2_WARPS * 32) lut_s[i] = c.clut[i];
+    for (int i = threadIdx.x; i < c.nsub; i += RC2_WARPS * 32)
+        sub2tile[i] = (unsigned char)(((i / c.subs_x) / RB_SUBS_PER_TILE) * c.tiles_x + (i % c.subs_x) / RB_SUBS_PER_TILE);
+    __syncthreads();
+    if (c.flags->pool_exhausted) return;                             // prepare could not privatise: skip the scan
+
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(c.cast_work, 1);
+        p = __shfl_sync(FULL, p, 0);
+        if (p >= c.N) break;
+        int sx, sy;
+        {
+            double x, y, cs_, sn_;
+            if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) continue;
+            __syncwarp();
+            if (lane == 0) {
+                frame[0] = x; frame[1] = y; frame[2] = cs_; frame[3] = sn_;
+                reinterpret_cast<int *>(frame + 4)[0] = sx;
+                reinterpret_cast<int *>(frame + 4)[1] = sy;
+            }
+        }
+        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
+        const unsigned long long ex_mask = c.exists[p];
+        unsigned long long ex_new = 0ull;
+        // every ray starts in the robot's cell: its sub-tile is the page-table hit of each beam's first cells
+        CastLane cl0;
+        cl0.key = 0xffffffffu; cl0.base = c.pool;
+        {
+            const int ox = 800 * c.txh + 400, oy = 800 * c.tyh + 400;
+            if ((unsigned)(sx + ox) < (unsigned)nx && (unsigned)(sy + oy) < (unsigned)ny) {
+                const unsigned s0 = lut_s[sx + ox] + lut_s[nx + sy + oy];
+                const uint32_t t0 = pt[(s0 & RC2_SUBMASK) >> 15];
+                if (t0 != RB_NONE) { cl0.key = s0 & RC2_SUBMASK; cl0.base = c.pool + (size_t)t0 * RB_SUB_BYTES; }
+            }
+        }
+
+        for (int j0 = 0; j0 < c.B; j0 += 32) {
+            __syncwarp();
+            {
+                cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny);
+                __syncwarp();
+                const int nb = min(32, c.B - j0);
+                for (int b = 0; b < nb; b++) {
+                    const int4 ra = recs[2 * b];
+                    const int w0 = ra.x, len = w0 & 0xfff;
+                    if (len == 0) continue;                             // hybridmap.py:278-281 empty list
+                    const int4 rb = recs[2 * b + 1];
+                    const int occ = (w0 >> 12) & 1, steep = (w0 >> 13) & 1;
+                    if (!((w0 >> 14) & 1)) {
+                        ex_new |= cast_general_ray(c.pool, pt, c.lutx, c.luty, c.flags, c.stats, c.txh, c.tyh, c.subs_x, c.tiles_x, lane,
+                                                   reinterpret_cast<const int *>(frame + 4)[0], reinterpret_cast<const int *>(frame + 4)[1],
+                                                   len, occ, (int)(short)(rb.w & 0xffff), rb.w >> 16, rb.z, ex_mask);
+                        continue;
+                    }
+                    const int d2 = ra.y, D2 = ra.z;
+                    const unsigned magic = (unsigned)ra.w;
+                    const int bmaj = rb.x, bmin = rb.y;
+                    const int smaj = (w0 >> 15) & 1 ? -1 : 1, smin = ((w0 >> 16) & 3) - 1;
+                    const int sh_maj = steep ? 28 : 30, sh_min = steep ? 30 : 28;
+                    const unsigned keymask = RC2_SUBMASK | (3u << sh_maj);
+                    const int fwd = smaj > 0 ? 1 : 2;
+                    CastLane cl = cl0;
+                    // ---- tail chunk first: cells [len - 32, len), lane 31 = end cell, lane 30 = the cell before it
+                    const int nt = len - 32 + lane;
+                    int8_t *taddr = nullptr;
+                    int tops = 0;
+                    if (nt >= 0) {
+                        const unsigned num = (unsigned)nt * (unsigned)d2 + (unsigned)(D2 >> 1);
+                        const unsigned m = __umulhi(num, magic);
+                        const unsigned s = lut_s[bmaj + smaj * nt] + lut_s[bmin + smin * (int)m];
+                        if ((s & RC2_SUBMASK) != cl.key) cast_new_sub(c, pt, sub2tile, s, cl, ex_mask, ex_new);
+                        bool alias_prev = false, alias_next = false;
+                        const unsigned A = (s >> sh_maj) & 3u;
+                        if (A) {
+                            const unsigned Bm = (s >> sh_min) & 3u;
+                            const int e = (int)(num - m * (unsigned)D2);
+                            const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
+                            const unsigned f = (unsigned)fwd, bk = 3u - f;
+                            const unsigned fm = smin > 0 ? 1u : 2u, bm = 3u - fm;
+                            alias_prev = nt >= 1 && (A & bk) && (!bump_prev || (Bm & bm));
+                            alias_next = nt + 1 < len && (A & f) && (!bump_next || (Bm & fm));
+                        }
+                        if (cl.key != 0xffffffffu && !alias_prev) {
+                            const int near_ok = (w0 >> 18) & 1;
+                            int o = (occ && lane == 31) ? 2 : 1;               // hybridmap.py:137-138 / :144
+                            if (near_ok && lane == 30) o |= 4;                 // hybridmap.py:139-142
+                            if (alias_next) {                                  // next cell's ops, applied after ours
+                                int o2 = (occ && lane == 30) ? 2 : 1;
+                                if (near_ok && lane == 29) o2 |= 4;
+                                o |= o2 << 3;
+                            }
+                            tops = o;
+                            taddr = cl.base + (s & RC2_OFFMASK);
+                        }
+                    }
+                    const int tt_ = tops ? (int)*taddr : 0;
+                    // ---- empty chunks over [0, len - 32)
+                    const int nf = len - 32;
+                    if (nf > 0) {
+                        cl = cl0;
+                        int imaj = bmaj + smaj * lane, n = lane;
+                        unsigned num = (unsigned)lane * (unsigned)d2 + (unsigned)(D2 >> 1);
+                        const int smaj32 = 32 * smaj;
+                        const unsigned d2x32 = 32u * (unsigned)d2;
+                        int left = (nf + 31) >> 5;
+#define RC2_GROUP(K) cast_empty_group<K>(c, lut_s, sub2tile, pt, imaj, num, n, nf, bmin, smaj32, smin, d2x32, magic, keymask, d2, D2, sh_maj, sh_min, fwd, cl, ex_mask, ex_new)
+                        while (left >= 4) { RC2_GROUP(4); left -= 4; }
+                        if (left == 3) RC2_GROUP(3);
+                        else if (left == 2) RC2_GROUP(2);
+                        else if (left == 1) RC2_GROUP(1);
+                    }
+                    if (tops) {
+                        int v = apply_ops(tt_, tops & 7);
+                        if (tops >> 3) v = apply_ops(v, tops >> 3);
+                        if (v != tt_) *taddr = (int8_t)v;
+                    }
+                    __syncwarp();                                       // the next beam must see these stores
+                }
+            }
+        }
+        // publish newly created reference tiles
+        for (int o = 16; o > 0; o >>= 1) ex_new |= __shfl_xor_sync(FULL, ex_new, o);
+        if (lane == 0 && ex_new) c.exists[p] = ex_mask | ex_new;
+    }
+}
+
 // ------------------------------------------------------- atomics variant --
 // EXPERIMENT, not the product path (RBPF_CAST_ATOMICS=1): the variant BASELINE.json's north_star names.
 // The beams of a particle are split over the four warps of a CTA and every cell update is a
@@ -568,6 +956,24 @@ void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
     static const int use_atomics = getenv("RBPF_CAST_ATOMICS") && atoi(getenv("RBPF_CAST_ATOMICS")) > 0;
     if (use_atomics) {                                            // experiment only, see raycast_cast_atomic_kernel
         raycast_cast_atomic_kernel<<<c.N, RC_WARPS * 32, 0, s>>>(c);
+        return;
+    }
+    static const int use_v1 = getenv("RBPF_CAST_V1") && atoi(getenv("RBPF_CAST_V1")) > 0;
+    if (!use_v1) {
+        const size_t smem = sizeof(uint32_t) * (800 * (size_t)(c.tiles_x + c.tiles_y) + RC2_WARPS * RC2_WARP_WORDS) + (((size_t)c.nsub + 15) & ~(size_t)15);
+        static size_t smem_set = 0;
+        static int resident = 0;
+        if (smem != smem_set) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(raycast_cast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_cast2_kernel, RC2_WARPS * 32, smem);
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+            smem_set = smem;
+        }
+        const int want = (c.N + RC2_WARPS - 1) / RC2_WARPS;
+        raycast_cast2_kernel<<<want < resident ? want : resident, RC2_WARPS * 32, smem, s>>>(c);
         return;
     }
     const int blocks = (c.N + RC_WARPS - 1) / RC_WARPS;
