@@ -200,7 +200,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     const size_t N = (size_t)d.N;
     cudaError_t e = cudaSuccess;
 #define A(ptr, n) if (e == cudaSuccess) e = dalloc(h, &(ptr), (size_t)(n))
-    A(d.pool, (size_t)d.pool_tiles * RB_SUB_BYTES);
+    A(d.pool, ((size_t)d.pool_tiles + 1) * RB_SUB_BYTES);              // + the sink sub-tile of the cast kernel (never referenced by a page table)
     A(d.refcnt, d.pool_tiles);
     A(d.free_list, d.pool_tiles);
     A(d.free_count, 4);
@@ -270,7 +270,6 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     for (size_t q = 0; q < luty.size(); q++)
         clut[lutx.size() + q] = RB_LUT_OFF(luty[q]) | ((RB_LUT_SUB(luty[q]) * (uint32_t)d.subs_x) << 15) |
                                 (((luty[q] >> RB_LUT_NEXT_BIT) & 1u) << 28) | (((luty[q] >> RB_LUT_PREV_BIT) & 1u) << 29);
-    if (d.nsub > 2048) return fail(RBPF_ERR_ARG, "world too large for the cast LUT (more than 2048 sub-tiles)");
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_clut, clut.data(), clut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_lutx, lutx.data(), lutx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||

@@ -496,18 +496,24 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 }
 
 // ------------------------------------------------------- cast, version 2 --
-// Same update order, a third of the instructions.  What changed against raycast_cast_kernel:
+// Same update order as raycast_cast_kernel, a third of the instructions.  What changed:
 //   * persistent CTAs (grid = resident CTAs), warps fetch particles from a work counter, so the
-//     two cast LUTs (rb_cast_lut: 800 entries per reference tile and axis) are staged in shared
-//     memory once per CTA instead of once per four particles;
+//     two cast LUTs (800 entries per reference tile and axis) are staged in shared memory once
+//     per CTA instead of once per four particles;
 //   * the cast LUT entries of the two axes ADD UP to one word: bits 0-14 byte offset inside the
-//     sub-tile, bits 15-25 page-table slot, bits 28-31 the aliasing flags (x: 30/31, y: 28/29).
-//     One compare of (word & key mask) against the cached slot finds both a sub-tile change and
-//     an aliasing pair along the major axis -- the only two things the empty-cell path cares about;
+//     sub-tile, bits 15-25 page-table slot, bits 28-31 the aliasing flags (x: 30/31, y: 28/29);
+//   * the page-table entries a sweep can reach (5 x 5 sub-tiles around the robot's: rays are
+//     clipped at 300 cells, a sub-tile has 160) sit in a per-warp table in shared memory, indexed
+//     by slot - slot of the window corner: no per-lane cache, no branch on a sub-tile change;
+//   * new reference tiles (HybridMapEntry allocation, hybridmap.py:125-131) are found per beam
+//     from the tiles of the two end cells; a ray that changes tile along both axes takes the
+//     per-cell path;
 //   * the minor coordinate of cell n is the closed form floor((n d2 + D) / D2) by a magic
 //     multiply (exact: n <= 300 cells after the 15 m clip), no error term is carried;
 //   * a ray is ceil(len / 32) chunks: "empty" chunks over [0, len - 32) and ONE tail chunk
-//     [len - 32, len) that holds the end / nearby cells in lanes 31 / 30;
+//     [len - 32, len) with the end / nearby cells in lanes 31 / 30; every cell's update is
+//     v = min(max(t - a, -30) + b, 30) with (a, b) per lane, which also covers two ray cells
+//     that share a storage cell (the earlier lane applies both, the later one nothing);
 //   * per-beam constants go through shared memory (two 16-byte broadcasts per beam).
 // Rays that leave the world take cast_general_ray (the old per-cell path).
 #ifndef RC2_WARPS
@@ -517,30 +523,52 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 #define RC2_MINBLOCKS 4
 #endif
 
-#define RC2_SUBMASK 0x03ff8000u
 #define RC2_OFFMASK 0x00007fffu
+#define RC2_TBL_WORDS 168            // 4 * subs_x + 5 <= 165 entries (subs_x <= 40)
+#define RC2_WARP_WORDS (256 + 16 + RC2_TBL_WORDS)   // per warp: 32 records of 32 bytes, the particle's frame, the slot table
 
-struct CastRec {     // per-beam constants, 32 bytes
-    int w0;          // len (bits 0-11) | occ << 12 | steep << 13 | inside << 14 | (smaj < 0) << 15 | (smin + 1) << 16 | near_ok << 18
-    int d2;          // 2 * minor extent
-    int D2;          // 2 * major extent (>= 2)
-    unsigned magic;  // ceil(2^32 / D2)
-    int bmaj, bmin;  // index into the staged LUTs of the major / minor coordinate of cell 0
-    int end_tile;    // reference tile of the end cell or -1 (general path only)
-    int ex, ey;      // (general path only: end cell)  -- ey overlays the padding word
-};
+// frame words (doubles): 0 x, 1 y, 2 cos, 3 sin; then ints at double index 4: sx, sy
+__device__ __forceinline__ Ray ray_of_beam_p(const double *px, const double *py, const double *dist, int j, double x, double y,
+                                             double cs_, double sn_, int sx, int sy)
+{
+    Ray r;
+    double gx, gy;
+    rb_xform(cs_, sn_, x, y, px[j], py[j], gx, gy);
+    r.ex = rb_trunc(gx / RB_CS);                                   // hybridmap.py:106
+    r.ey = rb_trunc(gy / RB_CS);
+    r.occ = 1;
+    const double d = dist[j];
+    if (d > RB_CLIP_R) {                                           // hybridmap.py:107-113
+        const double scale = 15.0 / d;
+        const int nex = rb_trunc((double)sx + scale * (double)(r.ex - sx));
+        const int ney = rb_trunc((double)sy + scale * (double)(r.ey - sy));
+        r.ex = nex;
+        r.ey = ney;
+        r.occ = 0;
+    }
+    const int dx = r.ex - sx, dy = r.ey - sy;
+    const int adx = abs(dx), ady = abs(dy);
+    if (adx == 0) r.len = dy >= 0 ? dy + 1 : 0;                    // hybridmap.py:278-279
+    else if (ady == 0) r.len = dx >= 0 ? dx + 1 : 0;               // hybridmap.py:280-281
+    else r.len = max(adx, ady) + 1;
+    return r;
+}
 
-// The old per-cell path for rays with a cell outside the world (rare: the world is sized for the log).
+// The old per-cell path for one beam (all lanes on the same beam) -- rays with a cell outside the world and rays
+// that change reference tile along both axes (rare: the world is sized for the log, tiles are 800 cells).
 // Scalars in, the newly touched reference tiles out: nothing of the caller has its address taken.
 __device__ __noinline__ unsigned long long cast_general_ray(int8_t *pool, const uint32_t *pt, const uint32_t *lutx, const uint32_t *luty,
                                                             RbFlags *flags, RbStats *stats, int txh, int tyh, int subs_x, int tiles_x,
-                                                            int lane, int sx, int sy, int len, int occ, int ex, int ey, int end_tile,
-                                                            unsigned long long ex_mask)
+                                                            int lane, const double *px, const double *py, const double *dist, int j,
+                                                            const double *frame, unsigned long long ex_mask)
 {
     unsigned long long ex_new = 0ull;
     unsigned dropped = 0;
-    Ray r;
-    r.ex = ex; r.ey = ey; r.len = len; r.occ = occ;
+    const int sx = reinterpret_cast<const int *>(frame + 4)[0], sy = reinterpret_cast<const int *>(frame + 4)[1];
+    const Ray r = ray_of_beam_p(px, py, dist, j, frame[0], frame[1], frame[2], frame[3], sx, sy);
+    const int len = r.len, occ = r.occ;
+    const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
+    const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(RB_LUT_TILE(pey) * tiles_x + RB_LUT_TILE(pex));
     const RayStep st = ray_step(sx, sy, r);
     const int steep = st.steep, smaj = st.smaj, smin = st.smin;
     const int D2 = (int)st.D2, d2 = (int)st.d2;
@@ -613,137 +641,129 @@ __device__ __noinline__ unsigned long long cast_general_ray(int8_t *pool, const 
     return ex_new;
 }
 
-struct CastLane {    // per-lane cache of the last page-table lookup
-    unsigned key;    // slot << 15 of the cached sub-tile (never matches when invalid)
-    int8_t *base;
-};
-
-// Sub-tile change: look the slot up, note a new reference tile (HybridMapEntry allocation, hybridmap.py:125-131).
-__device__ __forceinline__ void cast_new_sub(const RbCtx &c, const uint32_t *pt, const unsigned char *sub2tile, unsigned s,
-                                             CastLane &cl, unsigned long long ex_mask, unsigned long long &ex_new)
-{
-    const unsigned sub = (s & RC2_SUBMASK) >> 15;
-    const uint32_t tt = pt[sub];
-    const int tile = sub2tile[sub];
-    if (!((ex_mask >> tile) & 1ull)) ex_new |= 1ull << tile;
-    if (tt == RB_NONE) {                                             // cannot happen after prepare
-        atomicExch(&c.flags->world_overflow, 2);
-        cl.key = 0xffffffffu;
-        cl.base = c.pool;                                            // a valid address: the lane loads it and stores nothing
-    } else {
-        cl.key = s & RC2_SUBMASK;
-        cl.base = c.pool + (size_t)tt * RB_SUB_BYTES;
-    }
-}
-
-// NCH chunks of 32 consecutive "empty" cells each, loads of all chunks in flight together.
-template <int NCH>
-__device__ __forceinline__ void cast_empty_group(const RbCtx &c, const uint32_t *__restrict__ lut_s, const unsigned char *sub2tile,
-                                                 const uint32_t *pt, int &imaj, unsigned &num, int &n, int nf, int bmin,
-                                                 int smaj32, int smin, unsigned d2x32, unsigned magic, unsigned keymask,
-                                                 int d2, int D2, int sh_maj, int sh_min, int fwd, CastLane &cl,
-                                                 unsigned long long ex_mask, unsigned long long &ex_new)
-{
-    int8_t *addr[NCH];
-    int dec[NCH], t[NCH];
-#pragma unroll
-    for (int u = 0; u < NCH; u++) {
-        const unsigned m = __umulhi(num, magic);
-        const unsigned s = lut_s[imaj] + lut_s[bmin + smin * (int)m];
-        int d_ = n < nf ? RB_T_EMP : 0;                              // lanes past the last empty-only cell load and store nothing new
-        if ((s & keymask) != cl.key) {
-            if ((s & RC2_SUBMASK) != cl.key) cast_new_sub(c, pt, sub2tile, s, cl, ex_mask, ex_new);
-            const unsigned A = (s >> sh_maj) & 3u;                   // bit 0: shares storage with k + 1, bit 1: with k - 1
-            if (A) {
-                const unsigned Bm = (s >> sh_min) & 3u;
-                const int e = (int)(num - m * (unsigned)D2);
-                const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
-                const unsigned f = (unsigned)fwd, b = 3u - f;         // fwd: bit of the forward direction (1 or 2)
-                const unsigned fm = smin > 0 ? 1u : 2u, bm = 3u - fm;
-                const bool skip = n >= 1 && (A & b) && (!bump_prev || (Bm & bm));
-                const bool dbl = (A & f) && (!bump_next || (Bm & fm));
-                if (n < nf) d_ = skip ? 0 : dbl ? 2 * RB_T_EMP : RB_T_EMP;
-            }
-            if (cl.key == 0xffffffffu) d_ = 0;
-        }
-        addr[u] = cl.base + (s & RC2_OFFMASK);
-        dec[u] = d_;
-        n += 32;
-        imaj += smaj32;
-        num += d2x32;
-    }
-#pragma unroll
-    for (int u = 0; u < NCH; u++) t[u] = (int)*addr[u];
-#pragma unroll
-    for (int u = 0; u < NCH; u++) {
-        const int v = max(t[u] - dec[u], -RB_T_MAX);                 // dec 0: v == t (cells are never below the floor)
-        if (v != t[u]) *addr[u] = (int8_t)v;
-    }
-}
-
-// Per-beam constants of beams j0 .. j0 + 31 (one beam per lane) into the warp's record table.  Out of line:
-// the float64 frame and the per-beam geometry do not take registers away from the cell loop.
-__device__ __noinline__ void cast_setup_beams(const double *px, const double *py, const double *dist, const uint32_t *lutx,
-                                              const uint32_t *luty, int txh, int tyh, int tiles_x, int B, int j0, int lane,
-                                              const double *frame, int4 *recs, int nx, int ny)
+// Per-beam constants of beams j0 .. j0 + 31 (one beam per lane) into the warp's record table; returns the
+// reference tiles this lane's beam creates.  Out of line: the float64 frame and the per-beam geometry do not
+// take registers away from the cell loop.
+//   record word 0: len (bits 0-11) | occ << 12 | steep << 13 | fast << 14 | near_ok << 15
+//          1-3   : d2 = 2 * minor extent, D2 = 2 * major extent (>= 2), magic = ceil(2^32 / D2)
+//          4-5   : index into the staged LUTs of the major / minor coordinate of cell 0
+//          6-7   : 32 * (step along the major axis), step along the minor axis
+__device__ __noinline__ unsigned long long cast_setup_beams(const double *px, const double *py, const double *dist, const uint32_t *lutx,
+                                                            const uint32_t *luty, int txh, int tyh, int tiles_x, int B, int j0, int lane,
+                                                            const double *frame, int4 *recs, int nx, int ny, unsigned long long ex_mask)
 {
     const int ox = 800 * txh + 400, oy = 800 * tyh + 400;
-    int4 ra = make_int4(0, 0, 2, 0), rb = make_int4(0, 0, -1, 0);
+    unsigned long long ex_new = 0ull;
+    int4 ra = make_int4(0, 0, 2, 0), rb = make_int4(0, 0, 32, 0);
     if (j0 + lane < B) {
-        const double x = frame[0], y = frame[1], cs_ = frame[2], sn_ = frame[3];
         const int sx = reinterpret_cast<const int *>(frame + 4)[0], sy = reinterpret_cast<const int *>(frame + 4)[1];
-        const bool start_inside = (unsigned)(sx + ox) < (unsigned)nx && (unsigned)(sy + oy) < (unsigned)ny;
-        Ray r;
-        {
-            double gx, gy;
-            rb_xform(cs_, sn_, x, y, px[j0 + lane], py[j0 + lane], gx, gy);
-            r.ex = rb_trunc(gx / RB_CS);                              // hybridmap.py:106
-            r.ey = rb_trunc(gy / RB_CS);
-            r.occ = 1;
-            const double d = dist[j0 + lane];
-            if (d > RB_CLIP_R) {                                      // hybridmap.py:107-113
-                const double scale = 15.0 / d;
-                const int nex = rb_trunc((double)sx + scale * (double)(r.ex - sx));
-                const int ney = rb_trunc((double)sy + scale * (double)(r.ey - sy));
-                r.ex = nex;
-                r.ey = ney;
-                r.occ = 0;
-            }
-            const int dx = r.ex - sx, dy = r.ey - sy;
-            const int adx = abs(dx), ady = abs(dy);
-            if (adx == 0) r.len = dy >= 0 ? dy + 1 : 0;               // hybridmap.py:278-279
-            else if (ady == 0) r.len = dx >= 0 ? dx + 1 : 0;          // hybridmap.py:280-281
-            else r.len = max(adx, ady) + 1;
-        }
+        const Ray r = ray_of_beam_p(px, py, dist, j0 + lane, frame[0], frame[1], frame[2], frame[3], sx, sy);
         const RayStep st = ray_step(sx, sy, r);
+        const uint32_t psx = rb_write_lut(lutx, sx, txh), psy = rb_write_lut(luty, sy, tyh);
         const uint32_t pex = rb_write_lut(lutx, r.ex, txh), pey = rb_write_lut(luty, r.ey, tyh);
-        const int end_tile = (pex == RB_NONE || pey == RB_NONE) ? -1 : (int)(RB_LUT_TILE(pey) * tiles_x + RB_LUT_TILE(pex));
         int len = r.len;
         if (len > 4095 || st.D > 4095u) len = 0;                       // cannot happen: rays are clipped at 15 m = 300 cells
-        // start and end cell inside the world => every cell of the ray is (bounding box)
-        // (and the magic quotient is exact for D <= 700; the 15 m clip keeps D at 300)
-        const int inside = pex != RB_NONE && pey != RB_NONE && start_inside && st.D <= 700u;
+        // start and end cell inside the world => every cell of the ray is (bounding box);
+        // the magic quotient is exact for D <= 700 and the slot table covers 300 cells (the 15 m clip keeps D at 300)
+        int fast = pex != RB_NONE && pey != RB_NONE && psx != RB_NONE && psy != RB_NONE && st.D <= 300u && len <= 301;
+        // the end cell (hence every cell: rays are monotone along both axes) lies in the 5 x 5 sub-tile window of the slot table
+        if (fast && (abs((int)RB_LUT_SUB(pex) - (int)RB_LUT_SUB(psx)) > 2 || abs((int)RB_LUT_SUB(pey) - (int)RB_LUT_SUB(psy)) > 2)) fast = 0;
         int near_ok = 0;
-        if (inside && r.occ && len >= 2) {                              // hybridmap.py:139-142: the cell before the end, if the end's tile holds it
-            int qx, qy;
-            ray_cell(sx, sy, st, len - 2, qx, qy);
-            const uint32_t pqx = rb_write_lut(lutx, qx, txh), pqy = rb_write_lut(luty, qy, tyh);
-            near_ok = (int)(RB_LUT_TILE(pqy) * tiles_x + RB_LUT_TILE(pqx)) == end_tile;
+        if (fast && len > 0) {
+            const int tsx = (int)RB_LUT_TILE(psx), tsy = (int)RB_LUT_TILE(psy), tex = (int)RB_LUT_TILE(pex), tey = (int)RB_LUT_TILE(pey);
+            const int end_tile = tey * tiles_x + tex;
+            if (tsx != tex && tsy != tey) {
+                fast = 0;                                               // which corner tile the ray crosses is the per-cell path's business
+            } else {
+                // one axis changes tile at most once (300 < 800 cells): the ray's cells lie in the start tile (exists,
+                // hybridmap.py:98-100) and the end tile
+                if (!((ex_mask >> end_tile) & 1ull)) ex_new = 1ull << end_tile;
+                if (r.occ && len >= 2) {                                // hybridmap.py:139-142: the cell before the end, if the end's tile holds it
+                    int qx, qy;
+                    ray_cell(sx, sy, st, len - 2, qx, qy);
+                    const uint32_t pqx = rb_write_lut(lutx, qx, txh), pqy = rb_write_lut(luty, qy, tyh);
+                    near_ok = (int)(RB_LUT_TILE(pqy) * tiles_x + RB_LUT_TILE(pqx)) == end_tile;
+                }
+            }
         }
-        ra.x = len | (r.occ << 12) | (st.steep << 13) | (inside << 14) | ((st.smaj < 0) << 15) | ((st.smin + 1) << 16) | (near_ok << 18);
+        ra.x = len | (r.occ << 12) | (st.steep << 13) | (fast << 14) | (near_ok << 15);
         ra.y = (int)st.d2;
         ra.z = (int)st.D2;
         ra.w = (int)(unsigned)((0x100000000ull + st.D2 - 1) / st.D2);
         rb.x = st.steep ? nx + sy + oy : sx + ox;
         rb.y = st.steep ? sx + ox : nx + sy + oy;
-        rb.z = end_tile;
-        rb.w = (r.ex & 0xffff) | (r.ey << 16);                          // general path only; |cell| < 2^15: the world has at most 16 x 800 cells per axis
+        rb.z = 32 * st.smaj;
+        rb.w = st.smin;
     }
     recs[2 * lane] = ra;
     recs[2 * lane + 1] = rb;
+    return ex_new;
 }
 
-#define RC2_WARP_WORDS (256 + 16)    // per warp: 32 records of 32 bytes, then the particle's frame (x, y, cos, sin, start cell)
+struct CastBeam {    // warp-uniform constants of the beam in flight
+    const uint32_t *lut_s;
+    const uint32_t *tbl;       // slot table, already offset by the window corner: tbl[slot]
+    int8_t *pool;
+    int bmin, smin, d2, D2, len;
+    unsigned magic, amask;     // amask: the two aliasing flags of the major axis inside x + y
+    int sh_maj, sh_min, fwd;   // flag positions; fwd = flag (1: k + 1, 2: k - 1) of the direction of travel along the major axis
+    uint32_t sink;             // slot-table value of an unallocated sub-tile (the spare sub-tile behind the pool)
+    int *overflow;
+};
+
+// Cell n of the ray (LUT index imaj along the major axis, num = n d2 + D): address of its storage cell and
+// its update (a | b << 8).  ab_in = update if the cell had its storage cell to itself, ab_next = the next cell's.
+template <bool CHECK>
+__device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int n, int imaj, unsigned num, int ab_in, int ab_next, int &ab)
+{
+    const unsigned m = __umulhi(num, k.magic);
+    const unsigned s = k.lut_s[imaj] + k.lut_s[k.bmin + k.smin * (int)m];
+    const uint32_t tt = k.tbl[(s >> 15) & 0x7ffu];
+    if (CHECK && tt == k.sink && ab_in) atomicExch(k.overflow, 2);   // an unallocated sub-tile under the ray's end: cannot happen after prepare
+    ab = ab_in;
+    if (s & k.amask) {                                               // shares its storage cell with a neighbour along the major axis
+        const unsigned A = (s >> k.sh_maj) & 3u, Bm = (s >> k.sh_min) & 3u;   // bit 0: with k + 1, bit 1: with k - 1
+        const int e = (int)(num - m * (unsigned)k.D2);
+        const bool bump_prev = e < k.d2, bump_next = e + k.d2 >= k.D2;        // the minor coordinate changes from n - 1 / to n + 1
+        const unsigned f = (unsigned)k.fwd, bk = 3u - f;
+        const unsigned fm = k.smin > 0 ? 1u : 2u, bm = 3u - fm;
+        const bool with_prev = n >= 1 && (A & bk) && (!bump_prev || (Bm & bm));
+        const bool with_next = n + 1 < k.len && (A & f) && (!bump_next || (Bm & fm));
+        if (ab_in) ab = with_prev ? 0 : with_next ? ab_in + ab_next : ab_in;  // the earlier cell's lane applies both, in order
+    }
+    return k.pool + (size_t)tt * RB_SUB_BYTES + (s & RC2_OFFMASK);
+}
+
+// NCH chunks of 32 consecutive cells, the loads of all chunks in flight together.  TAIL: the last chunk is the
+// ray's tail [len - 32, len); the others are "empty" cells (-0.3, floor -3.0) at n, n + 32, ...
+template <int NCH, bool TAIL>
+__device__ __forceinline__ void cast_group(const CastBeam &k, int &imaj, unsigned &num, int &n, int nf, int smaj32, unsigned d2x32,
+                                           int t_imaj, unsigned t_num, int t_n, int t_ab, int t_ab_next)
+{
+    int8_t *addr[NCH];
+    int ab[NCH], t[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+        if (TAIL && u == NCH - 1) {
+            addr[u] = cast_cell<true>(k, t_n, t_imaj, t_num, t_ab, t_ab_next, ab[u]);
+        } else {
+            // lanes past the last empty-only cell load a cell of the ray and store nothing
+            addr[u] = cast_cell<false>(k, n, imaj, num, n < nf ? RB_T_EMP : 0, RB_T_EMP, ab[u]);
+            n += 32;
+            imaj += smaj32;
+            num += d2x32;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; u++) t[u] = (int)*addr[u];
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+        int v;
+        if (TAIL && u == NCH - 1) v = min(max(t[u] - (ab[u] & 0xff), -RB_T_MAX) + (ab[u] >> 8), RB_T_MAX);
+        else v = max(t[u] - ab[u], -RB_T_MAX);                        // ab 0: v == t (cells are never below the floor)
+        if (v != t[u]) *addr[u] = (int8_t)v;                          // saturated cells (most of a built map) are not rewritten
+    }
+}
 
 __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_kernel(RbCtx c)
 {
@@ -754,21 +774,22 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
     uint32_t *lut_s = smem2;                                         // x entries, then y entries
     int4 *recs = reinterpret_cast<int4 *>(smem2 + nx + ny + warp * RC2_WARP_WORDS);
     double *frame = reinterpret_cast<double *>(smem2 + nx + ny + warp * RC2_WARP_WORDS + 256);
-    unsigned char *sub2tile = reinterpret_cast<unsigned char *>(smem2 + nx + ny + RC2_WARPS * RC2_WARP_WORDS);
+    uint32_t *tbl = smem2 + nx + ny + warp * RC2_WARP_WORDS + 256 + 16;
     for (int i = threadIdx.x; i < nx + ny; i += RC2_WARPS * 32) lut_s[i] = c.clut[i];
-    for (int i = threadIdx.x; i < c.nsub; i += RC2_WARPS * 32)
-        sub2tile[i] = (unsigned char)(((i / c.subs_x) / RB_SUBS_PER_TILE) * c.tiles_x + (i % c.subs_x) / RB_SUBS_PER_TILE);
     __syncthreads();
     if (c.flags->pool_exhausted) return;                             // prepare could not privatise: skip the scan
+    const int subs_x = c.subs_x;
 
     for (;;) {
         int p = 0;
         if (lane == 0) p = atomicAdd(c.cast_work, 1);
         p = __shfl_sync(FULL, p, 0);
         if (p >= c.N) break;
-        int sx, sy;
+        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
+        int sub_lo = 0;                                              // slot of the window corner (may lie outside the world)
         {
             double x, y, cs_, sn_;
+            int sx, sy;
             if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) continue;
             __syncwarp();
             if (lane == 0) {
@@ -776,104 +797,79 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                 reinterpret_cast<int *>(frame + 4)[0] = sx;
                 reinterpret_cast<int *>(frame + 4)[1] = sy;
             }
-        }
-        const uint32_t *pt = c.pt + (size_t)p * c.nsub;
-        const unsigned long long ex_mask = c.exists[p];
-        unsigned long long ex_new = 0ull;
-        // every ray starts in the robot's cell: its sub-tile is the page-table hit of each beam's first cells
-        CastLane cl0;
-        cl0.key = 0xffffffffu; cl0.base = c.pool;
-        {
+            // page-table entries of the 5 x 5 sub-tiles around the robot's; unallocated -> the sink sub-tile behind the pool
             const int ox = 800 * c.txh + 400, oy = 800 * c.tyh + 400;
             if ((unsigned)(sx + ox) < (unsigned)nx && (unsigned)(sy + oy) < (unsigned)ny) {
                 const unsigned s0 = lut_s[sx + ox] + lut_s[nx + sy + oy];
-                const uint32_t t0 = pt[(s0 & RC2_SUBMASK) >> 15];
-                if (t0 != RB_NONE) { cl0.key = s0 & RC2_SUBMASK; cl0.base = c.pool + (size_t)t0 * RB_SUB_BYTES; }
+                const int sub0 = (int)((s0 >> 15) & 0x7ffu);
+                const int subx0 = sub0 % subs_x, suby0 = sub0 / subs_x;
+                sub_lo = (suby0 - 2) * subs_x + (subx0 - 2);
+                if (lane < 25) {
+                    const int dy = lane / 5, dx = lane - 5 * dy;
+                    const int qx = subx0 - 2 + dx, qy = suby0 - 2 + dy;
+                    uint32_t tt = RB_NONE;
+                    if ((unsigned)qx < (unsigned)subs_x && (unsigned)qy < (unsigned)c.subs_y) tt = pt[qy * subs_x + qx];
+                    tbl[dy * subs_x + dx] = tt == RB_NONE ? c.pool_tiles : tt;
+                }
             }
         }
+        const unsigned long long ex_mask = c.exists[p];
+        unsigned long long ex_new = 0ull;
+        CastBeam k;
+        k.lut_s = lut_s;
+        k.tbl = tbl - sub_lo;
+        k.pool = c.pool;
+        k.sink = c.pool_tiles;
+        k.overflow = &c.flags->world_overflow;
 
         for (int j0 = 0; j0 < c.B; j0 += 32) {
             __syncwarp();
-            {
-                cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny);
-                __syncwarp();
-                const int nb = min(32, c.B - j0);
-                for (int b = 0; b < nb; b++) {
-                    const int4 ra = recs[2 * b];
-                    const int w0 = ra.x, len = w0 & 0xfff;
-                    if (len == 0) continue;                             // hybridmap.py:278-281 empty list
-                    const int4 rb = recs[2 * b + 1];
-                    const int occ = (w0 >> 12) & 1, steep = (w0 >> 13) & 1;
-                    if (!((w0 >> 14) & 1)) {
-                        ex_new |= cast_general_ray(c.pool, pt, c.lutx, c.luty, c.flags, c.stats, c.txh, c.tyh, c.subs_x, c.tiles_x, lane,
-                                                   reinterpret_cast<const int *>(frame + 4)[0], reinterpret_cast<const int *>(frame + 4)[1],
-                                                   len, occ, (int)(short)(rb.w & 0xffff), rb.w >> 16, rb.z, ex_mask);
-                        continue;
-                    }
-                    const int d2 = ra.y, D2 = ra.z;
-                    const unsigned magic = (unsigned)ra.w;
-                    const int bmaj = rb.x, bmin = rb.y;
-                    const int smaj = (w0 >> 15) & 1 ? -1 : 1, smin = ((w0 >> 16) & 3) - 1;
-                    const int sh_maj = steep ? 28 : 30, sh_min = steep ? 30 : 28;
-                    const unsigned keymask = RC2_SUBMASK | (3u << sh_maj);
-                    const int fwd = smaj > 0 ? 1 : 2;
-                    CastLane cl = cl0;
-                    // ---- tail chunk first: cells [len - 32, len), lane 31 = end cell, lane 30 = the cell before it
-                    const int nt = len - 32 + lane;
-                    int8_t *taddr = nullptr;
-                    int tops = 0;
-                    if (nt >= 0) {
-                        const unsigned num = (unsigned)nt * (unsigned)d2 + (unsigned)(D2 >> 1);
-                        const unsigned m = __umulhi(num, magic);
-                        const unsigned s = lut_s[bmaj + smaj * nt] + lut_s[bmin + smin * (int)m];
-                        if ((s & RC2_SUBMASK) != cl.key) cast_new_sub(c, pt, sub2tile, s, cl, ex_mask, ex_new);
-                        bool alias_prev = false, alias_next = false;
-                        const unsigned A = (s >> sh_maj) & 3u;
-                        if (A) {
-                            const unsigned Bm = (s >> sh_min) & 3u;
-                            const int e = (int)(num - m * (unsigned)D2);
-                            const bool bump_prev = e < d2, bump_next = e + d2 >= D2;
-                            const unsigned f = (unsigned)fwd, bk = 3u - f;
-                            const unsigned fm = smin > 0 ? 1u : 2u, bm = 3u - fm;
-                            alias_prev = nt >= 1 && (A & bk) && (!bump_prev || (Bm & bm));
-                            alias_next = nt + 1 < len && (A & f) && (!bump_next || (Bm & fm));
-                        }
-                        if (cl.key != 0xffffffffu && !alias_prev) {
-                            const int near_ok = (w0 >> 18) & 1;
-                            int o = (occ && lane == 31) ? 2 : 1;               // hybridmap.py:137-138 / :144
-                            if (near_ok && lane == 30) o |= 4;                 // hybridmap.py:139-142
-                            if (alias_next) {                                  // next cell's ops, applied after ours
-                                int o2 = (occ && lane == 30) ? 2 : 1;
-                                if (near_ok && lane == 29) o2 |= 4;
-                                o |= o2 << 3;
-                            }
-                            tops = o;
-                            taddr = cl.base + (s & RC2_OFFMASK);
-                        }
-                    }
-                    const int tt_ = tops ? (int)*taddr : 0;
-                    // ---- empty chunks over [0, len - 32)
-                    const int nf = len - 32;
-                    if (nf > 0) {
-                        cl = cl0;
-                        int imaj = bmaj + smaj * lane, n = lane;
-                        unsigned num = (unsigned)lane * (unsigned)d2 + (unsigned)(D2 >> 1);
-                        const int smaj32 = 32 * smaj;
-                        const unsigned d2x32 = 32u * (unsigned)d2;
-                        int left = (nf + 31) >> 5;
-#define RC2_GROUP(K) cast_empty_group<K>(c, lut_s, sub2tile, pt, imaj, num, n, nf, bmin, smaj32, smin, d2x32, magic, keymask, d2, D2, sh_maj, sh_min, fwd, cl, ex_mask, ex_new)
-                        while (left >= 4) { RC2_GROUP(4); left -= 4; }
-                        if (left == 3) RC2_GROUP(3);
-                        else if (left == 2) RC2_GROUP(2);
-                        else if (left == 1) RC2_GROUP(1);
-                    }
-                    if (tops) {
-                        int v = apply_ops(tt_, tops & 7);
-                        if (tops >> 3) v = apply_ops(v, tops >> 3);
-                        if (v != tt_) *taddr = (int8_t)v;
-                    }
-                    __syncwarp();                                       // the next beam must see these stores
+            ex_new |= cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny, ex_mask);
+            __syncwarp();
+            const int nb = min(32, c.B - j0);
+            for (int b = 0; b < nb; b++) {
+                const int4 ra = recs[2 * b];
+                const int w0 = ra.x, len = w0 & 0xfff;
+                if (len == 0) continue;                              // hybridmap.py:278-281 empty list
+                if (!((w0 >> 14) & 1)) {
+                    ex_new |= cast_general_ray(c.pool, pt, c.lutx, c.luty, c.flags, c.stats, c.txh, c.tyh, subs_x, c.tiles_x, lane,
+                                               c.px, c.py, c.dist, j0 + b, frame, ex_mask);
+                    continue;
                 }
+                const int4 rb = recs[2 * b + 1];
+                const int steep = (w0 >> 13) & 1;
+                k.d2 = ra.y; k.D2 = ra.z; k.magic = (unsigned)ra.w; k.bmin = rb.y; k.smin = rb.w; k.len = len;
+                const int bmaj = rb.x, smaj32 = rb.z;
+                k.sh_maj = steep ? 28 : 30; k.sh_min = steep ? 30 : 28;
+                k.amask = 3u << k.sh_maj;
+                k.fwd = smaj32 > 0 ? 1 : 2;
+                const int smaj = smaj32 >> 5;
+                const unsigned Dm = (unsigned)(k.D2 >> 1);
+                // tail chunk: cells [len - 32, len), lane 31 = end cell, lane 30 = the cell before it; lanes before the ray's
+                // start (len < 32) sit on cell 0 and do nothing
+                const int nt_ = len - 32 + lane, nt = max(nt_, 0);
+                const int occ = (w0 >> 12) & 1, near_ok = (w0 >> 15) & 1;
+                // updates (a | b << 8) of the end cell (+0.8 if it is an obstacle, hybridmap.py:137-138, else -0.3, :144), of the
+                // cell before it (-0.3 when the ray passed, then +0.2 if the end's tile holds it, :139-142) and of plain cells
+                const int ab_end = occ ? (RB_T_OCC << 8) : RB_T_EMP, ab_near = near_ok ? (RB_T_EMP | (RB_T_NEAR << 8)) : RB_T_EMP;
+                int t_ab = lane == 31 ? ab_end : lane == 30 ? ab_near : RB_T_EMP;
+                const int t_ab_next = lane == 30 ? ab_end : lane == 29 ? ab_near : RB_T_EMP;
+                if (nt_ < 0) t_ab = 0;
+                const int t_imaj = bmaj + smaj * nt;
+                const unsigned t_num = (unsigned)nt * (unsigned)k.d2 + Dm;
+                // empty chunks over [0, len - 32)
+                const int nf = len - 32;
+                int imaj = bmaj + smaj * lane, n = lane;
+                unsigned num = (unsigned)lane * (unsigned)k.d2 + Dm;
+                const unsigned d2x32 = 32u * (unsigned)k.d2;
+                int left = nf > 0 ? ((nf + 31) >> 5) + 1 : 1;        // chunks of the ray, tail included
+#define RC2_GROUP(K, T) cast_group<K, T>(k, imaj, num, n, nf, smaj32, d2x32, t_imaj, t_num, nt, t_ab, t_ab_next)
+                while (left > 4) { RC2_GROUP(4, false); left -= 4; }
+                if (left == 4) RC2_GROUP(4, true);
+                else if (left == 3) RC2_GROUP(3, true);
+                else if (left == 2) RC2_GROUP(2, true);
+                else RC2_GROUP(1, true);
+                __syncwarp();                                        // the next beam must see these stores
             }
         }
         // publish newly created reference tiles
@@ -959,8 +955,9 @@ void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
         return;
     }
     static const int use_v1 = getenv("RBPF_CAST_V1") && atoi(getenv("RBPF_CAST_V1")) > 0;
-    if (!use_v1) {
-        const size_t smem = sizeof(uint32_t) * (800 * (size_t)(c.tiles_x + c.tiles_y) + RC2_WARPS * RC2_WARP_WORDS) + (((size_t)c.nsub + 15) & ~(size_t)15);
+    const size_t lut_bytes2 = sizeof(uint32_t) * 800 * (size_t)(c.tiles_x + c.tiles_y);
+    if (!use_v1 && c.subs_x <= 40 && lut_bytes2 <= 64 * 1024) {      // larger worlds: the staged LUTs / the slot table do not fit
+        const size_t smem = sizeof(uint32_t) * (800 * (size_t)(c.tiles_x + c.tiles_y) + RC2_WARPS * RC2_WARP_WORDS);
         static size_t smem_set = 0;
         static int resident = 0;
         if (smem != smem_set) {
