@@ -517,15 +517,16 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 //   * per-beam constants go through shared memory (two 16-byte broadcasts per beam).
 // Rays that leave the world take cast_general_ray (the old per-cell path).
 #ifndef RC2_WARPS
-#define RC2_WARPS 8
-#endif
+#define RC2_WARPS 16                 // 2 CTAs of 16 warps per SM: the staged LUTs take 2 x 32 KB, the rest of the 256 KB stays L1
+#endif                               // (8 warps x 4 CTAs: 6.67 ms, 16 x 2: 6.32, 32 x 1: 6.26 at 65,536 particles)
 #ifndef RC2_MINBLOCKS
-#define RC2_MINBLOCKS 4
+#define RC2_MINBLOCKS 2
 #endif
 
 #define RC2_OFFMASK 0x00007fffu
-#define RC2_TBL_WORDS 168            // 4 * subs_x + 5 <= 165 entries (subs_x <= 40)
-#define RC2_WARP_WORDS (256 + 16 + RC2_TBL_WORDS)   // per warp: 32 records of 32 bytes, the particle's frame, the slot table
+#define RC2_TBL_ENTRIES 168          // slot table of a warp: 4 * subs_x + 5 <= 165 sub-tile base pointers (subs_x <= 40)
+#define RC2_WARP_WORDS (256 + 16)    // per warp: 32 records of 32 bytes, the particle's frame
+static_assert(RC2_WARPS * RC2_TBL_ENTRIES <= 8192, "slot-table entry index has 13 bits");
 
 // frame words (doubles): 0 x, 1 y, 2 cos, 3 sin; then ints at double index 4: sx, sy
 __device__ __forceinline__ Ray ray_of_beam_p(const double *px, const double *py, const double *dist, int j, double x, double y,
@@ -701,25 +702,28 @@ __device__ __noinline__ unsigned long long cast_setup_beams(const double *px, co
 }
 
 struct CastBeam {    // warp-uniform constants of the beam in flight
-    const uint32_t *lut_s;
-    const uint32_t *tbl;       // slot table, already offset by the window corner: tbl[slot]
-    int8_t *pool;
-    int bmin, smin, d2, D2, len;
+    const char *smem;          // start of the dynamic shared memory = start of the slot tables
+    const char *pminb;         // LUT entry of the minor coordinate of cell 0
+    int smin4;                 // 4 * step along the minor axis (bytes per LUT entry)
+    unsigned kadd;             // (first entry of this warp's slot table - slot of the window corner) << 15
+    int smin, d2, D2, len;
     unsigned magic, amask;     // amask: the two aliasing flags of the major axis inside x + y
     int sh_maj, sh_min, fwd;   // flag positions; fwd = flag (1: k + 1, 2: k - 1) of the direction of travel along the major axis
-    uint32_t sink;             // slot-table value of an unallocated sub-tile (the spare sub-tile behind the pool)
+    int ab_end, ab_near;       // updates (a | b << 8) of the end cell and of the cell before it
+    int8_t *sink;              // slot-table value of an unallocated sub-tile (the spare sub-tile behind the pool)
     int *overflow;
 };
 
-// Cell n of the ray (LUT index imaj along the major axis, num = n d2 + D): address of its storage cell and
-// its update (a | b << 8).  ab_in = update if the cell had its storage cell to itself, ab_next = the next cell's.
-template <bool CHECK>
-__device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int n, int imaj, unsigned num, int ab_in, int ab_next, int &ab)
+// Cell n of the ray (pmaj = LUT entry of its major coordinate, num = n d2 + D): address of its storage cell and
+// its update (a | b << 8).  ab_in = update if the cell had its storage cell to itself.
+template <bool TAIL>
+__device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int lane, int n, const uint32_t *pmaj, unsigned num, int ab_in, int &ab)
 {
     const unsigned m = __umulhi(num, k.magic);
-    const unsigned s = k.lut_s[imaj] + k.lut_s[k.bmin + k.smin * (int)m];
-    const uint32_t tt = k.tbl[(s >> 15) & 0x7ffu];
-    if (CHECK && tt == k.sink && ab_in) atomicExch(k.overflow, 2);   // an unallocated sub-tile under the ray's end: cannot happen after prepare
+    // offset (bits 0-14) | entry of the slot table (15-27) | aliasing flags (28-31)
+    const unsigned s = *pmaj + *reinterpret_cast<const uint32_t *>(k.pminb + k.smin4 * (int)m) + k.kadd;
+    int8_t *base = *reinterpret_cast<int8_t *const *>(k.smem + ((s >> 12) & 0xfff8u));
+    if (TAIL && base == k.sink && ab_in) atomicExch(k.overflow, 2);  // an unallocated sub-tile under the ray's end: cannot happen after prepare
     ab = ab_in;
     if (s & k.amask) {                                               // shares its storage cell with a neighbour along the major axis
         const unsigned A = (s >> k.sh_maj) & 3u, Bm = (s >> k.sh_min) & 3u;   // bit 0: with k + 1, bit 1: with k - 1
@@ -729,28 +733,31 @@ __device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int n, int imaj,
         const unsigned fm = k.smin > 0 ? 1u : 2u, bm = 3u - fm;
         const bool with_prev = n >= 1 && (A & bk) && (!bump_prev || (Bm & bm));
         const bool with_next = n + 1 < k.len && (A & f) && (!bump_next || (Bm & fm));
+        const int ab_next = !TAIL ? RB_T_EMP : lane == 30 ? k.ab_end : lane == 29 ? k.ab_near : RB_T_EMP;
         if (ab_in) ab = with_prev ? 0 : with_next ? ab_in + ab_next : ab_in;  // the earlier cell's lane applies both, in order
     }
-    return k.pool + (size_t)tt * RB_SUB_BYTES + (s & RC2_OFFMASK);
+    return base + (s & RC2_OFFMASK);
 }
 
 // NCH chunks of 32 consecutive cells, the loads of all chunks in flight together.  TAIL: the last chunk is the
-// ray's tail [len - 32, len); the others are "empty" cells (-0.3, floor -3.0) at n, n + 32, ...
+// ray's tail [len - 32, len) and the one before it the last of the "empty" chunks (-0.3, floor -3.0), whose
+// lanes past cell len - 33 load a cell of the ray and store nothing; all other chunks are 32 empty cells.
 template <int NCH, bool TAIL>
-__device__ __forceinline__ void cast_group(const CastBeam &k, int &imaj, unsigned &num, int &n, int nf, int smaj32, unsigned d2x32,
-                                           int t_imaj, unsigned t_num, int t_n, int t_ab, int t_ab_next)
+__device__ __forceinline__ void cast_group(const CastBeam &k, int lane, const uint32_t *&pmaj, unsigned &num, int &n, int nf, int smaj32,
+                                           unsigned d2x32, const uint32_t *t_pmaj, unsigned t_num, int t_n, int t_ab)
 {
     int8_t *addr[NCH];
     int ab[NCH], t[NCH];
 #pragma unroll
     for (int u = 0; u < NCH; u++) {
         if (TAIL && u == NCH - 1) {
-            addr[u] = cast_cell<true>(k, t_n, t_imaj, t_num, t_ab, t_ab_next, ab[u]);
+            addr[u] = cast_cell<true>(k, lane, t_n, t_pmaj, t_num, t_ab, ab[u]);
         } else {
-            // lanes past the last empty-only cell load a cell of the ray and store nothing
-            addr[u] = cast_cell<false>(k, n, imaj, num, n < nf ? RB_T_EMP : 0, RB_T_EMP, ab[u]);
+            // the last empty chunk sits before the tail, or closes a full group when only the tail is left after it
+            const bool maybe_partial = TAIL ? u == NCH - 2 : u == NCH - 1;
+            addr[u] = cast_cell<false>(k, lane, n, pmaj, num, maybe_partial ? (n < nf ? RB_T_EMP : 0) : RB_T_EMP, ab[u]);
             n += 32;
-            imaj += smaj32;
+            pmaj += smaj32;
             num += d2x32;
         }
     }
@@ -767,18 +774,20 @@ __device__ __forceinline__ void cast_group(const CastBeam &k, int &imaj, unsigne
 
 __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_kernel(RbCtx c)
 {
-    extern __shared__ uint32_t smem2[];
+    extern __shared__ __align__(16) uint32_t smem2[];
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nx = 800 * c.tiles_x, ny = 800 * c.tiles_y;
-    uint32_t *lut_s = smem2;                                         // x entries, then y entries
-    int4 *recs = reinterpret_cast<int4 *>(smem2 + nx + ny + warp * RC2_WARP_WORDS);
-    double *frame = reinterpret_cast<double *>(smem2 + nx + ny + warp * RC2_WARP_WORDS + 256);
-    uint32_t *tbl = smem2 + nx + ny + warp * RC2_WARP_WORDS + 256 + 16;
+    // slot tables first (their entry index has to fit the 13 bits between offset and flags), then the LUTs, then records + frames
+    int8_t **tbl = reinterpret_cast<int8_t **>(smem2) + warp * RC2_TBL_ENTRIES;
+    uint32_t *lut_s = smem2 + 2 * RC2_WARPS * RC2_TBL_ENTRIES;       // x entries, then y entries
+    int4 *recs = reinterpret_cast<int4 *>(lut_s + nx + ny + warp * RC2_WARP_WORDS);
+    double *frame = reinterpret_cast<double *>(lut_s + nx + ny + warp * RC2_WARP_WORDS + 256);
     for (int i = threadIdx.x; i < nx + ny; i += RC2_WARPS * 32) lut_s[i] = c.clut[i];
     __syncthreads();
     if (c.flags->pool_exhausted) return;                             // prepare could not privatise: skip the scan
     const int subs_x = c.subs_x;
+    int8_t *const sink = c.pool + (size_t)c.pool_tiles * RB_SUB_BYTES;
 
     for (;;) {
         int p = 0;
@@ -797,7 +806,7 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                 reinterpret_cast<int *>(frame + 4)[0] = sx;
                 reinterpret_cast<int *>(frame + 4)[1] = sy;
             }
-            // page-table entries of the 5 x 5 sub-tiles around the robot's; unallocated -> the sink sub-tile behind the pool
+            // the 5 x 5 sub-tiles around the robot's; unallocated -> the sink sub-tile behind the pool
             const int ox = 800 * c.txh + 400, oy = 800 * c.tyh + 400;
             if ((unsigned)(sx + ox) < (unsigned)nx && (unsigned)(sy + oy) < (unsigned)ny) {
                 const unsigned s0 = lut_s[sx + ox] + lut_s[nx + sy + oy];
@@ -809,17 +818,16 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                     const int qx = subx0 - 2 + dx, qy = suby0 - 2 + dy;
                     uint32_t tt = RB_NONE;
                     if ((unsigned)qx < (unsigned)subs_x && (unsigned)qy < (unsigned)c.subs_y) tt = pt[qy * subs_x + qx];
-                    tbl[dy * subs_x + dx] = tt == RB_NONE ? c.pool_tiles : tt;
+                    tbl[dy * subs_x + dx] = tt == RB_NONE ? sink : c.pool + (size_t)tt * RB_SUB_BYTES;
                 }
             }
         }
         const unsigned long long ex_mask = c.exists[p];
         unsigned long long ex_new = 0ull;
         CastBeam k;
-        k.lut_s = lut_s;
-        k.tbl = tbl - sub_lo;
-        k.pool = c.pool;
-        k.sink = c.pool_tiles;
+        k.smem = reinterpret_cast<const char *>(smem2);
+        k.kadd = (unsigned)(warp * RC2_TBL_ENTRIES - sub_lo) << 15;
+        k.sink = sink;
         k.overflow = &c.flags->world_overflow;
 
         for (int j0 = 0; j0 < c.B; j0 += 32) {
@@ -838,32 +846,35 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                 }
                 const int4 rb = recs[2 * b + 1];
                 const int steep = (w0 >> 13) & 1;
-                k.d2 = ra.y; k.D2 = ra.z; k.magic = (unsigned)ra.w; k.bmin = rb.y; k.smin = rb.w; k.len = len;
-                const int bmaj = rb.x, smaj32 = rb.z;
+                k.d2 = ra.y; k.D2 = ra.z; k.magic = (unsigned)ra.w; k.smin = rb.w; k.len = len;
+                k.pminb = reinterpret_cast<const char *>(lut_s + rb.y);
+                k.smin4 = 4 * rb.w;
+                const int smaj32 = rb.z;
                 k.sh_maj = steep ? 28 : 30; k.sh_min = steep ? 30 : 28;
                 k.amask = 3u << k.sh_maj;
                 k.fwd = smaj32 > 0 ? 1 : 2;
                 const int smaj = smaj32 >> 5;
                 const unsigned Dm = (unsigned)(k.D2 >> 1);
+                // updates (a | b << 8) of the end cell (+0.8 if it is an obstacle, hybridmap.py:137-138, else -0.3, :144) and of the
+                // cell before it (-0.3 when the ray passed, then +0.2 if the end's tile holds it, :139-142)
+                k.ab_end = (w0 >> 12) & 1 ? (RB_T_OCC << 8) : RB_T_EMP;
+                k.ab_near = (w0 >> 15) & 1 ? (RB_T_EMP | (RB_T_NEAR << 8)) : RB_T_EMP;
                 // tail chunk: cells [len - 32, len), lane 31 = end cell, lane 30 = the cell before it; lanes before the ray's
                 // start (len < 32) sit on cell 0 and do nothing
                 const int nt_ = len - 32 + lane, nt = max(nt_, 0);
-                const int occ = (w0 >> 12) & 1, near_ok = (w0 >> 15) & 1;
-                // updates (a | b << 8) of the end cell (+0.8 if it is an obstacle, hybridmap.py:137-138, else -0.3, :144), of the
-                // cell before it (-0.3 when the ray passed, then +0.2 if the end's tile holds it, :139-142) and of plain cells
-                const int ab_end = occ ? (RB_T_OCC << 8) : RB_T_EMP, ab_near = near_ok ? (RB_T_EMP | (RB_T_NEAR << 8)) : RB_T_EMP;
-                int t_ab = lane == 31 ? ab_end : lane == 30 ? ab_near : RB_T_EMP;
-                const int t_ab_next = lane == 30 ? ab_end : lane == 29 ? ab_near : RB_T_EMP;
+                int t_ab = lane == 31 ? k.ab_end : lane == 30 ? k.ab_near : RB_T_EMP;
                 if (nt_ < 0) t_ab = 0;
-                const int t_imaj = bmaj + smaj * nt;
+                const uint32_t *pmaj0 = lut_s + rb.x;
+                const uint32_t *t_pmaj = pmaj0 + smaj * nt;
                 const unsigned t_num = (unsigned)nt * (unsigned)k.d2 + Dm;
                 // empty chunks over [0, len - 32)
                 const int nf = len - 32;
-                int imaj = bmaj + smaj * lane, n = lane;
+                const uint32_t *pmaj = pmaj0 + smaj * lane;
+                int n = lane;
                 unsigned num = (unsigned)lane * (unsigned)k.d2 + Dm;
                 const unsigned d2x32 = 32u * (unsigned)k.d2;
                 int left = nf > 0 ? ((nf + 31) >> 5) + 1 : 1;        // chunks of the ray, tail included
-#define RC2_GROUP(K, T) cast_group<K, T>(k, imaj, num, n, nf, smaj32, d2x32, t_imaj, t_num, nt, t_ab, t_ab_next)
+#define RC2_GROUP(K, T) cast_group<K, T>(k, lane, pmaj, num, n, nf, smaj32, d2x32, t_pmaj, t_num, nt, t_ab)
                 while (left > 4) { RC2_GROUP(4, false); left -= 4; }
                 if (left == 4) RC2_GROUP(4, true);
                 else if (left == 3) RC2_GROUP(3, true);
@@ -957,7 +968,7 @@ void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
     static const int use_v1 = getenv("RBPF_CAST_V1") && atoi(getenv("RBPF_CAST_V1")) > 0;
     const size_t lut_bytes2 = sizeof(uint32_t) * 800 * (size_t)(c.tiles_x + c.tiles_y);
     if (!use_v1 && c.subs_x <= 40 && lut_bytes2 <= 64 * 1024) {      // larger worlds: the staged LUTs / the slot table do not fit
-        const size_t smem = sizeof(uint32_t) * (800 * (size_t)(c.tiles_x + c.tiles_y) + RC2_WARPS * RC2_WARP_WORDS);
+        const size_t smem = sizeof(uint32_t) * (800 * (size_t)(c.tiles_x + c.tiles_y) + RC2_WARPS * (RC2_WARP_WORDS + 2 * RC2_TBL_ENTRIES));
         static size_t smem_set = 0;
         static int resident = 0;
         if (smem != smem_set) {
