@@ -36,7 +36,7 @@ MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
 # profiles/r2_*_raw.csv).  The matcher's is below its algorithmic figure: only blocks under the reference-set mask
 # are fetched and particles that share sub-tiles after a resample hit in L2.
 MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.79e6 + 5.21e6) / 8192
-CAST_DRAM_BYTES_PER_UPDATE_NCU = (473.00e6 + 318.49e6) / 8192
+CAST_DRAM_BYTES_PER_UPDATE_NCU = (472.18e6 + 322.54e6) / 8192      # raycast_cast2_kernel, profiles/r2_cast2_raw.csv
 WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.33e6 + 3.08e6) / 8192
 PREPARE_DRAM_BYTES_PER_UPDATE_NCU = (134.72e6 + 91.77e6) / 8192
 
@@ -376,7 +376,7 @@ def run_b200(args):
     per_update = {
         "match_kernel": ("match", MATCH_BYTES_PER_UPDATE, "int8 cells of the 240-degree sector of radius 11.7 m the search can reach",
                          MATCH_DRAM_BYTES_PER_UPDATE_NCU),
-        "raycast_cast_kernel": ("raycast_cast", 2.0 * a_r, "read + write of the int8 cells under the rays (A_r = sum min(r, 15 m) / 5 cm)", CAST_DRAM_BYTES_PER_UPDATE_NCU),
+        "raycast_cast2_kernel": ("raycast_cast", 2.0 * a_r, "read + write of the int8 cells under the rays (A_r = sum min(r, 15 m) / 5 cm)", CAST_DRAM_BYTES_PER_UPDATE_NCU),
         "raycast_prepare_kernel": ("raycast_prepare", (2.0 * cow + fresh) * 25600.0 / n_local,
                                    "copy-on-write: 2 x 25,600 B per shared sub-tile made private, 25,600 B per fresh one", PREPARE_DRAM_BYTES_PER_UPDATE_NCU),
         "weight_kernel": ("weight", 32.0 * args.beams, "one 32-byte sector per beam (the 30 samples of a beam fall into the same cells)", WEIGHT_DRAM_BYTES_PER_UPDATE_NCU),

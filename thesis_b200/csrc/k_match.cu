@@ -204,11 +204,14 @@ __device__ __forceinline__ unsigned long long mt_lane_key(const uint32_t pl[MT_P
 // Rasterise the curr points for rotation k into packed bitmap addresses.
 //
 // The lattice point is floor(v) of a float64 expression (same operations as the oracle).  A
-// float32 evaluation of v (points pre-scaled to cells, fused multiply-adds) is within 1e-4
-// of it (|v| < 256: conversions 2 x 1.3e-5, two roundings 1.4e-5 each, per term), so its floor
-// is the same unless v32 lies within MT_RAS_EPS of an integer -- only those points (0.4 %)
-// take the float64 expression.
-#define MT_RAS_EPS 2e-3f
+// float32 evaluation of v (points pre-scaled to cells, fused multiply-adds) is within 5e-5
+// of it (|c| <= 220 cells, |v| < 256: the two points' conversions 7.6e-6 and 3.8e-6 (|sin| <= 0.5), the
+// conversions of cos / sin 1.3e-5 and 6.6e-6, two roundings of 7.6e-6), so its floor is the same
+// unless v32 lies within MT_RAS_EPS of an integer -- only those points (0.05 %) take the float64
+// expression.  (2e-3 until round 2: one warp iteration in eight ran both paths.)
+#ifndef MT_RAS_EPS
+#define MT_RAS_EPS 2.5e-4f
+#endif
 struct MtRot {                                                             // one rotation of the search, per lane
     float ckf, skf, fxf, fyf;
     int k, xoff, yoff;
@@ -242,7 +245,7 @@ __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared 
         ox = __double2int_rd(rxq * 20.0 + 0.5); oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
     }
     int bx = ox + r.xoff, by = oy + r.yoff;
-    if (bx < 0 || bx + span_i >= 32 * (RB_BM_STRIDE - 1) || by < 0 || by + span_j >= RB_BM_ROWS) {
+    if ((unsigned)bx >= (unsigned)(32 * (RB_BM_STRIDE - 1) - span_i) || (unsigned)by >= (unsigned)(RB_BM_ROWS - span_j)) {
         sh->overflow = 1;                                                  // cannot happen for |c| < 11 m
         bx = 0; by = 0;
     }

@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 //     [len - 32, len) with the end / nearby cells in lanes 31 / 30; every cell's update is
 //     v = min(max(t - a, -30) + b, 30) with (a, b) per lane, which also covers two ray cells
 //     that share a storage cell (the earlier lane applies both, the later one nothing);
-//   * per-beam constants go through shared memory (two 16-byte broadcasts per beam).
+//   * per-beam constants go through shared memory (three 16-byte broadcasts per beam).
 // Rays that leave the world take cast_general_ray (the old per-cell path).
 #ifndef RC2_WARPS
 #define RC2_WARPS 16                 // 2 CTAs of 16 warps per SM: the staged LUTs take 2 x 32 KB, the rest of the 256 KB stays L1
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 
 #define RC2_OFFMASK 0x00007fffu
 #define RC2_TBL_ENTRIES 168          // slot table of a warp: 4 * subs_x + 5 <= 165 sub-tile base pointers (subs_x <= 40)
-#define RC2_WARP_WORDS (256 + 16)    // per warp: 32 records of 32 bytes, the particle's frame
+#define RC2_WARP_WORDS (384 + 16)    // per warp: 32 records of 48 bytes, the particle's frame
 static_assert(RC2_WARPS * RC2_TBL_ENTRIES <= 8192, "slot-table entry index has 13 bits");
 
 // frame words (doubles): 0 x, 1 y, 2 cos, 3 sin; then ints at double index 4: sx, sy
@@ -644,18 +644,23 @@ __device__ __noinline__ unsigned long long cast_general_ray(int8_t *pool, const 
 
 // Per-beam constants of beams j0 .. j0 + 31 (one beam per lane) into the warp's record table; returns the
 // reference tiles this lane's beam creates.  Out of line: the float64 frame and the per-beam geometry do not
-// take registers away from the cell loop.
-//   record word 0: len (bits 0-11) | occ << 12 | steep << 13 | fast << 14 | near_ok << 15
-//          1-3   : d2 = 2 * minor extent, D2 = 2 * major extent (>= 2), magic = ceil(2^32 / D2)
-//          4-5   : index into the staged LUTs of the major / minor coordinate of cell 0
-//          6-7   : 32 * (step along the major axis), step along the minor axis
+// take registers away from the cell loop.  A record is 12 words (three 16-byte broadcasts per beam):
+//   0    : len (bits 0-11) | occ << 12 | steep << 13 | fast << 14 | near_ok << 15 | (step along the major axis < 0) << 16
+//   1-3  : d2 = 2 * minor extent, D = major extent (>= 1), magic = ceil(2^32 / 2 D)
+//   4-5  : byte offsets (from the start of the dynamic shared memory) of the LUT entries of cell 0's major / minor coordinate
+//   6-7  : 4 * step along the major axis, 4 * step along the minor axis (bytes per LUT entry)
+//   8    : the two aliasing flags of the major axis inside the LUT sum
+//   9    : chunks of 32 cells, tail included
+//   10-11: updates (a | b << 8) of the end cell (+0.8 if it is an obstacle, hybridmap.py:137-138, else -0.3, :144) and of
+//          the cell before it (-0.3 when the ray passed, then +0.2 if the end's tile holds it, :139-142)
 __device__ __noinline__ unsigned long long cast_setup_beams(const double *px, const double *py, const double *dist, const uint32_t *lutx,
                                                             const uint32_t *luty, int txh, int tyh, int tiles_x, int B, int j0, int lane,
-                                                            const double *frame, int4 *recs, int nx, int ny, unsigned long long ex_mask)
+                                                            const double *frame, int4 *recs, int nx, int ny, int lut_off,
+                                                            unsigned long long ex_mask)
 {
     const int ox = 800 * txh + 400, oy = 800 * tyh + 400;
     unsigned long long ex_new = 0ull;
-    int4 ra = make_int4(0, 0, 2, 0), rb = make_int4(0, 0, 32, 0);
+    int4 ra = make_int4(0, 0, 1, 0), rb = make_int4(0, 0, 4, 0), rc = make_int4(0, 1, RB_T_EMP, RB_T_EMP);
     if (j0 + lane < B) {
         const int sx = reinterpret_cast<const int *>(frame + 4)[0], sy = reinterpret_cast<const int *>(frame + 4)[1];
         const Ray r = ray_of_beam_p(px, py, dist, j0 + lane, frame[0], frame[1], frame[2], frame[3], sx, sy);
@@ -687,52 +692,59 @@ __device__ __noinline__ unsigned long long cast_setup_beams(const double *px, co
                 }
             }
         }
-        ra.x = len | (r.occ << 12) | (st.steep << 13) | (fast << 14) | (near_ok << 15);
+        ra.x = len | (r.occ << 12) | (st.steep << 13) | (fast << 14) | (near_ok << 15) | ((st.smaj < 0) << 16);
         ra.y = (int)st.d2;
-        ra.z = (int)st.D2;
+        ra.z = (int)st.D;
         ra.w = (int)(unsigned)((0x100000000ull + st.D2 - 1) / st.D2);
-        rb.x = st.steep ? nx + sy + oy : sx + ox;
-        rb.y = st.steep ? sx + ox : nx + sy + oy;
-        rb.z = 32 * st.smaj;
-        rb.w = st.smin;
+        rb.x = lut_off + 4 * (st.steep ? nx + sy + oy : sx + ox);
+        rb.y = lut_off + 4 * (st.steep ? sx + ox : nx + sy + oy);
+        rb.z = 4 * st.smaj;
+        rb.w = 4 * st.smin;
+        rc.x = (int)(3u << (st.steep ? 28 : 30));
+        rc.y = max((len + 31) >> 5, 1);
+        rc.z = r.occ ? (RB_T_OCC << 8) : RB_T_EMP;
+        rc.w = near_ok ? (RB_T_EMP | (RB_T_NEAR << 8)) : RB_T_EMP;
     }
-    recs[2 * lane] = ra;
-    recs[2 * lane + 1] = rb;
+    recs[3 * lane] = ra;
+    recs[3 * lane + 1] = rb;
+    recs[3 * lane + 2] = rc;
     return ex_new;
 }
 
 struct CastBeam {    // warp-uniform constants of the beam in flight
     const char *smem;          // start of the dynamic shared memory = start of the slot tables
-    const char *pminb;         // LUT entry of the minor coordinate of cell 0
+    int pminb;                 // byte offset of the LUT entry of the minor coordinate of cell 0
     int smin4;                 // 4 * step along the minor axis (bytes per LUT entry)
     unsigned kadd;             // (first entry of this warp's slot table - slot of the window corner) << 15
-    int smin, d2, D2, len;
+    int w0, d2, Dm;            // record word 0, 2 * minor extent, major extent
     unsigned magic, amask;     // amask: the two aliasing flags of the major axis inside x + y
-    int sh_maj, sh_min, fwd;   // flag positions; fwd = flag (1: k + 1, 2: k - 1) of the direction of travel along the major axis
     int ab_end, ab_near;       // updates (a | b << 8) of the end cell and of the cell before it
     int8_t *sink;              // slot-table value of an unallocated sub-tile (the spare sub-tile behind the pool)
     int *overflow;
 };
 
-// Cell n of the ray (pmaj = LUT entry of its major coordinate, num = n d2 + D): address of its storage cell and
-// its update (a | b << 8).  ab_in = update if the cell had its storage cell to itself.
+// Cell n of the ray (pmaj = byte offset of the LUT entry of its major coordinate, num = n d2 + D): address of its
+// storage cell and its update (a | b << 8).  ab_in = update if the cell had its storage cell to itself.
 template <bool TAIL>
-__device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int lane, int n, const uint32_t *pmaj, unsigned num, int ab_in, int &ab)
+__device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int lane, int n, int pmaj, unsigned num, int ab_in, int &ab)
 {
     const unsigned m = __umulhi(num, k.magic);
     // offset (bits 0-14) | entry of the slot table (15-27) | aliasing flags (28-31)
-    const unsigned s = *pmaj + *reinterpret_cast<const uint32_t *>(k.pminb + k.smin4 * (int)m) + k.kadd;
+    const unsigned s = *reinterpret_cast<const uint32_t *>(k.smem + pmaj) +
+                       *reinterpret_cast<const uint32_t *>(k.smem + (k.pminb + k.smin4 * (int)m)) + k.kadd;
     int8_t *base = *reinterpret_cast<int8_t *const *>(k.smem + ((s >> 12) & 0xfff8u));
     if (TAIL && base == k.sink && ab_in) atomicExch(k.overflow, 2);  // an unallocated sub-tile under the ray's end: cannot happen after prepare
     ab = ab_in;
     if (s & k.amask) {                                               // shares its storage cell with a neighbour along the major axis
-        const unsigned A = (s >> k.sh_maj) & 3u, Bm = (s >> k.sh_min) & 3u;   // bit 0: with k + 1, bit 1: with k - 1
-        const int e = (int)(num - m * (unsigned)k.D2);
-        const bool bump_prev = e < k.d2, bump_next = e + k.d2 >= k.D2;        // the minor coordinate changes from n - 1 / to n + 1
-        const unsigned f = (unsigned)k.fwd, bk = 3u - f;
-        const unsigned fm = k.smin > 0 ? 1u : 2u, bm = 3u - fm;
+        const int steep = (k.w0 >> 13) & 1, len = k.w0 & 0xfff, D2 = 2 * k.Dm;
+        const int sh_maj = steep ? 28 : 30, sh_min = steep ? 30 : 28;
+        const unsigned A = (s >> sh_maj) & 3u, Bm = (s >> sh_min) & 3u;       // bit 0: with k + 1, bit 1: with k - 1
+        const int e = (int)(num - m * (unsigned)D2);
+        const bool bump_prev = e < k.d2, bump_next = e + k.d2 >= D2;          // the minor coordinate changes from n - 1 / to n + 1
+        const unsigned f = (k.w0 >> 16) & 1 ? 2u : 1u, bk = 3u - f;           // flag of the direction of travel along the major axis
+        const unsigned fm = k.smin4 > 0 ? 1u : 2u, bm = 3u - fm;
         const bool with_prev = n >= 1 && (A & bk) && (!bump_prev || (Bm & bm));
-        const bool with_next = n + 1 < k.len && (A & f) && (!bump_next || (Bm & fm));
+        const bool with_next = n + 1 < len && (A & f) && (!bump_next || (Bm & fm));
         const int ab_next = !TAIL ? RB_T_EMP : lane == 30 ? k.ab_end : lane == 29 ? k.ab_near : RB_T_EMP;
         if (ab_in) ab = with_prev ? 0 : with_next ? ab_in + ab_next : ab_in;  // the earlier cell's lane applies both, in order
     }
@@ -743,8 +755,8 @@ __device__ __forceinline__ int8_t *cast_cell(const CastBeam &k, int lane, int n,
 // ray's tail [len - 32, len) and the one before it the last of the "empty" chunks (-0.3, floor -3.0), whose
 // lanes past cell len - 33 load a cell of the ray and store nothing; all other chunks are 32 empty cells.
 template <int NCH, bool TAIL>
-__device__ __forceinline__ void cast_group(const CastBeam &k, int lane, const uint32_t *&pmaj, unsigned &num, int &n, int nf, int smaj32,
-                                           unsigned d2x32, const uint32_t *t_pmaj, unsigned t_num, int t_n, int t_ab)
+__device__ __forceinline__ void cast_group(const CastBeam &k, int lane, int &pmaj, unsigned &num, int &n, int nf, int smaj128,
+                                           unsigned d2x32, int t_pmaj, unsigned t_num, int t_n, int t_ab)
 {
     int8_t *addr[NCH];
     int ab[NCH], t[NCH];
@@ -757,7 +769,7 @@ __device__ __forceinline__ void cast_group(const CastBeam &k, int lane, const ui
             const bool maybe_partial = TAIL ? u == NCH - 2 : u == NCH - 1;
             addr[u] = cast_cell<false>(k, lane, n, pmaj, num, maybe_partial ? (n < nf ? RB_T_EMP : 0) : RB_T_EMP, ab[u]);
             n += 32;
-            pmaj += smaj32;
+            pmaj += smaj128;
             num += d2x32;
         }
     }
@@ -782,12 +794,13 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
     int8_t **tbl = reinterpret_cast<int8_t **>(smem2) + warp * RC2_TBL_ENTRIES;
     uint32_t *lut_s = smem2 + 2 * RC2_WARPS * RC2_TBL_ENTRIES;       // x entries, then y entries
     int4 *recs = reinterpret_cast<int4 *>(lut_s + nx + ny + warp * RC2_WARP_WORDS);
-    double *frame = reinterpret_cast<double *>(lut_s + nx + ny + warp * RC2_WARP_WORDS + 256);
+    double *frame = reinterpret_cast<double *>(lut_s + nx + ny + warp * RC2_WARP_WORDS + 384);
     for (int i = threadIdx.x; i < nx + ny; i += RC2_WARPS * 32) lut_s[i] = c.clut[i];
     __syncthreads();
     if (c.flags->pool_exhausted) return;                             // prepare could not privatise: skip the scan
     const int subs_x = c.subs_x;
     int8_t *const sink = c.pool + (size_t)c.pool_tiles * RB_SUB_BYTES;
+    const int lane_m32 = lane - 32;
 
     for (;;) {
         int p = 0;
@@ -832,11 +845,12 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
 
         for (int j0 = 0; j0 < c.B; j0 += 32) {
             __syncwarp();
-            ex_new |= cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny, ex_mask);
+            ex_new |= cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny,
+                                       8 * RC2_WARPS * RC2_TBL_ENTRIES, ex_mask);
             __syncwarp();
             const int nb = min(32, c.B - j0);
             for (int b = 0; b < nb; b++) {
-                const int4 ra = recs[2 * b];
+                const int4 ra = recs[3 * b];
                 const int w0 = ra.x, len = w0 & 0xfff;
                 if (len == 0) continue;                              // hybridmap.py:278-281 empty list
                 if (!((w0 >> 14) & 1)) {
@@ -844,37 +858,26 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                                                c.px, c.py, c.dist, j0 + b, frame, ex_mask);
                     continue;
                 }
-                const int4 rb = recs[2 * b + 1];
-                const int steep = (w0 >> 13) & 1;
-                k.d2 = ra.y; k.D2 = ra.z; k.magic = (unsigned)ra.w; k.smin = rb.w; k.len = len;
-                k.pminb = reinterpret_cast<const char *>(lut_s + rb.y);
-                k.smin4 = 4 * rb.w;
-                const int smaj32 = rb.z;
-                k.sh_maj = steep ? 28 : 30; k.sh_min = steep ? 30 : 28;
-                k.amask = 3u << k.sh_maj;
-                k.fwd = smaj32 > 0 ? 1 : 2;
-                const int smaj = smaj32 >> 5;
-                const unsigned Dm = (unsigned)(k.D2 >> 1);
-                // updates (a | b << 8) of the end cell (+0.8 if it is an obstacle, hybridmap.py:137-138, else -0.3, :144) and of the
-                // cell before it (-0.3 when the ray passed, then +0.2 if the end's tile holds it, :139-142)
-                k.ab_end = (w0 >> 12) & 1 ? (RB_T_OCC << 8) : RB_T_EMP;
-                k.ab_near = (w0 >> 15) & 1 ? (RB_T_EMP | (RB_T_NEAR << 8)) : RB_T_EMP;
+                const int4 rb = recs[3 * b + 1], rc = recs[3 * b + 2];
+                k.w0 = w0; k.d2 = ra.y; k.Dm = ra.z; k.magic = (unsigned)ra.w;
+                k.pminb = rb.y; k.smin4 = rb.w;
+                k.amask = (unsigned)rc.x; k.ab_end = rc.z; k.ab_near = rc.w;
+                const int smaj4 = rb.z;
                 // tail chunk: cells [len - 32, len), lane 31 = end cell, lane 30 = the cell before it; lanes before the ray's
                 // start (len < 32) sit on cell 0 and do nothing
-                const int nt_ = len - 32 + lane, nt = max(nt_, 0);
+                const int nt_ = len + lane_m32, nt = max(nt_, 0);
                 int t_ab = lane == 31 ? k.ab_end : lane == 30 ? k.ab_near : RB_T_EMP;
                 if (nt_ < 0) t_ab = 0;
-                const uint32_t *pmaj0 = lut_s + rb.x;
-                const uint32_t *t_pmaj = pmaj0 + smaj * nt;
-                const unsigned t_num = (unsigned)nt * (unsigned)k.d2 + Dm;
+                const int t_pmaj = rb.x + smaj4 * nt;
+                const unsigned t_num = (unsigned)nt * (unsigned)k.d2 + (unsigned)k.Dm;
                 // empty chunks over [0, len - 32)
                 const int nf = len - 32;
-                const uint32_t *pmaj = pmaj0 + smaj * lane;
-                int n = lane;
-                unsigned num = (unsigned)lane * (unsigned)k.d2 + Dm;
+                int pmaj = rb.x + smaj4 * lane, n = lane;
+                unsigned num = (unsigned)lane * (unsigned)k.d2 + (unsigned)k.Dm;
                 const unsigned d2x32 = 32u * (unsigned)k.d2;
-                int left = nf > 0 ? ((nf + 31) >> 5) + 1 : 1;        // chunks of the ray, tail included
-#define RC2_GROUP(K, T) cast_group<K, T>(k, lane, pmaj, num, n, nf, smaj32, d2x32, t_pmaj, t_num, nt, t_ab)
+                const int smaj128 = 32 * smaj4;
+                int left = rc.y;                                     // chunks of the ray, tail included
+#define RC2_GROUP(K, T) cast_group<K, T>(k, lane, pmaj, num, n, nf, smaj128, d2x32, t_pmaj, t_num, nt, t_ab)
                 while (left > 4) { RC2_GROUP(4, false); left -= 4; }
                 if (left == 4) RC2_GROUP(4, true);
                 else if (left == 3) RC2_GROUP(3, true);
