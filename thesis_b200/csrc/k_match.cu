@@ -820,33 +820,37 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         const int x0 = sh->x0, y0 = sh->y0;
         uint32_t *H = bm, *Gp = bmg;                                        // both free until the dilation pass
         for (int idx = tid; idx < MT_RAW_ROWS * RB_RAW_STRIDE; idx += MT_THREADS) raw[idx] = 0u;
-        // rows: |ref| < 11.5 m (:239) as a column interval [lo, hi) per bitmap row, float64 predicate as in the oracle
+        // rows: |ref| < 11.5 m (:239) as a column interval [lo, hi) per bitmap row, float64 predicate as in the oracle:
+        // sqrt(dx^2 + dy^2) < 11.5 holds exactly when dx^2 + dy^2 < 132.25 (sqrt is correctly rounded and monotone, 132.25 and
+        // 11.5 are exact, and the double below 132.25 has a root 0.7 ulp below 11.5), so the per-column test is one fused
+        // multiply-add on a table of the 512 column offsets -- the float64 divisions of index_to_distance happen once per column
+        // and row instead of once per probe.  The table sits in Gp, which is free until the first prefix pass.
+        double *colx = reinterpret_cast<double *>(Gp);
+        for (int cb = tid; cb < 512; cb += MT_THREADS) {
+            const int ux = x0 + cb;
+            const int tX = (ux + 800 * 1024) / 800 - 1024, ix = ux - 800 * tX;
+            colx[cb] = rb_cell_corner(ix, tX - c.txh) - sh->gx;
+        }
+        __syncthreads();
         for (int r = tid; r < RB_BM_ROWS; r += MT_THREADS) {
             const int uy = y0 + r;
             const int tY = (uy + 800 * 1024) / 800 - 1024, iy = uy - 800 * tY;
             const double dyr = rb_cell_corner(iy, tY - c.tyh) - sh->gy;
             int lo = 0, hi = 0;
-            const double lim = RB_MATCH_MAX_R + 0.5;
-            if (fabs(dyr) < lim) {
-                const double dy2 = dyr * dyr;
-                auto inside = [&](int cbit) {
-                    const int ux = x0 + cbit;
-                    const int tX = (ux + 800 * 1024) / 800 - 1024, ix = ux - 800 * tX;
-                    const double dxr = rb_cell_corner(ix, tX - c.txh) - sh->gx;
-                    return sqrt(dxr * dxr + dy2) < lim;
-                };
-                // column c is dx = (c - cg) * 0.05 - fx away from the guess (0 <= fx < 0.05): the interval ends lie
-                // within one column of these estimates; the float64 predicate of the oracle decides
-                const double half = sqrt(lim * lim - dy2) * 20.0;
+            const double lim = RB_MATCH_MAX_R + 0.5, lim2 = lim * lim;
+            const double dy2 = dyr * dyr;
+            if (dy2 < lim2) {
+                auto inside = [&](int cbit) { const double dxr = colx[cbit]; return dxr * dxr + dy2 < lim2; };
+                // column c is dx = (c - cg) * 0.05 - fx away from the guess (0 <= fx < 0.05): a float32 estimate of the interval
+                // ends, then the float64 predicate decides (the interval is contiguous: the column offsets are monotone)
+                const int half = (int)(sqrtf((float)(lim2 - dy2)) * 20.0f);
                 const int cg = sh->g0xu - x0;
-                lo = cg - (int)half;
-                hi = cg + (int)half + 2;
-                if (inside(lo - 1)) lo--;
+                lo = min(max(cg - half, 0), 512);
+                hi = min(max(cg + half + 2, lo), 512);
+                while (lo > 0 && inside(lo - 1)) lo--;
                 while (lo < hi && !inside(lo)) lo++;
-                if (inside(hi)) hi++;
+                while (hi < 512 && inside(hi)) hi++;
                 while (hi > lo && !inside(hi - 1)) hi--;
-                lo = max(lo, 0); hi = min(hi, 512);
-                if (hi < lo) hi = lo;
             }
             sh->row_lo[r] = (unsigned short)lo;
             sh->row_hi[r] = (unsigned short)hi;
@@ -923,9 +927,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             }
             __syncthreads();
         }
-        if (tid < MT_NBLK) {
-            const int rb = tid / RB_RAW_STRIDE, wc = tid - rb * RB_RAW_STRIDE;
-            if ((sh->need[rb] >> wc) & 1u) sh->blist[atomicAdd(&sh->nblk, 1)] = (unsigned short)tid;
+        static_assert(MT_NBLK <= MT_THREADS, "one thread per block of the staging window");
+        {
+            bool want = false;
+            if (tid < MT_NBLK) {
+                const int rb = tid / RB_RAW_STRIDE, wc = tid - rb * RB_RAW_STRIDE;
+                want = (sh->need[rb] >> wc) & 1u;
+            }
+            const unsigned wb = __ballot_sync(0xffffffffu, want);              // one atomic per warp
+            int base = 0;
+            if (lane == 0 && wb) base = atomicAdd(&sh->nblk, __popc(wb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (want) sh->blist[base + __popc(wb & ((1u << lane) - 1u))] = (unsigned short)tid;
         }
         MT_CLK(3)
         __syncthreads();
