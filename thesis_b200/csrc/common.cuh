@@ -107,6 +107,7 @@ struct RbCtx {
     unsigned long long *exists2;
     // scan
     const double *px, *py, *dist;
+    const float4 *beamf;                    // (px, py, 1 if RB_W_MIN_R < dist < RB_W_MAX_R else 0, 0) in float32 (weight stage)
     // matcher
     const double *rot_cs;                   // (2*nk+1) * 2 : cos, sin of k*step
     int nk;

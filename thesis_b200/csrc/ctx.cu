@@ -20,6 +20,7 @@ struct rbpf_ctx {
     std::string err;
     std::vector<void *> allocs;
     double *d_px, *d_py, *d_dist;  // scan
+    float4 *d_beamf;               // the same beams in float32 for the weight stage: (px, py, inside the weight stage's range gate, 0)
     double *d_rot;                 // rotation table
     uint32_t *d_lutx, *d_luty, *d_clut;
     double *d_prev;                // 2 * RB_MAXB: previous scan endpoints (x then y)
@@ -29,7 +30,7 @@ struct rbpf_ctx {
     double *d_tile;                // 800*800 export buffer
     int *d_slice;                  // 29*29 debug slice
     unsigned long long *d_refstats;
-    double *h_scan;                // pinned staging: 2 slots x (px, py, dist | prev x, prev y), used alternately
+    double *h_scan;                // pinned staging: 2 slots x (px, py, dist | prev x, prev y | float4 beams), used alternately
     cudaEvent_t stage_ev[2];       // "the copies out of slot i have completed"
     int stage_slot;
     int have_scan;
@@ -60,6 +61,7 @@ struct rbpf_ctx {
     unsigned long long snap_step_no = 0;
 };
 
+#define RB_STAGE_DOUBLES (7 * RB_MAXB)   // px, py, dist, prev x, prev y, RB_MAXB float4 (= 2 RB_MAXB doubles)
 #define RB_NSTAGES 8               // set_scan, match, weight, raycast_prepare, raycast_cast, weight_fallback, resample_plan, resample_apply
 
 #define CK(call)                                                                             \
@@ -209,7 +211,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(d.weight, N);
     A(d.pt, N * d.nsub); A(d.pt2, N * d.nsub);
     A(d.exists, N); A(d.exists2, N);
-    A(h->d_px, RB_MAXB); A(h->d_py, RB_MAXB); A(h->d_dist, RB_MAXB);
+    A(h->d_px, RB_MAXB); A(h->d_py, RB_MAXB); A(h->d_dist, RB_MAXB); A(h->d_beamf, RB_MAXB);
     A(h->d_rot, 2 * (2 * d.nk + 1));
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
@@ -235,7 +237,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         memcpy(h->phys, phys, sizeof(phys));
         h->parity = 0;
     }
-    if (cudaMallocHost((void **)&h->h_scan, 2 * 5 * RB_MAXB * sizeof(double)) != cudaSuccess)
+    if (cudaMallocHost((void **)&h->h_scan, 2 * RB_STAGE_DOUBLES * sizeof(double)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
     if (cudaMallocHost((void **)&h->h_flags, 2 * sizeof(RbFlags)) != cudaSuccess)
         return fail(RBPF_ERR_CUDA, "cudaMallocHost failed");
@@ -249,7 +251,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
         if (cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming) != cudaSuccess)
             return fail(RBPF_ERR_CUDA, "cudaEventCreate failed");
     d.prev_x = h->d_prev; d.prev_y = h->d_prev + RB_MAXB; d.n_prev = 0;
-    d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist;
+    d.px = h->d_px; d.py = h->d_py; d.dist = h->d_dist; d.beamf = h->d_beamf;
     d.rot_cs = h->d_rot;
     d.lutx = h->d_lutx;
     d.luty = h->d_luty;
@@ -337,7 +339,7 @@ extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *
     // two pinned slots used alternately: only wait for the copies issued two calls ago
     h->stage_slot ^= 1;
     CK(cudaEventSynchronize(h->stage_ev[h->stage_slot]));
-    double *px = h->h_scan + (size_t)h->stage_slot * 5 * RB_MAXB, *py = px + RB_MAXB, *dist = py + RB_MAXB;
+    double *px = h->h_scan + (size_t)h->stage_slot * RB_STAGE_DOUBLES, *py = px + RB_MAXB, *dist = py + RB_MAXB;
     for (int j = 0; j < n_beams; j++) {                          // Scan.__init__ lidar.py:76-80 (host libm, like the reference)
         px[j] = ranges[j] * cos(angles[j]);
         py[j] = ranges[j] * sin(angles[j]);
@@ -346,6 +348,10 @@ extern "C" int rbpf_set_scan(rbpf_handle h, const double *ranges, const double *
     CK(cudaMemcpyAsync(h->d_px, px, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_py, py, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_dist, dist, n_beams * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    float4 *bf = reinterpret_cast<float4 *>(px + 5 * RB_MAXB);   // weight stage: float32 beams + the range gate of robot.py:130
+    for (int j = 0; j < n_beams; j++)
+        bf[j] = make_float4((float)px[j], (float)py[j], (dist[j] < RB_W_MAX_R && dist[j] > RB_W_MIN_R) ? 1.0f : 0.0f, 0.0f);
+    CK(cudaMemcpyAsync(h->d_beamf, bf, n_beams * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->stage_ev[h->stage_slot], h->stream));
     h->have_scan = 1;
     return RBPF_OK;
@@ -379,7 +385,7 @@ extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, in
     CK(cudaSetDevice(h->cfg.device));
     // shares the slot of the preceding rbpf_set_scan (its event is re-recorded after this copy)
     CK(cudaEventSynchronize(h->stage_ev[h->stage_slot]));
-    double *hp = h->h_scan + (size_t)h->stage_slot * 5 * RB_MAXB + 3 * RB_MAXB;
+    double *hp = h->h_scan + (size_t)h->stage_slot * RB_STAGE_DOUBLES + 3 * RB_MAXB;
     for (int q = 0; q < n_points; q++) { hp[q] = last_scan_xy[2 * q]; hp[RB_MAXB + q] = last_scan_xy[2 * q + 1]; }
     CK(cudaMemcpyAsync(h->d_prev, hp, 2 * RB_MAXB * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->stage_ev[h->stage_slot], h->stream));

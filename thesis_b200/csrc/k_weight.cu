@@ -23,6 +23,35 @@
 #ifndef WT_INFLIGHT
 #define WT_INFLIGHT 4                   // beam lookups in flight per lane
 #endif
+#ifndef WT_F32_EPS
+#define WT_F32_EPS 5e-4f                // float32 cell lookups: distance from a lattice boundary below which float64 decides
+#endif
+
+// The float64 cell lookup for the lanes the float32 evaluation cannot decide (out of line: rare, and its
+// registers stay out of the beam loop): floor(20 g) from two fused multiply-adds, and the reference's own
+// expressions (rb_xform + rb_read_axis) within 1e-6 of a lattice boundary.  Returns (page-table slot or -1, offset).
+__device__ __noinline__ int2 wt_locate_f64(double bpx, double bpy, double cs_, double sn_, double g0, double g1, int txh, int tyh,
+                                           int subs_x, int ux_max, int uy_max)
+{
+    const double c20 = cs_ * 20.0, s20 = sn_ * 20.0, x20 = g0 * 20.0, y20 = g1 * 20.0;
+    const double vx = fma(c20, bpx, fma(-s20, bpy, x20)), vy = fma(s20, bpx, fma(c20, bpy, y20));
+    const int kx = __double2int_rd(vx), ky = __double2int_rd(vy);
+    const double dx = vx - (double)kx, dy = vy - (double)ky;
+    int ux, uy;
+    if (dx > 1e-6 && dx < 1.0 - 1e-6 && dy > 1e-6 && dy < 1.0 - 1e-6 && fabs(vx) < 1e6 && fabs(vy) < 1e6) {
+        ux = kx + 400 + 800 * txh; uy = ky + 400 + 800 * tyh;
+    } else {
+        double gx, gy;
+        rb_xform(cs_, sn_, g0, g1, bpx, bpy, gx, gy);
+        int tx, ty, ix, iy;
+        rb_read_axis(gx, tx, ix);
+        rb_read_axis(gy, ty, iy);
+        if (tx < -txh || tx > txh || ty < -tyh || ty > tyh) return make_int2(-1, 0);
+        ux = 800 * (tx + txh) + ix; uy = 800 * (ty + tyh) + iy;
+    }
+    if ((unsigned)ux >= (unsigned)ux_max || (unsigned)uy >= (unsigned)uy_max) return make_int2(-1, 0);
+    return make_int2((uy / RB_SUB) * subs_x + ux / RB_SUB, RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB));
+}
 
 // fallback_phase == 0: particles with a valid match (robot.py:80-114)
 // fallback_phase == 1: particles whose match failed, after the map update
@@ -116,12 +145,19 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
         int S = 0;
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
         // WT_INFLIGHT beams in flight: locate (ALU) -> page-table entries -> cells.
-        // The cell of a beam end is floor(20 g) per axis (rb_locate_fast); here 20 g comes from two fused
-        // multiply-adds on the pre-scaled frame -- within 1e-11 of 20 x the reference's own float64 chain,
-        // so the floor is the same unless 20 g lies within 1e-6 of an integer, and then the reference's
-        // expressions are replayed (rb_xform + rb_locate).
-        const double c20 = cs_ * 20.0, s20 = sn_ * 20.0, x20 = g0 * 20.0, y20 = g1 * 20.0;
+        // The cell of a beam end is floor(V) per axis with V = 20 g = x20 + c20 px - s20 py (rb_locate_fast: within 1e-11
+        // of 20 x the reference's own float64 chain, same floor unless V lies within 1e-6 of an integer).  V is
+        // evaluated in float32 RELATIVE to floor(x20): |c20 px| <= 500 cells (ranges below 25 m), so the float32 value
+        // is within 1.7e-4 of V - floor(x20) (conversions of c20, s20, px, py: 3e-5 each; the two fused roundings 1.5e-5
+        // and 3e-5) and its floor is right unless it lies within WT_F32_EPS of an integer; those lanes (0.2 %) take the
+        // float64 expression, and there the reference's own expressions within 1e-6 of a lattice boundary
+        // (rb_xform + rb_locate).  (Absolute float32 coordinates need 4e-3 and diverge in 38 % of the iterations.)
+        const double x20 = g0 * 20.0, y20 = g1 * 20.0;
         const int offx = 400 + 800 * c.txh, offy = 400 + 800 * c.tyh;
+        const double X0d = floor(x20), Y0d = floor(y20);
+        const bool f32_ok = fabs(x20) < 1e6 && fabs(y20) < 1e6;
+        const int X0 = f32_ok ? (int)X0d + offx : 0, Y0 = f32_ok ? (int)Y0d + offy : 0;
+        const float xr = (float)(x20 - X0d), yr = (float)(y20 - Y0d), cf = (float)(cs_ * 20.0), sf = (float)(sn_ * 20.0);
         for (int j = 0; j < c.B; j += WT_INFLIGHT) {
             int sub[WT_INFLIGHT], off[WT_INFLIGHT];
 #pragma unroll
@@ -129,22 +165,20 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
                 const int jj = j + u;
                 sub[u] = -1; off[u] = 0;
                 if (jj < c.B) {
-                    const double d = c.dist[jj];
-                    if (d < RB_W_MAX_R && d > RB_W_MIN_R) {
-                        const double bpx = c.px[jj], bpy = c.py[jj];
-                        const double vx = fma(c20, bpx, fma(-s20, bpy, x20)), vy = fma(s20, bpx, fma(c20, bpy, y20));
-                        const int kx = __double2int_rd(vx), ky = __double2int_rd(vy);
-                        const double dx = vx - (double)kx, dy = vy - (double)ky;
-                        if (dx > 1e-6 && dx < 1.0 - 1e-6 && dy > 1e-6 && dy < 1.0 - 1e-6 && fabs(vx) < 1e6 && fabs(vy) < 1e6) {
-                            const int ux = kx + offx, uy = ky + offy;
+                    const float4 bf = __ldg(&c.beamf[jj]);
+                    if (bf.z != 0.0f) {                                             // robot.py:130 range gate
+                        const float vxf = fmaf(cf, bf.x, fmaf(-sf, bf.y, xr)), vyf = fmaf(sf, bf.x, fmaf(cf, bf.y, yr));
+                        const float flx = floorf(vxf), fly = floorf(vyf);
+                        const float dxf = vxf - flx, dyf = vyf - fly;
+                        if (f32_ok && dxf > WT_F32_EPS && dxf < 1.0f - WT_F32_EPS && dyf > WT_F32_EPS && dyf < 1.0f - WT_F32_EPS) {
+                            const int ux = (int)flx + X0, uy = (int)fly + Y0;
                             if ((unsigned)ux < (unsigned)c.ux_max && (unsigned)uy < (unsigned)c.uy_max) {
                                 sub[u] = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
                                 off[u] = RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB);
                             }
                         } else {
-                            double gx, gy;
-                            rb_xform(cs_, sn_, g0, g1, bpx, bpy, gx, gy);
-                            rb_locate(c, gx, gy, sub[u], off[u]);
+                            const int2 so = wt_locate_f64(c.px[jj], c.py[jj], cs_, sn_, g0, g1, c.txh, c.tyh, c.subs_x, c.ux_max, c.uy_max);
+                            sub[u] = so.x; off[u] = so.y;
                         }
                     }
                 }
