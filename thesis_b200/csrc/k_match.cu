@@ -908,22 +908,27 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             __syncthreads();
             // rows of this tile row: window [r - 35, r + 36] of centre rows, clipped to 11.5 m; into raw (+ block list)
             const int rlo = max(800 * TY - y0, 0), rhi = min(800 * TY + 800 - y0, RB_BM_ROWS);
-            for (int idx = tid; idx < (rhi - rlo) * 16; idx += MT_THREADS) {
-                const int r = rlo + (idx >> 4), wq = idx & 15;
+            // one thread per half row (8 words): the row's clip interval and window rows are set up once, one shared-memory
+            // atomic per half row says which 32-cell words of the band hold anything
+            for (int it = tid; it < (rhi - rlo) * 2; it += MT_THREADS) {
+                const int r = rlo + (it >> 1), w0 = (it & 1) * 8;
                 const int a_ = r - 35, b_ = min(r + 36, RB_BM_ROWS - 1);
-                uint32_t v;
-                if (a_ <= 0) v = Gp[b_ * RB_BM_STRIDE + wq];
-                else if (a_ / 72 == b_ / 72) v = H[a_ * RB_BM_STRIDE + wq];
-                else v = H[a_ * RB_BM_STRIDE + wq] | Gp[b_ * RB_BM_STRIDE + wq];
-                const int lo = (int)sh->row_lo[r] - 32 * wq, hi = (int)sh->row_hi[r] - 32 * wq;
-                uint32_t keep = 0u;
-                if (hi > 0 && lo < 32) keep = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << max(lo, 0)) - 1u);
-                v &= keep;
-                if (v) {
-                    const int rho = r + dy0 + 1;
-                    raw[rho * RB_RAW_STRIDE + wq + 1] = v;
-                    atomicOr(&sh->need[rho >> 5], 1u << (wq + 1));
+                const bool use_h = a_ > 0, use_g = a_ <= 0 || a_ / 72 != b_ / 72;
+                const uint32_t *ha = H + max(a_, 0) * RB_BM_STRIDE + w0, *gb = Gp + b_ * RB_BM_STRIDE + w0;
+                const int lo = (int)sh->row_lo[r] - 32 * w0, hi = (int)sh->row_hi[r] - 32 * w0;
+                const int rho = r + dy0 + 1;
+                uint32_t *out = raw + rho * RB_RAW_STRIDE + w0 + 1;
+                uint32_t nb = 0u;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    uint32_t v = (use_h ? ha[e] : 0u) | (use_g ? gb[e] : 0u);
+                    const int l = lo - 32 * e, h_ = hi - 32 * e;
+                    uint32_t keep = 0u;
+                    if (h_ > 0 && l < 32) keep = (h_ >= 32 ? 0xffffffffu : ((1u << h_) - 1u)) & ~((1u << max(l, 0)) - 1u);
+                    v &= keep;
+                    if (v) { out[e] = v; nb |= 1u << (w0 + e + 1); }
                 }
+                if (nb) atomicOr(&sh->need[rho >> 5], nb);
             }
             __syncthreads();
         }
