@@ -31,7 +31,8 @@
 // consecutive lattice steps.  A point at range <= 11 m moves at most one cell per
 // rotation step, so scoring the group's middle rotation against the bitmap
 // dilated by MT_GRAD cells bounds the score of every rotation of the group at
-// every translation from above.  The rotations around the guess are scored first
+// every translation from above (mt_bound_pass: four row shifts per lane, four points
+// per instruction).  The rotations around the guess are scored first
 // (seeds), phase A then scores every group once (231/8 = 29 passes instead of
 // 231), phase B visits groups in decreasing bound and scores a member rotation
 // only while its bound can still beat the best key so far.  Every pass gives up
@@ -368,6 +369,135 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
     return true;
 }
 
+// Group-bound pass (phase A).  A bound only has to be admissible, so a lane need not own ONE row shift: bmg row r is the OR of
+// the dilated rows r .. r + MT_BSUB - 1 (built by the dilation walker), and a lookup at row y + MT_BSUB * b bounds the hits of the
+// MT_BSUB row shifts MT_BSUB * b .. MT_BSUB * b + MT_BSUB - 1 at once.  With MT_BSUB = 4 eight lanes cover the 29 row shifts and the
+// four quarters of the warp score four different points per instruction: a quarter of the instructions of mt_pass per point.  The
+// quarters' bit-sliced counters are added (two shuffle rounds of nine full adders) for every abort check and at the end.
+#define MT_BSUB 4
+#ifndef MT_BCHUNK
+#define MT_BCHUNK 64                    // points between two abort checks of a bound pass (multiple of 32)
+#endif
+#define MT_BQ (MT_BCHUNK / 4)           // points per quarter and chunk
+#define MT_NULLPT ((uint32_t)(RB_BM_STRIDE - 1) << MT_PT_WORD_SHIFT)   // the zeroed pad word of a row, shift 0: never a hit
+
+__device__ __forceinline__ void mt_quarter_sum(uint32_t T[MT_PLANES])
+{
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        uint32_t carry = 0u;
+#pragma unroll
+        for (int p = 0; p < MT_PLANES; p++) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, T[p], o);
+            const uint32_t s = T[p] ^ other ^ carry;
+            carry = (T[p] & other) | ((T[p] ^ other) & carry);
+            T[p] = s;
+        }
+    }
+}
+
+// Returns false when the pass was given up (no translation of the group can reach the best complete score); else ub = the
+// largest bound over the translation window.
+__device__ __forceinline__ bool mt_bound_pass(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
+                                              const float2 *__restrict__ ccf, int k, int nx, int ny, uint32_t bmg_addr, uint32_t *pts,
+                                              int M, int lane, uint32_t colmask, const volatile unsigned long long *best_key,
+                                              int *visited, int &ub)
+{
+    const MtRot r = mt_rot(c, sh, k, -nx, -ny);
+    const int qd = lane >> 3, b = lane & 7;
+    const bool rows_ok = MT_BSUB * b <= 2 * ny;
+    const uint32_t bm_lane = bmg_addr + (uint32_t)((rows_ok ? MT_BSUB * b : 0) * RB_BM_STRIDE * 4);
+    const uint32_t rowmask = rows_ok ? colmask : 0u;
+    const uint32_t *ptq = pts + MT_BQ * qd;
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, pl[MT_PLANES];
+#pragma unroll
+    for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
+#define MT_LOAD8(Q)                                                                     \
+    uint32_t h[8];                                                                      \
+    {                                                                                   \
+        const uint4 pa = *reinterpret_cast<const uint4 *>(ptq + (Q));                   \
+        const uint4 pb = *reinterpret_cast<const uint4 *>(ptq + (Q) + 4);               \
+        const uint32_t pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};        \
+        _Pragma("unroll") for (int e = 0; e < 8; e++) {                                 \
+            const uint32_t a = mt_pt_addr(pk[e], bm_lane);                              \
+            h[e] = __funnelshift_r(mt_lds(a), mt_lds4(a), pk[e]);                       \
+        }                                                                               \
+    }
+#define MT_TREE8(E8)                                                                    \
+    {                                                                                   \
+        uint32_t t0, t1, f0, f1;                                                        \
+        CSA(t0, ones, ones, h[0], h[1]);                                                \
+        CSA(t1, ones, ones, h[2], h[3]);                                                \
+        CSA(f0, twos, twos, t0, t1);                                                    \
+        CSA(t0, ones, ones, h[4], h[5]);                                                \
+        CSA(t1, ones, ones, h[6], h[7]);                                                \
+        CSA(f1, twos, twos, t0, t1);                                                    \
+        CSA(E8, fours, fours, f0, f1);                                                  \
+    }
+    for (int q0 = 0; q0 < M; q0 += MT_BCHUNK) {
+        if (q0) {
+            const int need = (int)(*best_key >> 32) - (M - q0);
+            if (need > 0) {
+                uint32_t T[MT_PLANES] = {ones, twos, fours, eights, pl[4], pl[5], pl[6], pl[7], pl[8]};
+                mt_quarter_sum(T);
+                uint32_t gt = 0u, eq = rowmask;
+#pragma unroll
+                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+                    const uint32_t tb = (need >> pbit) & 1 ? 0xffffffffu : 0u;
+                    gt |= eq & T[pbit] & ~tb;
+                    eq &= ~(T[pbit] ^ tb);
+                }
+                if (!__any_sync(0xffffffffu, (gt | eq) != 0u)) {
+                    *visited += q0;
+                    return false;
+                }
+            }
+        }
+        const int n = min(MT_BCHUNK, M - q0), npad = (n + 31) & ~31;
+        __syncwarp();                                                       // the previous chunk has been read
+#pragma unroll
+        for (int e = 0; e < MT_BCHUNK; e += 32) {
+            const int idx = e + lane;                                       // point idx of the chunk goes to quarter idx & 3
+            if (idx < npad)
+                pts[(idx & 3) * MT_BQ + (idx >> 2)] = idx < n ? mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + idx, 2 * nx, 2 * ny) : MT_NULLPT;
+        }
+        __syncwarp();
+        const int nq = npad >> 2;                                           // multiple of 8
+        int q = 0;
+        for (; q + 16 <= nq; q += 16) {
+            uint32_t ea, eb, s16;
+            { MT_LOAD8(q) MT_TREE8(ea) }
+            { MT_LOAD8(q + 8) MT_TREE8(eb) }
+            CSA(s16, eights, eights, ea, eb);
+#pragma unroll
+            for (int p = 4; p < MT_PLANES; p++) { uint32_t t = pl[p] & s16; pl[p] ^= s16; s16 = t; }
+        }
+        if (q < nq) {
+            uint32_t e8;
+            { MT_LOAD8(q) MT_TREE8(e8) }
+            uint32_t t = eights & e8; eights ^= e8; e8 = t;
+#pragma unroll
+            for (int p = 4; p < MT_PLANES; p++) { uint32_t t2 = pl[p] & e8; pl[p] ^= e8; e8 = t2; }
+        }
+    }
+#undef MT_LOAD8
+#undef MT_TREE8
+    *visited += M;
+    uint32_t T[MT_PLANES] = {ones, twos, fours, eights, pl[4], pl[5], pl[6], pl[7], pl[8]};
+    mt_quarter_sum(T);
+    uint32_t cand = rowmask;
+    int sc = 0;
+#pragma unroll
+    for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
+        const uint32_t t = cand & T[pbit];
+        if (t) { cand = t; sc |= 1 << pbit; }
+    }
+    if (!rowmask) sc = 0;
+    for (int o = 4; o > 0; o >>= 1) sc = max(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+    ub = sc;
+    return true;
+}
+
 // curr point of beam j relative to the guess position (hybridmap.py:216-228,236,240; adj: :165-172)
 // Returns bit 1 when the beam is a curr point of the matcher (|c| < 11 m, :240) and bit 0 when it is a
 // curr point of hybridmap.py:216-228 at all -- those span the 72 x 72-cell windows of the reference set
@@ -666,7 +796,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm = smem;
-    uint32_t *bmg = bm + mt_bm_words();                                     // bm dilated by MT_GRAD (group bounds)
+    uint32_t *bmg = bm + mt_bm_words();                                     // bm dilated by MT_GRAD, rows r .. r + MT_BSUB - 1 ORed (group bounds)
     uint32_t *raw = bmg + mt_bm_words();                                    // staging, then per-warp point lists
     size_t w_end = (2 * mt_bm_words() + mt_raw_words() + 1) & ~(size_t)1;
     double *ccx = reinterpret_cast<double *>(smem + w_end);
@@ -996,29 +1126,30 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     // ---- 2b. both dilations in one pass down the rows --------------------------------
     //   bm  = raw dilated by 1 (a lookup counts when the cell or one of its 8 neighbours is
     //         occupied: the proximity kernel of our matcher)
-    //   bmg = raw dilated by 1 + MT_GRAD (upper bound for every rotation of a group)
+    //   bmg = raw dilated by 1 + MT_GRAD (upper bound for every rotation of a group), rows r .. r + MT_BSUB - 1
+    //         ORed into row r (a bound lookup covers MT_BSUB row shifts, mt_bound_pass)
     // A thread owns one 32-cell word column over MT_SEG_ROWS rows and walks down the staged
     // rows once: three loads per row, the vertical windows are running ORs in registers
-    // (13 rows = doubling 2, 4, 8 and two of those 5 apart).  Rows of raw beyond the buffer
+    // (13 + 3 = 16 rows: doubling 2, 4, 8, 16).  Rows of raw beyond the buffer
     // count as empty, like rows of bm beyond the window.
     {
-        static_assert(MT_GRAD == 5, "the running OR below is a 13-row window");
+        static_assert(MT_GRAD == 5 && MT_BSUB == 4, "the running OR below is a 16-row window: 13 rows of dilation + MT_BSUB - 1");
         static_assert((MT_THREADS / 16) * MT_SEG_ROWS >= RB_BM_ROWS, "segments must cover the window");
         const int w = tid & 15, r0 = (tid >> 4) * MT_SEG_ROWS, r1 = min(r0 + MT_SEG_ROWS, RB_BM_ROWS);
         bool live = false;
         if (r0 < RB_BM_ROWS) {
-            const int rb0 = max(r0 + dy0 + 1 - 6, 0) >> 5, rb1 = min(r1 + dy0 + 6, MT_RAW_ROWS - 1) >> 5;
+            const int rb0 = max(r0 + dy0 + 1 - 6, 0) >> 5, rb1 = min(r1 + dy0 + 6 + MT_BSUB - 1, MT_RAW_ROWS - 1) >> 5;
             for (int rb = rb0; rb <= rb1; rb++) live |= (sh->need[rb] >> (w + 1)) & 1u;
         }
         if (r0 < RB_BM_ROWS && !live) {
             for (int r = r0; r < r1; r++) { bm[r * RB_BM_STRIDE + w] = 0u; bmg[r * RB_BM_STRIDE + w] = 0u; }
         } else if (r0 < RB_BM_ROWS) {
-            // step s reads raw row rho = rs + s; bm row rho - dy0 - 2 and bmg row rho - dy0 - 7 complete there
+            // step s reads raw row rho = rs + s; bm row rho - dy0 - 2 and bmg row rho - dy0 - 10 complete there
             const int rs = r0 + dy0 - 5;
             uint32_t h1p = 0, h1pp = 0;                                     // 3-wide rows rho-1, rho-2
-            uint32_t h6p = 0, A[2] = {0, 0}, Bq[4] = {0, 0, 0, 0}, Cq[5] = {0, 0, 0, 0, 0};
+            uint32_t h6p = 0, A[2] = {0, 0}, Bq[4] = {0, 0, 0, 0}, Cq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int s_ = 0; s_ < MT_SEG_ROWS + 12; s_++) {
+            for (int s_ = 0; s_ < MT_SEG_ROWS + 15; s_++) {
                 const int rho = rs + s_;
                 uint32_t l = 0, cw = 0, rw = 0;
                 if (rho >= 0 && rho < MT_RAW_ROWS) {
@@ -1035,9 +1166,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                 const uint32_t a_ = h6 | h6p;                               // rows rho-1 .. rho
                 const uint32_t b_ = a_ | A[s_ & 1];                         // | a(rho-2): rows rho-3 .. rho
                 const uint32_t c_ = b_ | Bq[s_ & 3];                        // | b(rho-4): rows rho-7 .. rho
-                const uint32_t o_ = c_ | Cq[s_ % 5];                        // | c(rho-5): rows rho-12 .. rho
-                h6p = h6; A[s_ & 1] = a_; Bq[s_ & 3] = b_; Cq[s_ % 5] = c_;
-                const int rg = rho - dy0 - 7;
+                const uint32_t o_ = c_ | Cq[s_ & 7];                        // | c(rho-8): rows rho-15 .. rho
+                h6p = h6; A[s_ & 1] = a_; Bq[s_ & 3] = b_; Cq[s_ & 7] = c_;
+                const int rg = rho - dy0 - 10;                              // dilated rows rg .. rg + 3 = raw rows rg - 6 .. rg + 9
                 if (rg >= r0 && rg < r1) bmg[rg * RB_BM_STRIDE + w] = o_;
             }
         }
@@ -1053,7 +1184,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     uint32_t *pts = raw + warp * RB_MAXB;                                   // raw is dead now: per-warp point lists
     const uint32_t lane_off = (uint32_t)((lane < nrows ? lane : 0) * RB_BM_STRIDE * 4);
     const uint32_t bm_lane = (uint32_t)__cvta_generic_to_shared(bm) + lane_off;
-    const uint32_t bmg_lane = (uint32_t)__cvta_generic_to_shared(bmg) + lane_off;
+    const uint32_t bmg_addr = (uint32_t)__cvta_generic_to_shared(bmg);
     const int nrot = 2 * c.nk + 1, ngroups = (nrot + MT_GROUP - 1) / MT_GROUP;
 
     // ---- 3a0. seed the best key with MT_SEEDS rotations around the guess ---------
@@ -1106,23 +1237,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                 if (lane == 0) { sh->group_ub[g] = -1; atomicAdd(&sh->evals, -1); }   // every member is a seed: nothing to bound
                 continue;
             }
-            uint32_t pl[MT_PLANES];
-            const bool done = mt_pass<true>(c, sh, ccx, ccy, ccf, kmid, nx, ny, bmg_lane, pts, M, lane, pl, lane < nrows ? colmask : 0u,
-                                            &sh->best_key, &visited);
+            int sc = 0;
+            const bool done = mt_bound_pass(c, sh, ccx, ccy, ccf, kmid, nx, ny, bmg_addr, pts, M, lane, colmask, &sh->best_key, &visited, sc);
             if (!done) {                                                    // even the bound cannot reach the seeded best
                 if (lane == 0) sh->group_ub[g] = -1;
                 continue;
             }
-            int sc = 0;
-            if (lane < nrows) {
-                uint32_t cand = colmask;
-#pragma unroll
-                for (int pbit = MT_PLANES - 1; pbit >= 0; pbit--) {
-                    uint32_t t = cand & pl[pbit];
-                    if (t) { cand = t; sc |= 1 << pbit; }
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) sc = max(sc, __shfl_xor_sync(0xffffffffu, sc, o));
             if (lane == 0) sh->group_ub[g] = sc;
         }
     }
