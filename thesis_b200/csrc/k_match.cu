@@ -97,6 +97,7 @@ struct MatchShared {
     int sxb0, syb0;                     // sub-tile coordinates of ptw[0] (may be negative at the world border)
     unsigned long long best_key;
     long long mom[9];                   // W0 Wx Wy Wxx Wyy Wxy T0 T1 T2
+    long long mom_part[MT_WARPS][9];    // per-warp partial moments (64-bit shared-memory atomics are CAS loops)
     int group_ub[MT_MAXGROUPS];         // phase A: upper bound of every rotation group
     int group_order[MT_MAXGROUPS];      // groups by decreasing bound
     int next_group;                     // phase A work queue
@@ -251,15 +252,6 @@ __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared 
         bx = 0; by = 0;
     }
     return ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << MT_PT_WORD_SHIFT) | (uint32_t)(bx & 31);
-}
-
-__device__ __forceinline__ void mt_rasterise(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
-                                             const float2 *__restrict__ ccf, int k, uint32_t *pts, int lane, int shift_i,
-                                             int shift_j, int span_i, int span_j)
-{
-    const MtRot r = mt_rot(c, sh, k, shift_i, shift_j);
-    const int M = sh->M;
-    for (int q = lane; q < M; q += 32) pts[q] = mt_raster_point(c, sh, ccx, ccy, ccf, r, q, span_i, span_j);
 }
 
 // One scoring pass: the points of rotation k are rasterised MT_CHUNK at a time, just before
@@ -907,9 +899,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             if (lane == 0) sh->ord_cnt[b * MT_WARPS + warp] = __popc(mb);
         }
         __syncthreads();
-        if (tid == 0) {                                                         // exclusive prefix, class-major then warp
-            int run = 0;
-            for (int e = 0; e < 4 * MT_WARPS; e++) { const int n = sh->ord_cnt[e]; sh->ord_cnt[e] = run; run += n; }
+        if (warp == 0) {                                                        // exclusive prefix, class-major then warp
+            static_assert(4 * MT_WARPS <= 64, "two entries per lane");
+            const int e0 = 2 * lane, e1 = 2 * lane + 1;
+            const int n0 = e0 < 4 * MT_WARPS ? sh->ord_cnt[e0] : 0, n1 = e1 < 4 * MT_WARPS ? sh->ord_cnt[e1] : 0;
+            int inc = n0 + n1;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int ex = inc - n0 - n1;
+            if (e0 < 4 * MT_WARPS) sh->ord_cnt[e0] = ex;
+            if (e1 < 4 * MT_WARPS) sh->ord_cnt[e1] = ex + n0;
         }
         __syncthreads();
         if (key >= 0) {
@@ -1322,27 +1320,33 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
         if (sh->ok) {                                                       // rotation line at the best translation (all warps)
             long long T0 = 0, T1 = 0, T2 = 0;
             const int klo = max(bk - MT_ROT_LINE_HALF, -c.nk), khi = min(bk + MT_ROT_LINE_HALF, c.nk);
+            // A rotation whose score ends more than 40 below the best has weight zero: with misses counted as the points go by
+            // (far points first, they miss first) such a rotation is given up as soon as bs - (M - misses) > 40 is certain.
+            const int miss_max = 40 - (bs - M);                             // misses a rotation can afford
             for (int k = klo + warp; k <= khi; k += MT_WARPS) {
-                __syncwarp();
-                mt_rasterise(c, sh, ccx, ccy, ccf, k, pts, lane, bi, bj, 0, 0);
-                __syncwarp();
-                int s = 0;
-                for (int q = lane; q < M; q += 32) {
-                    const uint32_t pk = pts[q];
-                    s += (int)((bm[pk >> MT_PT_WORD_SHIFT] >> (pk & 31)) & 1u);
+                const MtRot r = mt_rot(c, sh, k, bi, bj);
+                int s = 0, seen = 0;
+                for (int q0 = 0; q0 < M; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool hit = false;
+                    if (q < M) {
+                        const uint32_t pk = mt_raster_point(c, sh, ccx, ccy, ccf, r, q, 0, 0);
+                        hit = (bm[pk >> MT_PT_WORD_SHIFT] >> (pk & 31)) & 1u;
+                    }
+                    s += __popc(__ballot_sync(0xffffffffu, hit));
+                    seen = min(q0 + 32, M);
+                    if (seen - s > miss_max) break;
                 }
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (seen < M) continue;
                 const int d = bs - s;
                 if (d <= 40) {
                     const long long w = 1ll << (40 - d);
                     T0 += w; T1 += w * k; T2 += w * k * k;
                 }
             }
-            if (lane == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[6]), (unsigned long long)T0);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[7]), (unsigned long long)T1);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[8]), (unsigned long long)T2);
-            }
+            if (lane == 0) { sh->mom_part[warp][6] = T0; sh->mom_part[warp][7] = T1; sh->mom_part[warp][8] = T2; }
+        } else if (lane == 0) {
+            sh->mom_part[warp][6] = sh->mom_part[warp][7] = sh->mom_part[warp][8] = 0;
         }
         __syncthreads();
         if (sh->ok && sh->slot_warp >= 0) {                                 // translation slice at the best rotation: every thread decodes a few cells
@@ -1362,8 +1366,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
 #pragma unroll
             for (int e = 0; e < 6; e++) {
                 for (int o = 16; o > 0; o >>= 1) mo[e] += __shfl_xor_sync(0xffffffffu, mo[e], o);
-                if (lane == 0 && mo[e]) atomicAdd(reinterpret_cast<unsigned long long *>(&sh->mom[e]), (unsigned long long)mo[e]);
+                if (lane == 0) sh->mom_part[warp][e] = mo[e];
             }
+        } else if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 6; e++) sh->mom_part[warp][e] = 0;
+        }
+        __syncthreads();
+        if (tid < 9) {
+            long long t = 0;
+#pragma unroll
+            for (int wq = 0; wq < MT_WARPS; wq++) t += sh->mom_part[wq][tid];
+            sh->mom[tid] = t;
         }
     }
     __syncthreads();
