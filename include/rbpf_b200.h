@@ -249,6 +249,15 @@ int64_t rbpf_migrate_bytes(rbpf_handle h, int32_t n_particles, int32_t n_subtile
  * (replaces Robot.copy robot.py:141-149 by page-table sharing).  Call after the
  * packs and before the unpacks. */
 int rbpf_resample_apply_local(rbpf_handle h);
+/* The same with the reference-count pass deferred: the gather of the local ancestors
+ * (main.py:69-76 by page-table sharing) runs now; the reference counts -- and with them
+ * every free, and every in-place write into a tile a peer may still be pulling -- are
+ * launched by the next call that needs the pool's bookkeeping (rbpf_integrate, a
+ * resample, statistics, snapshots, rbpf_synchronize ...), behind `gate_event`
+ * (a cudaEvent_t recorded by the caller once every peer has finished pulling: the
+ * job-wide barrier, taken off the critical path; 0 = no gate).  Motion, matching and
+ * weighting of the next scan run in between: they only read tiles. */
+int rbpf_resample_apply_local_deferred(rbpf_handle h, uint64_t gate_event);
 
 /* Pull migration over peer memory (NVLink): instead of pack -> NCCL -> unpack, the
  * receiving rank maps the source rank's particle state with CUDA IPC once and then
@@ -261,7 +270,8 @@ int rbpf_resample_apply_local(rbpf_handle h);
  *                    host synchronisation.  The caller orders the steps of one resample
  *                    as: all ranks pull -> job-wide barrier -> rbpf_resample_apply_local
  *                    -> rbpf_resample_commit, because a source may only free or overwrite
- *                    state after every peer has read it. */
+ *                    state after every peer has read it (or: pull -> barrier on a side
+ *                    stream + event -> rbpf_resample_apply_local_deferred(event) -> commit). */
 typedef struct {
     unsigned char ipc[9][64]; /* cudaIpcMemHandle_t of pool, page tables x2, poses x2, covariances x2, tile masks x2 */
     uint64_t ptr[9];          /* the same allocations as device pointers of the exporting process */

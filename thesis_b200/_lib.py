@@ -94,6 +94,7 @@ SIGNATURES = {
     "rbpf_migrate_pack": (C.c_int, [_H, C.c_uint64]),
     "rbpf_migrate_bytes": (C.c_int64, [_H, C.c_int32, C.c_int32]),
     "rbpf_resample_apply_local": (C.c_int, [_H]),
+    "rbpf_resample_apply_local_deferred": (C.c_int, [_H, C.c_uint64]),
     "rbpf_migrate_unpack": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int32, _ip, _ip, C.c_int32]),
     "rbpf_resample_commit": (C.c_int, [_H]),
     "rbpf_peer_export": (C.c_int, [_H, C.POINTER(RbpfPeerView)]),

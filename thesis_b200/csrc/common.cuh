@@ -280,6 +280,8 @@ void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);
 void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s);
 void rb_launch_resample(const RbCtx &c, const double *weights_all, const double *u01_dev, cudaStream_t s);
 void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s);
+void rb_launch_resample_gather(const RbCtx &c, cudaStream_t s);
+void rb_launch_resample_refs(const RbCtx &c, cudaStream_t s);
 void rb_launch_export_tile(const RbCtx &c, int particle, int tx, int ty, double *out_dev, cudaStream_t s);
 void rb_launch_init(const RbCtx &c, cudaStream_t s);
 void rb_launch_refstats(const RbCtx &c, unsigned long long *out2_dev, cudaStream_t s);

@@ -43,6 +43,9 @@ struct rbpf_ctx {
     unsigned char *d_pull_rank = nullptr;
     void *phys[9];                 // pool, pt x2, pose x2, cov x2, exists x2 as allocated (index 1 + 2*k + parity)
     int parity;                    // which of the double buffers is current (flips with every commit)
+    bool refs_pending = false;     // rbpf_resample_apply_local_deferred: the reference-count pass has not been launched yet
+    cudaEvent_t refs_gate = nullptr; // ... and has to wait for this event (every peer has finished pulling)
+    uint32_t *refs_pt = nullptr;   // ... on the page tables of the particles that were resampled
     struct PeerMap { bool attached = false, ipc = false; void *base[9] = {}; };
     std::vector<PeerMap> peers;    // by rank
     std::vector<cudaEvent_t> tev;  // (RB_NSTAGES + 1) events per recorded step
@@ -308,6 +311,8 @@ static int check_flags(rbpf_ctx *h)
     return flags_status(h, f);
 }
 
+static int flush_refs(rbpf_ctx *h);
+
 extern "C" int rbpf_clear_errors(rbpf_handle h)
 {
     if (!h) return RBPF_ERR_ARG;
@@ -326,6 +331,7 @@ extern "C" int rbpf_synchronize(rbpf_handle h)
 {
     if (!h) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return check_flags(h);
@@ -422,11 +428,28 @@ extern "C" int rbpf_weight_guesses(rbpf_handle h, const double *guesses)
     return RBPF_OK;
 }
 
+// The reference-count pass of a sharded resample may be deferred (rbpf_resample_apply_local_deferred): it is launched
+// here, behind its gate, by the first call that needs the pool's bookkeeping -- reference counts, free list, `mult`,
+// or the old page tables as the target of the next gather.  Motion, matching and weighting only read tiles.
+static int flush_refs(rbpf_ctx *h)
+{
+    if (!h->refs_pending) return RBPF_OK;
+    h->refs_pending = false;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->refs_gate) CK(cudaStreamWaitEvent(h->stream, h->refs_gate, 0));
+    RbCtx d = h->d;
+    d.pt = h->refs_pt;
+    rb_launch_resample_refs(d, h->stream);
+    CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
 extern "C" int rbpf_integrate(rbpf_handle h, int32_t fallback_weights)
 {
     if (h) h->d.use_dup = 0;
     if (!h || !h->have_scan) { if (h) h->err = "integrate: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     rb_launch_raycast_prepare(h->d, h->stream);
     rb_launch_raycast_cast(h->d, h->stream);
     if (fallback_weights) rb_launch_weight(h->d, nullptr, nullptr, 1, h->stream);
@@ -476,6 +499,7 @@ extern "C" int rbpf_resample(rbpf_handle h, const double *u01, int32_t *ancestor
     if (!h) return RBPF_ERR_ARG;
     if (h->d.world != 1) { h->err = "resample: sharded handle, use rbpf_resample_global"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     int rc = resample_common(h, h->d.weight, u01, ancestors_out, did_resample);
     rb_launch_resample_apply(h->d, h->stream);                  // identity gather when nothing triggered / on error
     CK(cudaGetLastError());
@@ -489,6 +513,7 @@ extern "C" int rbpf_step(rbpf_handle h, const double *ranges, const double *angl
     if (!h) return RBPF_ERR_ARG;
     if (h->d.world != 1) { h->err = "step: sharded handle, drive the stages from thesis_b200.dist"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     // errors of the step before the previous one (pool exhausted, world overflow, resample assertion):
     // their flags were copied to pinned memory behind that step; waiting for them keeps the host at
     // most two steps ahead of the device
@@ -678,6 +703,7 @@ extern "C" int rbpf_stats(rbpf_handle h, rbpf_stats_t *out)
 {
     if (!h || !out) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     RbStats s;
     int fc = 0;
     unsigned long long rs[3];
@@ -746,6 +772,7 @@ extern "C" int rbpf_migrate_count(rbpf_handle h, const int32_t *src_slots, int32
 {
     if (!h || n < 0 || n > h->d.N || (n > 0 && !src_slots) || !n_subtiles) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     int rc = upload_ints(h, h->d_mg_slots, src_slots, n);
     if (rc) return rc;
     rb_launch_migrate_claim(h->d, h->d_mg_slots, n, h->d_mg_mark, h->d_mg_list, h->d_mg_count, h->stream);
@@ -765,6 +792,7 @@ extern "C" int rbpf_migrate_pack(rbpf_handle h, uint64_t dev_buf)
 {
     if (!h || (!dev_buf && h->mg_n > 0)) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     rb_launch_migrate_pack(h->d, h->d_mg_slots, h->mg_n, h->mg_tiles, h->d_mg_mark, h->d_mg_list, h->d_mg_count,
                            (unsigned char *)(uintptr_t)dev_buf, h->stream);
     CK(cudaGetLastError());
@@ -780,6 +808,7 @@ extern "C" int rbpf_migrate_unpack(rbpf_handle h, uint64_t dev_buf, int32_t n_pa
     if (!h || n_particles < 0 || m < 0 || m > h->d.N || (m > 0 && (!dst_slots || !rec_index || !dev_buf))) return RBPF_ERR_ARG;
     if ((uint32_t)n_subtiles > h->d.pool_tiles) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     int rc = upload_ints(h, h->d_mg_slots, dst_slots, m);
     if (!rc) rc = upload_ints(h, h->d_mg_slots + h->d.N, rec_index, m);
     if (rc) return rc;
@@ -796,8 +825,24 @@ extern "C" int rbpf_resample_apply_local(rbpf_handle h)
 {
     if (!h) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     rb_launch_resample_apply(h->d, h->stream);
     CK(cudaGetLastError());
+    return RBPF_OK;
+}
+
+// Same, with the reference-count pass deferred (include/rbpf_b200.h): the gather runs now, the counts -- and with them
+// every free and every in-place write of a tile a peer may still be pulling -- wait for `gate_event`.
+extern "C" int rbpf_resample_apply_local_deferred(rbpf_handle h, uint64_t gate_event)
+{
+    if (!h) return RBPF_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
+    rb_launch_resample_gather(h->d, h->stream);
+    CK(cudaGetLastError());
+    h->refs_pending = true;
+    h->refs_gate = (cudaEvent_t)(uintptr_t)gate_event;
+    h->refs_pt = h->d.pt;
     return RBPF_OK;
 }
 
@@ -896,6 +941,7 @@ extern "C" int rbpf_migrate_pull(rbpf_handle h)
         peers.p[r].exists = (const unsigned long long *)pm.base[7 + q];
     }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     if (!h->d_pull_mark) {                                      // first use: one claim table per source rank
         const size_t n = (size_t)h->d.world * h->d.pool_tiles;
         CK(cudaMalloc((void **)&h->d_pull_mark, n * sizeof(uint32_t)));
@@ -945,6 +991,7 @@ extern "C" int rbpf_snapshot(rbpf_handle h)
 {
     if (!h) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     RbCtx &d = h->d;
     const size_t N = d.N;
     if (h->snap.empty()) {
@@ -985,6 +1032,7 @@ extern "C" int rbpf_restore(rbpf_handle h)
     if (!h) return RBPF_ERR_ARG;
     if (!h->snap_valid) { h->err = "restore: no snapshot"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     for (const auto &s2 : h->snap) CK(cudaMemcpyAsync(s2.live, s2.shadow, s2.bytes, cudaMemcpyDeviceToDevice, h->stream));
     if (h->parity != h->snap_parity) swap_buffers(h);
     h->d.use_dup = h->snap_use_dup;
@@ -1028,6 +1076,7 @@ extern "C" int rbpf_checkpoint_write(rbpf_handle h, const char *path)
 {
     if (!h || !path) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(h->stream));
     const RbCtx &d = h->d;
     std::vector<uint32_t> rc(d.pool_tiles);
@@ -1058,6 +1107,7 @@ extern "C" int rbpf_checkpoint_read(rbpf_handle h, const char *path)
 {
     if (!h || !path) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_refs(h); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(h->stream));
     RbCtx &d = h->d;
     FILE *f = fopen(path, "rb");

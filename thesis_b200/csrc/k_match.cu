@@ -232,6 +232,15 @@ __device__ __forceinline__ MtRot mt_rot(const RbCtx &c, const MatchShared *sh, i
     return r;
 }
 
+// the oracle's float64 expression, for the few points whose float32 value lies next to a lattice boundary
+__device__ __noinline__ int2 mt_raster_exact(const double *__restrict__ cs, double cx, double cy, double fx, double fy)
+{
+    const double ck = cs[0], sk = cs[1];
+    const double rxq = (ck * cx - sk * cy) + fx;
+    const double ryq = (sk * cx + ck * cy) + fy;
+    return make_int2(__double2int_rd(rxq * 20.0 + 0.5), __double2int_rd(ryq * 20.0 + 0.5));   // nearest lattice point (see oracle)
+}
+
 __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
                                                     const float2 *__restrict__ ccf, const MtRot &r, int q, int span_i, int span_j)
 {
@@ -240,11 +249,10 @@ __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared 
     const float flx = floorf(vx), fly = floorf(vy);
     int ox = (int)flx, oy = (int)fly;
     const float dx = vx - flx, dy = vy - fly;
+    // out of line: if-converted, the float64 path would be issued (predicated off) for every point of every pass
     if (!(dx > MT_RAS_EPS && dx < 1.0f - MT_RAS_EPS && dy > MT_RAS_EPS && dy < 1.0f - MT_RAS_EPS)) {
-        const double ck = c.rot_cs[2 * (r.k + c.nk)], sk = c.rot_cs[2 * (r.k + c.nk) + 1];
-        const double rxq = (ck * ccx[q] - sk * ccy[q]) + sh->fx;
-        const double ryq = (sk * ccx[q] + ck * ccy[q]) + sh->fy;
-        ox = __double2int_rd(rxq * 20.0 + 0.5); oy = __double2int_rd(ryq * 20.0 + 0.5);   // nearest lattice point (see oracle)
+        const int2 o = mt_raster_exact(c.rot_cs + 2 * (r.k + c.nk), ccx[q], ccy[q], sh->fx, sh->fy);
+        ox = o.x; oy = o.y;
     }
     int bx = ox + r.xoff, by = oy + r.yoff;
     if ((unsigned)bx >= (unsigned)(32 * (RB_BM_STRIDE - 1) - span_i) || (unsigned)by >= (unsigned)(RB_BM_ROWS - span_j)) {

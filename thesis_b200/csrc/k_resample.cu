@@ -21,180 +21,197 @@
 //                 descendants contributes m - 1 (or releases its tiles if m = 0).
 #include "common.cuh"
 
-#define RS_THREADS 256                  // 8 warps: the kernel is a chain of dependent chunk scans, not throughput work
+#ifndef RS_THREADS
+#define RS_THREADS 1024                 // one CTA: the running sum is a chain of windows, every window one block scan
+#endif
+#ifndef RS_EPT
 #define RS_EPT 4                        // consecutive elements per thread
-#define RS_CHUNK (RS_THREADS * RS_EPT)  // 1,024
-static_assert(RS_THREADS == 256, "the block scan assumes 8 warps");
+#endif
+#define RS_CHUNK (RS_THREADS * RS_EPT)  // 4,096 elements per window
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_SEQ 64                       // elements of a sequential stretch (start of the sum, non-finite or denormal carries)
+static_assert(RS_WARPS <= 32, "the block scan folds one warp total per lane");
 
+// The running sum c_i = fl(c_{i-1} + v_i) (main.py:57 == :62), float64, round to nearest even, is inherently a
+// chain of N dependent adds -- except that while the sum stays inside one binade [2^k, 2^(k+1)) every add rounds to a
+// multiple of u = 2^(k-52).  With S = c/u (an integer in [2^52, 2^53)) and v = (m + f) u, m integer, 0 <= f < 1:
+//     S' = S + m + [f > 1/2]          (f == 1/2, a tie, depends on the parity of S + m)
+// so a stretch without ties that does not leave the binade is an exact INTEGER prefix sum.  A window of RS_CHUNK
+// elements is scanned in parallel in units of the carry's u; the first element that is a tie, is not a positive
+// normal number, or takes the sum to 2^53 u or beyond ends the window: everything before it is final, the element
+// itself is added with one genuine float64 add by the thread that owns it, and the next window starts behind it
+// in the (possibly new) binade.  The sum of N positive weights crosses about log2(N) binades, almost all of them
+// within the first few elements, which a single thread chains (RS_SEQ elements); 65,536 weights take about 16 + 12
+// windows instead of 65,536 dependent adds -- with every rounding of the reference reproduced.
 __global__ void __launch_bounds__(RS_THREADS) resample_plan_kernel(RbCtx c, const double *__restrict__ w_in,
                                                                    const double *__restrict__ u01_in)
 {
-    __shared__ double red_mx[RS_THREADS / 32], red_mn[RS_THREADS / 32];
-    __shared__ double chunk[RS_CHUNK];
-    __shared__ long long scan_tot[RS_THREADS / 32];
+    __shared__ double red_mx[RS_WARPS], red_mn[RS_WARPS], red_mn2[RS_WARPS];
+    __shared__ long long scan_tot[RS_WARPS];
+    __shared__ int s_stop[2];
     __shared__ double s_mn2, s_carry;
     __shared__ int s_do;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NG = c.n_global;
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
-    double *w = c.w_all;                                                     // scratch: adjusted weights, then cumsum
+    double *w = c.w_all;                                                     // the running sum
 
-    // max / min of the raw weights (main.py:50)
-    double mx = -INF, mn = INF;
-    for (int i = tid; i < NG; i += RS_THREADS) { double v = w_in[i]; mx = fmax(mx, v); mn = fmin(mn, v); }
+    // max / min of the raw weights (main.py:50) and min after -inf -> 0 (:53-54), one pass
+    double mx = -INF, mn = INF, mn2 = INF;
+    for (int i = tid; i < NG; i += RS_THREADS) {
+        const double v = w_in[i];
+        mx = fmax(mx, v); mn = fmin(mn, v); mn2 = fmin(mn2, v == -INF ? 0.0 : v);
+    }
     for (int o = 16; o > 0; o >>= 1) {
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mn2 = fmin(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
     }
-    if (lane == 0) { red_mx[warp] = mx; red_mn[warp] = mn; }
+    if (lane == 0) { red_mx[warp] = mx; red_mn[warp] = mn; red_mn2[warp] = mn2; }
     __syncthreads();
     if (tid == 0) {
-        for (int k = 1; k < RS_THREADS / 32; k++) { mx = fmax(mx, red_mx[k]); mn = fmin(mn, red_mn[k]); }
+        for (int k = 1; k < RS_WARPS; k++) { mx = fmax(mx, red_mx[k]); mn = fmin(mn, red_mn[k]); mn2 = fmin(mn2, red_mn2[k]); }
         s_do = (mx - mn > RB_RESAMPLE_TRIGGER) ? 1 : 0;
         if (c.flags->pool_exhausted) s_do = 0;                               // maps missed a scan: freeze the set until the caller reacts
         c.flags->did_resample = s_do;
         c.flags->resample_error = 0;
         c.flags->remote_needed = 0;
         if (s_do) c.stats->resamples += 1ull;
+        s_mn2 = mn2;
+        s_carry = 0.0;
+        s_stop[0] = s_stop[1] = 0x7fffffff;
     }
     __syncthreads();
     if (!s_do) return;                                                       // particles unchanged (identity ancestors)
-    // -inf -> 0, then min of the result (main.py:53-54)
-    mn = INF;
-    for (int i = tid; i < NG; i += RS_THREADS) {
-        double v = w_in[i];
-        if (v == -INF) v = 0.0;
-        w[i] = v;
-        mn = fmin(mn, v);
-    }
-    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    __syncthreads();
-    if (lane == 0) red_mn[warp] = mn;
-    __syncthreads();
-    if (tid == 0) {
-        for (int k = 1; k < RS_THREADS / 32; k++) mn = fmin(mn, red_mn[k]);
-        s_mn2 = mn;
-        s_carry = 0.0;
-    }
-    __syncthreads();
     const double shift = s_mn2 < 0.0 ? fabs(s_mn2) : 0.0;
     const bool do_shift = s_mn2 < 0.0;
-    // running sum c_i = fl(c_{i-1} + v_i) (main.py:57 == :62), float64, round to nearest even:
-    // inherently a chain of N dependent adds -- except that while the sum stays inside one
-    // binade [2^k, 2^(k+1)) every add rounds to a multiple of u = 2^(k-52).  With S = c/u
-    // (an integer in [2^52, 2^53)) and v = (m + f) u, m integer, 0 <= f < 1:
-    //     S' = S + m + [f > 1/2]          (f == 1/2, a tie, depends on the parity of S + m)
-    // so a chunk without ties that does not leave the binade is an exact INTEGER prefix sum,
-    // done in parallel (RS_EPT consecutive elements per thread, two barriers).  Chunks with a tie,
-    // a binade crossing, a denormal or the very first chunk take the sequential chain.
-    const int n_chunks = (NG + RS_CHUNK - 1) / RS_CHUNK;
     const unsigned long long MANT = (1ull << 52) - 1ull;
-    double carry = 0.0;                                                      // uniform over the block
     auto load = [&](int i) {
         double v = 0.0;
         if (i < NG) {
-            v = w[i];
+            v = w_in[i];
+            if (v == -INF) v = 0.0;                                          // main.py:53
             if (do_shift && v != 0.0) v += shift;                            // main.py:55
         }
         return v;
     };
+    int pos = 0, pre_pos = -1, it = 0;
+    double carry = 0.0;                                                      // uniform over the block
     double v_next[RS_EPT];
-#pragma unroll
-    for (int e = 0; e < RS_EPT; e++) v_next[e] = load(RS_EPT * tid + e);
-    for (int k = 0; k < n_chunks; k++) {
-        const int i0 = k * RS_CHUNK + RS_EPT * tid;
-        double v[RS_EPT];
-#pragma unroll
-        for (int e = 0; e < RS_EPT; e++) { v[e] = v_next[e]; v_next[e] = load(i0 + RS_CHUNK + e); }
+    while (pos < NG) {
         const unsigned long long cb = (unsigned long long)__double_as_longlong(carry);
         const int kexp = (int)((cb >> 52) & 0x7ffull);
         const bool fast_ok = !(cb >> 63) && kexp >= 54 && kexp < 0x7ff;      // carry > 0, normal, u normal
-        long long a[RS_EPT];
-        bool slow = !fast_ok;
+        if (pos == 0 || !fast_ok) {
+            // sequential stretch by one thread: the start of the sum (carry 0, a binade crossing every few elements) and
+            // carries the integer scan cannot express (non-finite, denormal, negative: pathological input)
+            const int n = min(RS_SEQ, NG - pos);
+            if (tid == 0) {
+                double cur = carry;
+                for (int e0 = 0; e0 < n; e0 += 8) {
+                    double x[8];
 #pragma unroll
-        for (int e = 0; e < RS_EPT; e++) {
+                    for (int e = 0; e < 8; e++) x[e] = load(pos + e0 + e);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { cur += x[e]; if (e0 + e < n) { w[pos + e0 + e] = cur; s_carry = cur; } }
+                }
+            }
+            __syncthreads();
+            carry = s_carry;
+            pos += n;
+            __syncthreads();
+            continue;
+        }
+        const int i0 = pos + RS_EPT * tid;
+        double v[RS_EPT];
+        if (pre_pos == pos) {
+#pragma unroll
+            for (int e = 0; e < RS_EPT; e++) v[e] = v_next[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < RS_EPT; e++) v[e] = load(i0 + e);
+        }
+        pre_pos = pos + RS_CHUNK;                                            // the usual next window is on its way
+#pragma unroll
+        for (int e = 0; e < RS_EPT; e++) v_next[e] = load(i0 + RS_CHUNK + e);
+        long long a[RS_EPT];
+        int first_bad = RS_EPT;                                              // first element of this thread that needs a real add
+#pragma unroll
+        for (int e = RS_EPT - 1; e >= 0; e--) {
             a[e] = 0;
-            if (i0 + e < NG && fast_ok && v[e] != 0.0) {
+            if (i0 + e < NG && v[e] != 0.0) {
                 const unsigned long long vb = (unsigned long long)__double_as_longlong(v[e]);
                 const int ve = (int)((vb >> 52) & 0x7ffull);
-                if ((vb >> 63) || ve == 0x7ff || ve == 0) slow = true;       // negative, inf / nan, denormal
+                if ((vb >> 63) || ve == 0x7ff || ve == 0) first_bad = e;     // negative, inf / nan, denormal
                 else {
                     const unsigned long long M = (vb & MANT) | (1ull << 52);
                     const int sft = kexp - ve;
-                    if (sft < 1) slow = true;                                // v >= 2^k: the sum leaves the binade
+                    if (sft < 1) first_bad = e;                              // v >= 2^k: the sum leaves the binade
                     else if (sft <= 54) {
                         const unsigned long long r = M & ((1ull << sft) - 1ull), half = 1ull << (sft - 1);
                         a[e] = (long long)(M >> sft);
                         if (r > half) a[e] += 1;
-                        else if (r == half) slow = true;                     // tie
+                        else if (r == half) first_bad = e;                   // tie
                     }                                                        // sft > 54: v < u/4, rounds away
                 }
             }
         }
-        bool done = false;
-        if (!__syncthreads_or(slow)) {
-            // inclusive integer scan: inside the thread, across the warp, across the 8 warps
+        // inclusive integer scan: inside the thread, across the warp, across the 32 warps (every warp folds the totals itself)
 #pragma unroll
-            for (int e = 1; e < RS_EPT; e++) a[e] += a[e - 1];
-            long long p = a[RS_EPT - 1];
+        for (int e = 1; e < RS_EPT; e++) a[e] += a[e - 1];
+        long long pw = a[RS_EPT - 1];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long q = __shfl_up_sync(0xffffffffu, p, o);
-                if (lane >= o) p += q;
-            }
-            if (lane == 31) scan_tot[warp] = p;
-            __syncthreads();
-            long long before = p - a[RS_EPT - 1], total = 0;                 // exclusive prefix of this thread inside the warp
-#pragma unroll
-            for (int q = 0; q < RS_THREADS / 32; q++) {
-                const long long t = scan_tot[q];
-                if (q < warp) before += t;
-                total += t;
-            }
-            const unsigned long long S_in = (cb & MANT) | (1ull << 52);
-            if (S_in + (unsigned long long)total < (1ull << 53)) {            // stays in the binade
-                const unsigned long long hi = (unsigned long long)kexp << 52;
-#pragma unroll
-                for (int e = 0; e < RS_EPT; e++)
-                    if (i0 + e < NG) w[i0 + e] = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)(before + a[e])) & MANT)));
-                carry = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)total) & MANT)));
-                done = true;
-            }
-            __syncthreads();                                                 // scan_tot is reused by the next chunk
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long q = __shfl_up_sync(0xffffffffu, pw, o);
+            if (lane >= o) pw += q;
         }
-        if (!done) {                                                         // sequential chain for this chunk
-            // (a[] may hold partial prefix sums here; the chain works on the values themselves)
+        if (lane == 31) scan_tot[warp] = pw;
+        if (tid == 0) s_stop[(it + 1) & 1] = 0x7fffffff;                     // the other buffer: its readers passed the last barrier
+        __syncthreads();
+        long long tw = lane < RS_WARPS ? scan_tot[lane] : 0, ti = tw;
 #pragma unroll
-            for (int e = 0; e < RS_EPT; e++) chunk[RS_EPT * tid + e] = v[e];
-            __syncthreads();
-            if (tid == 0) {
-                const int n = min(RS_CHUNK, NG - k * RS_CHUNK);
-                double cur = carry;
-                int e0 = 0;
-                for (; e0 + 8 <= n; e0 += 8) {
-                    double x[8];
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long q = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += q;
+        }
+        const long long total = __shfl_sync(0xffffffffu, ti, RS_WARPS - 1);
+        const long long before = __shfl_sync(0xffffffffu, ti - tw, warp) + (pw - a[RS_EPT - 1]);   // exclusive prefix of this thread
+        const unsigned long long S_in = (cb & MANT) | (1ull << 52);
+        // first element that ends the window: needs a real add, or takes the sum out of the binade (the prefix is non-decreasing)
+        int stop_e = first_bad;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) x[e] = chunk[e0 + e];
+        for (int e = RS_EPT - 1; e >= 0; e--)
+            if (e < stop_e && S_in + (unsigned long long)(before + a[e]) >= (1ull << 53)) stop_e = e;
+        int my_stop = (stop_e < RS_EPT && i0 + stop_e < NG) ? i0 + stop_e : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, o));
+        if (lane == 0 && my_stop != 0x7fffffff) atomicMin(&s_stop[it & 1], my_stop);
+        __syncthreads();
+        const int stop = s_stop[it & 1];
+        const unsigned long long hi = (unsigned long long)kexp << 52;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { cur += x[e]; x[e] = cur; }
-#pragma unroll
-                    for (int e = 0; e < 8; e++) chunk[e0 + e] = x[e];
-                }
-                for (; e0 < n; e0++) { cur += chunk[e0]; chunk[e0] = cur; }
+        for (int e = 0; e < RS_EPT; e++)
+            if (i0 + e < NG && i0 + e < stop)
+                w[i0 + e] = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)(before + a[e])) & MANT)));
+        if (stop == 0x7fffffff) {
+            carry = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)total) & MANT)));
+            pos += RS_CHUNK;
+        } else {
+            if (stop >= i0 && stop < i0 + RS_EPT) {                          // the owner adds its element for real
+                const int e = stop - i0;
+                const long long pre = before + (e ? a[e - 1] : 0);           // a[] below `stop` is exact
+                const double cprev = __longlong_as_double((long long)(hi | ((S_in + (unsigned long long)pre) & MANT)));
+                const double cur = cprev + v[e];
+                w[stop] = cur;
                 s_carry = cur;
             }
             __syncthreads();
-#pragma unroll
-            for (int e = 0; e < RS_EPT; e++)
-                if (i0 + e < NG) w[i0 + e] = chunk[RS_EPT * tid + e];
             carry = s_carry;
-            __syncthreads();
+            pos = stop + 1;
         }
+        it++;
     }
-    if (tid == 0) s_carry = carry;
-    __syncthreads();
     if (tid == 0) {
-        double slice = s_carry / (double)NG;                                 // main.py:57
+        double slice = carry / (double)NG;                                   // main.py:57
         double u;
         if (u01_in) u = *u01_in;
         else {
@@ -309,7 +326,17 @@ void rb_launch_resample(const RbCtx &c, const double *weights_all, const double 
 // Applies the planned ancestors to this rank's particles (local part).
 void rb_launch_resample_apply(const RbCtx &c, cudaStream_t s)
 {
-    int blocks = (c.N * 32 + 255) / 256;
-    resample_gather_kernel<<<blocks, 256, 0, s>>>(c);
-    resample_refs_kernel<<<blocks, 256, 0, s>>>(c);
+    rb_launch_resample_gather(c, s);
+    rb_launch_resample_refs(c, s);
+}
+
+void rb_launch_resample_gather(const RbCtx &c, cudaStream_t s)
+{
+    resample_gather_kernel<<<(c.N * 32 + 255) / 256, 256, 0, s>>>(c);
+}
+
+// c.pt must be the page tables the gather read (the old particles'), c.mult the counts it left.
+void rb_launch_resample_refs(const RbCtx &c, cudaStream_t s)
+{
+    resample_refs_kernel<<<(c.N * 32 + 255) / 256, 256, 0, s>>>(c);
 }

@@ -11,7 +11,9 @@ particles; the one exchange step is resampling:
      (default): every rank maps its peers' particle state once with CUDA IPC and
      then PULLS what it needs -- page tables, poses and de-duplicated sub-tiles --
      through NVLink straight into its own pool (`rbpf_migrate_pull`), followed by a
-     one-element all-reduce as the "everybody has read" barrier; no packing, no
+     one-element all-reduce as the "everybody has read" barrier -- on a side stream:
+     only the reference-count pass that frees tiles waits for it, at the next scan's
+     map integration (`rbpf_resample_apply_local_deferred`); no packing, no
      size negotiation, no host synchronisation in the data path.  Transport "nccl"
      (fallback, `RBPF_DIST_TRANSPORT=nccl`): the sender packs
      (`rbpf_migrate_count/pack`), NCCL point-to-point moves the buffers, the
@@ -257,6 +259,9 @@ class ShardedParticleSet(MigratingSet):
                       file=sys.stderr)
             self.transport = "nccl"
         self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        self._defer_barrier = os.environ.get("RBPF_DIST_BARRIER", "deferred") != "inline"
+        self._side = torch.cuda.Stream(device=self._dev)
+        self._gate = torch.cuda.Event()
 
     def _resample_peer(self, u01, want_ancestors):
         import time
@@ -272,11 +277,27 @@ class ShardedParticleSet(MigratingSet):
         if prof is not None:
             torch.cuda.synchronize()
             t2 = time.perf_counter()
-        dist.all_reduce(self._barrier_flag, group=self.group)            # every rank has read what it needs
-        if prof is not None:
-            torch.cuda.synchronize()
-            t3 = time.perf_counter()
-        self.finish_resample()
+        if self._defer_barrier:
+            # "every rank has read what it needs" off the critical path: the barrier runs on a side stream behind the
+            # pull, the gather of the local ancestors runs now, and the reference counts -- frees and in-place writes
+            # of tiles a peer may still be reading -- wait for the barrier's event at the next call that needs the
+            # pool (the next scan's integrate): motion, matching and weighting of that scan only read tiles
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream(self._dev))
+            with torch.cuda.stream(side):
+                dist.all_reduce(self._barrier_flag, group=self.group)
+                self._gate.record(side)
+            if prof is not None:
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+            self._ck(self._lib.rbpf_resample_apply_local_deferred(self._h, int(self._gate.cuda_event)))
+            self._ck(self._lib.rbpf_resample_commit(self._h))
+        else:
+            dist.all_reduce(self._barrier_flag, group=self.group)        # every rank has read what it needs
+            if prof is not None:
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+            self.finish_resample()
         if prof is not None:
             torch.cuda.synchronize()
             t4 = time.perf_counter()
