@@ -35,10 +35,10 @@ MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 8,192 particles, per update (`ncu --set full`,
 # profiles/r2_*_raw.csv).  The matcher's is below its algorithmic figure: only blocks under the reference-set mask
 # are fetched and particles that share sub-tiles after a resample hit in L2.
-MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.79e6 + 5.21e6) / 8192
-CAST_DRAM_BYTES_PER_UPDATE_NCU = (472.18e6 + 322.54e6) / 8192      # raycast_cast2_kernel, profiles/r2_cast2_raw.csv
-WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.33e6 + 3.08e6) / 8192
-PREPARE_DRAM_BYTES_PER_UPDATE_NCU = (134.72e6 + 91.77e6) / 8192
+MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.41e6 + 5.07e6) / 8192       # match_kernel, profiles/r2_match_v8_raw.csv
+CAST_DRAM_BYTES_PER_UPDATE_NCU = (472.81e6 + 321.70e6) / 8192      # raycast_cast2_kernel, profiles/r2_cast2_v2_raw.csv
+WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.91e6 + 2.62e6) / 8192        # weight_kernel, profiles/r2_weight_v2_raw.csv
+PREPARE_DRAM_BYTES_PER_UPDATE_NCU = (134.72e6 + 91.77e6) / 8192     # raycast_prepare_kernel, profiles/r2_prepare_raw.csv
 
 
 def parse():
@@ -391,7 +391,7 @@ def run_b200(args):
     dominant = max(rooflines.values(), key=lambda r: r["launch_ms"])
     for r_ in rooflines.values():
         r_["traffic_source"] = "ncu --set full on an 8,192-particle launch (profiles/r2_*_raw.csv), scaled per update"
-    rooflines["match_kernel"]["note"] = ("the correlative search is bound by shared-memory wavefronts and the ALU pipe (ncu: 71 % / 72 % "
+    rooflines["match_kernel"]["note"] = ("the correlative search is bound by shared-memory wavefronts and the ALU pipe (ncu: 69 % / 65 % "
                                          "of peak), not by HBM; see DESIGN.md")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

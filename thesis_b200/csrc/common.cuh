@@ -121,6 +121,8 @@ struct RbCtx {
     const uint32_t *lutx, *luty;            // per axis, packed (RB_LUT_*)
     const uint32_t *clut;                   // cast LUT (k_raycast.cu, version 2): x entries then y entries, packed so that x + y is
                                             // offset (0-14) | page-table slot (15-25) | aliasing flags (x: 30/31, y: 28/29)
+    const uint32_t *rlut;                   // read LUT: storage coordinate -> page-table slot (bits 0-11) | byte offset in the sub-tile (12-31),
+                                            // ux_max x entries then uy_max y entries; the entries of the two axes add up (k_weight.cu)
     int *cast_work;                         // particle counter of the persistent cast kernel (zeroed by raycast_prepare)
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch

@@ -22,7 +22,7 @@ struct rbpf_ctx {
     double *d_px, *d_py, *d_dist;  // scan
     float4 *d_beamf;               // the same beams in float32 for the weight stage: (px, py, inside the weight stage's range gate, 0)
     double *d_rot;                 // rotation table
-    uint32_t *d_lutx, *d_luty, *d_clut;
+    uint32_t *d_lutx, *d_luty, *d_clut, *d_rlut;
     double *d_prev;                // 2 * RB_MAXB: previous scan endpoints (x then y)
     double *h_prev;                // pinned staging
     double *d_z;                   // N*K*3 host-supplied normals
@@ -219,6 +219,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_lutx, 800 * d.tiles_x);
     A(h->d_luty, 800 * d.tiles_y);
     A(h->d_clut, 800 * (d.tiles_x + d.tiles_y));
+    A(h->d_rlut, 800 * (d.tiles_x + d.tiles_y));
     A(d.cast_work, 4);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
     A(d.w_all, d.n_global); A(d.plan_scal, 4); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
@@ -259,6 +260,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     d.lutx = h->d_lutx;
     d.luty = h->d_luty;
     d.clut = h->d_clut;
+    d.rlut = h->d_rlut;
 
     std::vector<double> rot(2 * (2 * d.nk + 1));
     for (int k = -d.nk; k <= d.nk; k++) {
@@ -275,6 +277,13 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     for (size_t q = 0; q < luty.size(); q++)
         clut[lutx.size() + q] = RB_LUT_OFF(luty[q]) | ((RB_LUT_SUB(luty[q]) * (uint32_t)d.subs_x) << 15) |
                                 (((luty[q] >> RB_LUT_NEXT_BIT) & 1u) << 28) | (((luty[q] >> RB_LUT_PREV_BIT) & 1u) << 29);
+    // read LUT: page-table slot and byte offset of a storage coordinate, per axis, packed so that x + y is slot | offset << 12
+    std::vector<uint32_t> rlut((size_t)d.ux_max + (size_t)d.uy_max);
+    for (int ux = 0; ux < d.ux_max; ux++) rlut[ux] = (uint32_t)(ux / RB_SUB) | ((uint32_t)RB_OFF_X(ux % RB_SUB) << 12);
+    for (int uy = 0; uy < d.uy_max; uy++)
+        rlut[(size_t)d.ux_max + uy] = (uint32_t)((uy / RB_SUB) * d.subs_x) | ((uint32_t)RB_OFF_Y(uy % RB_SUB) << 12);
+    if (cudaMemcpy(h->d_rlut, rlut.data(), rlut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(RBPF_ERR_CUDA, "table upload failed");
     if (cudaMemcpy(h->d_rot, rot.data(), rot.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_clut, clut.data(), clut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_lutx, lutx.data(), lutx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||

@@ -24,7 +24,7 @@
 #define WT_INFLIGHT 4                   // beam lookups in flight per lane
 #endif
 #ifndef WT_F32_EPS
-#define WT_F32_EPS 5e-4f                // float32 cell lookups: distance from a lattice boundary below which float64 decides
+#define WT_F32_EPS 2.5e-4f              // float32 cell lookups: distance from a lattice boundary below which float64 decides (error bound 1.7e-4)
 #endif
 
 // The float64 cell lookup for the lanes the float32 evaluation cannot decide (out of line: rare, and its
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
         // of 20 x the reference's own float64 chain, same floor unless V lies within 1e-6 of an integer).  V is
         // evaluated in float32 RELATIVE to floor(x20): |c20 px| <= 500 cells (ranges below 25 m), so the float32 value
         // is within 1.7e-4 of V - floor(x20) (conversions of c20, s20, px, py: 3e-5 each; the two fused roundings 1.5e-5
-        // and 3e-5) and its floor is right unless it lies within WT_F32_EPS of an integer; those lanes (0.2 %) take the
+        // and 3e-5) and its floor is right unless it lies within WT_F32_EPS of an integer; those lanes (0.1 %) take the
         // float64 expression, and there the reference's own expressions within 1e-6 of a lattice boundary
         // (rb_xform + rb_locate).  (Absolute float32 coordinates need 4e-3 and diverge in 38 % of the iterations.)
         const double x20 = g0 * 20.0, y20 = g1 * 20.0;
@@ -173,8 +173,16 @@ __global__ void __launch_bounds__(WT_WARPS * 32, WT_MINBLOCKS) weight_kernel(RbC
                         if (f32_ok && dxf > WT_F32_EPS && dxf < 1.0f - WT_F32_EPS && dyf > WT_F32_EPS && dyf < 1.0f - WT_F32_EPS) {
                             const int ux = (int)flx + X0, uy = (int)fly + Y0;
                             if ((unsigned)ux < (unsigned)c.ux_max && (unsigned)uy < (unsigned)c.uy_max) {
+#ifdef WT_NO_RLUT
                                 sub[u] = (uy / RB_SUB) * c.subs_x + ux / RB_SUB;
                                 off[u] = RB_OFF_Y(uy % RB_SUB) + RB_OFF_X(ux % RB_SUB);
+#else
+                                // page-table slot | offset << 12 from two table entries (L1 hits) instead of two divisions by 160,
+                                // two remainders and the block layout arithmetic: the kernel is issue-bound, its LSU pipe is idle
+                                const uint32_t so = __ldg(&c.rlut[ux]) + __ldg(&c.rlut[c.ux_max + uy]);
+                                sub[u] = (int)(so & 0xfffu);
+                                off[u] = (int)(so >> 12);
+#endif
                             }
                         } else {
                             const int2 so = wt_locate_f64(c.px[jj], c.py[jj], cs_, sn_, g0, g1, c.txh, c.tyh, c.subs_x, c.ux_max, c.uy_max);
