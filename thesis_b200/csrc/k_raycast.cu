@@ -878,7 +878,18 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
                 const int smaj128 = 32 * smaj4;
                 int left = rc.y;                                     // chunks of the ray, tail included
 #define RC2_GROUP(K, T) cast_group<K, T>(k, lane, pmaj, num, n, nf, smaj128, d2x32, t_pmaj, t_num, nt, t_ab)
-                while (left > 4) { RC2_GROUP(4, false); left -= 4; }
+#ifndef RC2_NCH
+#define RC2_NCH 4                    // chunks of 32 cells whose loads are in flight together
+#endif
+                while (left > RC2_NCH) { RC2_GROUP(RC2_NCH, false); left -= RC2_NCH; }
+#if RC2_NCH >= 6
+                if (left == 6) RC2_GROUP(6, true);
+                else
+#endif
+#if RC2_NCH >= 5
+                if (left == 5) RC2_GROUP(5, true);
+                else
+#endif
                 if (left == 4) RC2_GROUP(4, true);
                 else if (left == 3) RC2_GROUP(3, true);
                 else if (left == 2) RC2_GROUP(2, true);
