@@ -91,8 +91,9 @@ def main():
             o.append("| `%s` | %.3f | %.0f | %.0f | %.3f | %s |" % (k, r["launch_ms"], r["algorithmic_bytes_per_update"], r["achieved"], r["frac"],
                                                                    "%.0f" % (r["traffic"] / r["updates_per_launch"]) if r.get("traffic") else "-"))
         o += ["", "None of the three big kernels streams: the matcher runs at the shared-memory-wavefront and ALU-pipe limits, the ray-cast",
-              "and the weight stage at the issue / FP64-pipe limits (ncu tables below); `raycast_prepare` is dominated by marking the",
-              "sub-tiles a sweep touches, its copies overlap with that.", ""]
+              "waits for its cell loads (an order-dependent read-modify-write chain per particle) at 57 % issue utilisation, the weight",
+              "stage is issue-bound (ncu tables below); `raycast_prepare` is dominated by marking the sub-tiles a sweep touches, its",
+              "copies overlap with that.", ""]
         cb = n1.get("cpu_baseline")
         if cb:
             o += ["CPU baseline in the same run (%d host cores): %s %.1f updates/s (%s)" % (cb["cores"], cb["kind"], cb["value"], cb["sample"])]
@@ -136,8 +137,8 @@ def main():
         o += ["", "`dist_parity`: before the timed region every multi-GPU run drives a Freiburg-shaped 360-beam CARMEN log through the drop-in",
               "`Robot` / `resample` API once sharded over all ranks and once as a single set and compares poses, covariances, weights and",
               "maps bit for bit (`thesis_b200.dist.dist_parity_check`).  8 ranks x 4,096 = 32,768 particles is configs[3]'s shape.",
-              "The exchange (all-gather, plan, pull over NVLink, barrier, apply) is a fixed 0.65-0.7 ms per scan from 2 GPUs up; host-side",
-              "phase timers at 2 GPUs: plan + pull 0.30 ms (plan 0.20), barrier 0.12, apply 0.13.", ""]
+              "The exchange (all-gather, plan, pull over NVLink, gather; the barrier and the reference-count pass are off the critical path)",
+              "is a fixed cost per scan from 2 GPUs up: 0.65-0.7 ms at the start of the round, 0.45 ms at the end (plan 0.16).", ""]
     # parity evidence
     fl = line("r2_full_intel_log_1024p_vs_oracle.json")
     if fl:
@@ -148,12 +149,17 @@ def main():
                   fl["particles"], fl["frames"], fl["updates"], fl["triggered"], fl["failed_matches"], fl["seconds"]), ""]
     # ncu
     o += ["## `ncu --set full`, one launch each over 8,192 particles (`bench.py --particles 8192 --steps 3 --warmup 3 --burnin 12`)", ""]
-    for f in ("r2_match_v7_raw.csv", "r2_cast_ordered_raw.csv", "r2_cast_atomic_raw.csv", "r2_weight_raw.csv", "r2_prepare_raw.csv"):
+    for f in ("r2_match_v8_raw.csv", "r2_cast2_v2_raw.csv", "r2_weight_v2_raw.csv", "r2_prepare_raw.csv", "r2_plan_v2_raw.csv",
+              "r2_cast_ordered_raw.csv", "r2_cast_atomic_raw.csv"):
         r = ncu_row(f)
         if r:
             o.append("* `%s` (`%s`): " % (r.pop("kernel"), f) + ", ".join("%s=%s" % kv for kv in r.items()))
-    o += ["", "(`r2_weight_raw.csv` was taken before the weight stage's `floor(20 g)` lookup path, `r2_prepare_raw.csv` after the cheaper sub-tile",
-          "marking; `r2_match_v7_raw.csv` is the final matcher.)", ""]
+    o += ["", "(`r2_match_v8`, `r2_cast2_v2`, `r2_weight_v2`: the kernels of the final bench line except for the last two small changes --",
+          "the matcher's float64 raster fallback moved out of line, the weight stage's read LUT; `r2_plan_v2`: the windowed plan kernel on",
+          "65,536 weights; `r2_cast_ordered` / `r2_cast_atomic`: the first cast kernel against the atomics experiment on the same launch;",
+          "`r2_match_v7_raw.csv`, `r2_cast2_raw.csv`, `r2_weight_raw.csv`: earlier states of the round, kept for the history.)",
+          "Launch list of one bench run (`ncu --metrics gpu__time_duration.sum`, 8,192 particles): `r2_launches_8192p.csv`;",
+          "GPU test log of the final tree: `r2_pytest_gpu.log` (74 passed).", ""]
     extra = os.path.join(P, "r2_notes.md")
     if os.path.exists(extra):
         o += open(extra).read().splitlines()
