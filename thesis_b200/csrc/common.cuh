@@ -123,7 +123,9 @@ struct RbCtx {
                                             // offset (0-14) | page-table slot (15-25) | aliasing flags (x: 30/31, y: 28/29)
     const uint32_t *rlut;                   // read LUT: storage coordinate -> page-table slot (bits 0-11) | byte offset in the sub-tile (12-31),
                                             // ux_max x entries then uy_max y entries; the entries of the two axes add up (k_weight.cu)
-    int *cast_work;                         // particle counter of the persistent cast kernel (zeroed by raycast_prepare)
+    int *cast_work;                         // work counter of the persistent cast kernel (zeroed by raycast_prepare)
+    int *cast_done;                         // N: parts of a particle's sweep already cast (split mode of the cast kernel, zeroed per launch)
+    int cast_ipp;                           // work items per particle (1: whole sweeps; set by the launcher)
     // resample
     double *w_all;                          // n_global adjusted weights / cumsum scratch
     double *plan_scal;                      // slice, start of the last plan (main.py:57,59)

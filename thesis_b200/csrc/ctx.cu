@@ -221,6 +221,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_clut, 800 * (d.tiles_x + d.tiles_y));
     A(h->d_rlut, 800 * (d.tiles_x + d.tiles_y));
     A(d.cast_work, 4);
+    A(d.cast_done, N);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
     A(d.w_all, d.n_global); A(d.plan_scal, 4); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);

@@ -524,6 +524,10 @@ __global__ void __launch_bounds__(RC_WARPS * 32) raycast_cast_kernel(RbCtx c)
 #endif
 
 #define RC2_OFFMASK 0x00007fffu
+#define RC2_PART_BEAMS 96            // beams per work item in split mode (multiple of 32)
+#ifndef RC2_SPLIT_BELOW
+#define RC2_SPLIT_BELOW 4             // whole sweeps when every resident warp gets at least this many particles (measured: parts win 6 % at 8,192 particles, 1 % at 16,384, lose 2 % at 32,768)
+#endif
 #define RC2_TBL_ENTRIES 168          // slot table of a warp: 4 * subs_x + 5 <= 165 sub-tile base pointers (subs_x <= 40)
 #define RC2_WARP_WORDS (384 + 16)    // per warp: 32 records of 48 bytes, the particle's frame
 static_assert(RC2_WARPS * RC2_TBL_ENTRIES <= 8192, "slot-table entry index has 13 bits");
@@ -802,17 +806,41 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
     int8_t *const sink = c.pool + (size_t)c.pool_tiles * RB_SUB_BYTES;
     const int lane_m32 = lane - 32;
 
+    // Work items: whole sweeps (cast_ipp == 1), or -- when a GPU holds so few particles that whole sweeps would leave the
+    // last round of the persistent grid half empty (8,192 particles on 4,736 resident warps: two rounds for 1.7 rounds of
+    // work) -- parts of RC2_PART_BEAMS beams.  Item i is part i / N of particle i % N: every first part is handed out
+    // before any second part, a part waits for its predecessor's release (which is running or done: items are handed out
+    // in order and every CTA of the grid is resident), so the beams of a particle are still applied in order.
+    const int ipp = c.cast_ipp, n_items = c.N * ipp;
     for (;;) {
-        int p = 0;
-        if (lane == 0) p = atomicAdd(c.cast_work, 1);
-        p = __shfl_sync(FULL, p, 0);
-        if (p >= c.N) break;
+        int it = 0;
+        if (lane == 0) it = atomicAdd(c.cast_work, 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= n_items) break;
+        const int part = it / c.N, p = it - part * c.N;
+        const int j_begin = ipp > 1 ? part * RC2_PART_BEAMS : 0, j_end = ipp > 1 ? min(c.B, j_begin + RC2_PART_BEAMS) : c.B;
+        if (part > 0) {
+            if (lane == 0) {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c.cast_done + p) : "memory");
+                    if (seen < part) __nanosleep(200);
+                } while (seen < part);
+            }
+            __syncwarp();
+        }
+#define RC2_RELEASE_PART()                                                                                       \
+        if (ipp > 1) {                                                                                           \
+            __threadfence();                                                                                     \
+            __syncwarp();                                                                                        \
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.cast_done + p), "r"(part + 1) : "memory"); \
+        }
         const uint32_t *pt = c.pt + (size_t)p * c.nsub;
         int sub_lo = 0;                                              // slot of the window corner (may lie outside the world)
         {
             double x, y, cs_, sn_;
             int sx, sy;
-            if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) continue;
+            if (!particle_frame(c, p, x, y, cs_, sn_, sx, sy)) { RC2_RELEASE_PART() continue; }
             __syncwarp();
             if (lane == 0) {
                 frame[0] = x; frame[1] = y; frame[2] = cs_; frame[3] = sn_;
@@ -843,12 +871,12 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
         k.sink = sink;
         k.overflow = &c.flags->world_overflow;
 
-        for (int j0 = 0; j0 < c.B; j0 += 32) {
+        for (int j0 = j_begin; j0 < j_end; j0 += 32) {
             __syncwarp();
-            ex_new |= cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, c.B, j0, lane, frame, recs, nx, ny,
+            ex_new |= cast_setup_beams(c.px, c.py, c.dist, c.lutx, c.luty, c.txh, c.tyh, c.tiles_x, j_end, j0, lane, frame, recs, nx, ny,
                                        8 * RC2_WARPS * RC2_TBL_ENTRIES, ex_mask);
             __syncwarp();
-            const int nb = min(32, c.B - j0);
+            const int nb = min(32, j_end - j0);
             for (int b = 0; b < nb; b++) {
                 const int4 ra = recs[3 * b];
                 const int w0 = ra.x, len = w0 & 0xfff;
@@ -900,7 +928,9 @@ __global__ void __launch_bounds__(RC2_WARPS * 32, RC2_MINBLOCKS) raycast_cast2_k
         // publish newly created reference tiles
         for (int o = 16; o > 0; o >>= 1) ex_new |= __shfl_xor_sync(FULL, ex_new, o);
         if (lane == 0 && ex_new) c.exists[p] = ex_mask | ex_new;
+        RC2_RELEASE_PART()
     }
+#undef RC2_RELEASE_PART
 }
 
 // ------------------------------------------------------- atomics variant --
@@ -994,8 +1024,15 @@ void rb_launch_raycast_cast(const RbCtx &c, cudaStream_t s)
             resident = sms * (per_sm > 0 ? per_sm : 1);
             smem_set = smem;
         }
-        const int want = (c.N + RC2_WARPS - 1) / RC2_WARPS;
-        raycast_cast2_kernel<<<want < resident ? want : resident, RC2_WARPS * 32, smem, s>>>(c);
+        // split sweeps into parts when whole sweeps would fill fewer than RC2_SPLIT_BELOW rounds of the resident warps
+        static const int force_ipp = getenv("RBPF_CAST_PARTS") ? atoi(getenv("RBPF_CAST_PARTS")) : 0;      // 1: never split (A/B)
+        RbCtx d = c;
+        d.cast_ipp = 1;
+        if (force_ipp != 1 && c.N < RC2_SPLIT_BELOW * resident * RC2_WARPS) d.cast_ipp = (c.B + RC2_PART_BEAMS - 1) / RC2_PART_BEAMS;
+        if (d.cast_ipp > 1) cudaMemsetAsync(c.cast_done, 0, sizeof(int) * (size_t)c.N, s);
+        const long long items = (long long)c.N * d.cast_ipp;
+        const int want = (int)((items + RC2_WARPS - 1) / RC2_WARPS);
+        raycast_cast2_kernel<<<want < resident ? want : resident, RC2_WARPS * 32, smem, s>>>(d);
         return;
     }
     const int blocks = (c.N + RC_WARPS - 1) / RC_WARPS;
