@@ -286,6 +286,12 @@ typedef struct {
 int rbpf_peer_export(rbpf_handle h, rbpf_peer_view *out);
 int rbpf_peer_attach(rbpf_handle h, int32_t peer_rank, const rbpf_peer_view *view);
 int rbpf_migrate_pull(rbpf_handle h);
+/* The same with the sub-tile payloads copied on `copy_stream` (a cudaStream_t; 0 = the handle's stream, i.e.
+ * rbpf_migrate_pull): claims, allocation, page tables and particle state stay on the handle's stream, so the rest of
+ * the resample and the next scan go ahead; rbpf_scan_match matches the local particles first and the migrated ones
+ * behind the copies, every other call that touches tiles waits for them.  The caller's job-wide barrier has to
+ * follow the copies, i.e. be issued on `copy_stream`. */
+int rbpf_migrate_pull_async(rbpf_handle h, uint64_t copy_stream);
 /* Receiver: adopt a packed buffer; local slot dst_slots[i] becomes a copy of
  * received record rec_index[i] (weight 1.0, main.py:77-78). */
 int rbpf_migrate_unpack(rbpf_handle h, uint64_t dev_buf, int32_t n_particles, int32_t n_subtiles,

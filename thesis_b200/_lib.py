@@ -100,6 +100,7 @@ SIGNATURES = {
     "rbpf_peer_export": (C.c_int, [_H, C.POINTER(RbpfPeerView)]),
     "rbpf_peer_attach": (C.c_int, [_H, C.c_int32, C.POINTER(RbpfPeerView)]),
     "rbpf_migrate_pull": (C.c_int, [_H]),
+    "rbpf_migrate_pull_async": (C.c_int, [_H, C.c_uint64]),
 }
 
 _LIB = None

@@ -124,6 +124,7 @@ struct RbCtx {
     const uint32_t *rlut;                   // read LUT: storage coordinate -> page-table slot (bits 0-11) | byte offset in the sub-tile (12-31),
                                             // ux_max x entries then uy_max y entries; the entries of the two axes add up (k_weight.cu)
     int *cast_work;                         // work counter of the persistent cast kernel (zeroed by raycast_prepare)
+    unsigned char *pulled;                  // N: 1 = the particle arrived with the last sharded resample (its sub-tiles may still be in flight)
     int *cast_done;                         // N: parts of a particle's sweep already cast (split mode of the cast kernel, zeroed per launch)
     int cast_ipp;                           // work items per particle (1: whole sweeps; set by the launcher)
     // resample
@@ -277,7 +278,7 @@ __device__ __forceinline__ double rb_u01(uint32_t hi, uint32_t lo)   // (0,1), 5
 
 // ---- launchers (one per kernel file) ----
 void rb_launch_motion(const RbCtx &c, int family, const double *u, double dt, const double *par, cudaStream_t s);
-void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s);
+void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s, int sel = 0, bool copy_dups = true);   // sel 1: all but pulled particles, 2: only those
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, int adj, cudaStream_t s);
 void rb_launch_weight(const RbCtx &c, const double *z_dev, const double *guesses_dev, int fallback_phase, cudaStream_t s);
 void rb_launch_raycast_prepare(const RbCtx &c, cudaStream_t s);
@@ -300,4 +301,4 @@ void rb_launch_migrate_unpack(const RbCtx &c, const unsigned char *buf, int n, i
                               const int *rec_idx_dev, int m, uint32_t *map, cudaStream_t s);
 size_t rb_migrate_bytes(int n, int n_tiles, int nsub);
 void rb_launch_migrate_pull(const RbCtx &c, const RbPeers &peers, uint32_t *mark, uint32_t *list, unsigned char *list_rank,
-                            int *count, cudaStream_t s);
+                            uint32_t *list_local, int *count, cudaStream_t s, cudaStream_t copy_stream, cudaEvent_t ev_alloc);

@@ -41,6 +41,9 @@ struct rbpf_ctx {
     int mg_n, mg_tiles;
     uint32_t *d_pull_mark = nullptr;   // world x pool_tiles claim table of the pull migration (allocated on first use)
     unsigned char *d_pull_rank = nullptr;
+    uint32_t *d_pull_local = nullptr;  // local sub-tile of every claim
+    bool pulled_pending = false;       // rbpf_migrate_pull_async: the payload copies run on another stream ...
+    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr;   // ... between these two events
     void *phys[9];                 // pool, pt x2, pose x2, cov x2, exists x2 as allocated (index 1 + 2*k + parity)
     int parity;                    // which of the double buffers is current (flips with every commit)
     bool refs_pending = false;     // rbpf_resample_apply_local_deferred: the reference-count pass has not been launched yet
@@ -141,6 +144,8 @@ extern "C" int rbpf_destroy(rbpf_handle h)
     for (auto &pm : h->peers)
         if (pm.attached && pm.ipc)
             for (void *b : pm.base) cudaIpcCloseMemHandle(b);
+    if (h->ev_alloc) cudaEventDestroy(h->ev_alloc);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     for (void *p : h->allocs) cudaFree(p);
     for (auto &s2 : h->snap) cudaFree(s2.shadow);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -222,6 +227,7 @@ extern "C" int rbpf_create(const rbpf_config *cfg, rbpf_handle *out)
     A(h->d_rlut, 800 * (d.tiles_x + d.tiles_y));
     A(d.cast_work, 4);
     A(d.cast_done, N);
+    A(d.pulled, N);
     A(d.m_pose, N * 3); A(d.m_cov, N * 9); A(d.m_score, N); A(d.m_valid, N); A(d.m_best, N * 4); A(d.m_refine, N * 2);
     A(d.w_all, d.n_global); A(d.plan_scal, 4); A(d.ancestors, d.n_global); A(d.mult, N); A(d.dup_of, N);
     A(d.stats, 1); A(d.flags, 1);
@@ -322,6 +328,7 @@ static int check_flags(rbpf_ctx *h)
 }
 
 static int flush_refs(rbpf_ctx *h);
+static int flush_pulled(rbpf_ctx *h);
 
 extern "C" int rbpf_clear_errors(rbpf_handle h)
 {
@@ -386,7 +393,15 @@ extern "C" int rbpf_scan_match(rbpf_handle h)
 {
     if (!h || !h->have_scan) { if (h) h->err = "scan_match: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
-    rb_launch_match(h->d, 0, h->stream);
+    if (h->pulled_pending) {
+        // the sub-tiles of migrated particles are still arriving on the copy stream: match the local particles now,
+        // the migrated ones behind the copies
+        rb_launch_match(h->d, 0, h->stream, 1, false);
+        { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
+        rb_launch_match(h->d, 0, h->stream, 2, true);
+    } else {
+        rb_launch_match(h->d, 0, h->stream);
+    }
     h->last_adj = 0;
     CK(cudaGetLastError());
     return RBPF_OK;
@@ -399,6 +414,7 @@ extern "C" int rbpf_scan_match_adj(rbpf_handle h, const double *last_scan_xy, in
         return RBPF_ERR_ARG;
     }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     // shares the slot of the preceding rbpf_set_scan (its event is re-recorded after this copy)
     CK(cudaEventSynchronize(h->stage_ev[h->stage_slot]));
     double *hp = h->h_scan + (size_t)h->stage_slot * RB_STAGE_DOUBLES + 3 * RB_MAXB;
@@ -417,6 +433,7 @@ extern "C" int rbpf_weight(rbpf_handle h, const double *z)
     if (h) h->d.use_dup = 0;       // samples make duplicates diverge
     if (!h || !h->have_scan) { if (h) h->err = "weight: no scan set"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     const double *zd = nullptr;
     if (z) {
         CK(cudaMemcpyAsync(h->d_z, z, (size_t)h->d.N * h->d.K * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -432,6 +449,7 @@ extern "C" int rbpf_weight_guesses(rbpf_handle h, const double *guesses)
     if (h) h->d.use_dup = 0;
     if (!h || !h->have_scan || !guesses) { if (h) h->err = "weight_guesses: no scan set or no samples"; return RBPF_ERR_ARG; }
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(h->d_z, guesses, (size_t)h->d.N * h->d.K * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     rb_launch_weight(h->d, nullptr, h->d_z, 0, h->stream);
     CK(cudaGetLastError());
@@ -441,8 +459,20 @@ extern "C" int rbpf_weight_guesses(rbpf_handle h, const double *guesses)
 // The reference-count pass of a sharded resample may be deferred (rbpf_resample_apply_local_deferred): it is launched
 // here, behind its gate, by the first call that needs the pool's bookkeeping -- reference counts, free list, `mult`,
 // or the old page tables as the target of the next gather.  Motion, matching and weighting only read tiles.
+// Sub-tiles of migrated particles may still be arriving on the copy stream (rbpf_migrate_pull_async): everything that
+// touches tiles of arbitrary particles waits for them here; rbpf_scan_match matches the local particles first.
+static int flush_pulled(rbpf_ctx *h)
+{
+    if (!h->pulled_pending) return RBPF_OK;
+    h->pulled_pending = false;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
+    return RBPF_OK;
+}
+
 static int flush_refs(rbpf_ctx *h)
 {
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     if (!h->refs_pending) return RBPF_OK;
     h->refs_pending = false;
     CK(cudaSetDevice(h->cfg.device));
@@ -669,6 +699,7 @@ extern "C" int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *ou
 {
     if (!h || !out || particle < 0 || particle >= h->d.N || !h->have_scan) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     CK(cudaMemsetAsync(h->d_slice, 0, sizeof(int) * RB_SLICE_W * RB_SLICE_W, h->stream));
     rb_launch_match_slice(h->d, particle, h->d_slice, h->last_adj, h->stream);
     CK(cudaGetLastError());
@@ -678,6 +709,7 @@ extern "C" int rbpf_get_match_slice(rbpf_handle h, int32_t particle, int32_t *ou
 extern "C" int rbpf_export_tile(rbpf_handle h, int32_t particle, int32_t cx, int32_t cy, double *out, int32_t *exists)
 {
     if (!h || !out || particle < 0 || particle >= h->d.N || cx % 40 || cy % 40) return RBPF_ERR_ARG;
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     const int tx = cx / 40, ty = cy / 40;
     memset(out, 0, sizeof(double) * RB_DIM * RB_DIM);
     if (exists) *exists = 0;
@@ -933,7 +965,7 @@ extern "C" int rbpf_peer_attach(rbpf_handle h, int32_t peer_rank, const rbpf_pee
 // becomes a copy of that particle, read through the peer mappings (the job runs in
 // lockstep: the peers' current buffers have this handle's parity).  The plan is the
 // ancestor vector on the device: nothing is copied to or from the host, nothing waits.
-extern "C" int rbpf_migrate_pull(rbpf_handle h)
+extern "C" int rbpf_migrate_pull_async(rbpf_handle h, uint64_t copy_stream)
 {
     if (!h) return RBPF_ERR_ARG;
     if (h->d.world > RB_MAX_WORLD) { h->err = "migrate_pull: world larger than RB_MAX_WORLD"; return RBPF_ERR_ARG; }
@@ -958,12 +990,25 @@ extern "C" int rbpf_migrate_pull(rbpf_handle h)
         h->allocs.push_back(h->d_pull_mark);
         CK(cudaMalloc((void **)&h->d_pull_rank, h->d.pool_tiles));
         h->allocs.push_back(h->d_pull_rank);
+        CK(cudaMalloc((void **)&h->d_pull_local, (size_t)h->d.pool_tiles * sizeof(uint32_t)));
+        h->allocs.push_back(h->d_pull_local);
+        CK(cudaEventCreateWithFlags(&h->ev_alloc, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
         CK(cudaMemsetAsync(h->d_pull_mark, 0xFF, n * sizeof(uint32_t), h->stream));
     }
-    rb_launch_migrate_pull(h->d, peers, h->d_pull_mark, h->d_mg_list, h->d_pull_rank, h->d_mg_count, h->stream);
+    cudaStream_t cs = copy_stream ? (cudaStream_t)(uintptr_t)copy_stream : h->stream;
+    rb_launch_migrate_pull(h->d, peers, h->d_pull_mark, h->d_mg_list, h->d_pull_rank, h->d_pull_local, h->d_mg_count, h->stream, cs,
+                           h->ev_alloc);
     CK(cudaGetLastError());
+    if (cs != h->stream) {                                      // the payloads arrive behind this event
+        CK(cudaEventRecord(h->ev_copied, cs));
+        h->pulled_pending = true;
+    }
     return RBPF_OK;
 }
+
+extern "C" int rbpf_migrate_pull(rbpf_handle h) { return rbpf_migrate_pull_async(h, 0); }
+
 
 extern "C" int64_t rbpf_migrate_bytes(rbpf_handle h, int32_t n_particles, int32_t n_subtiles)
 {
@@ -977,6 +1022,7 @@ extern "C" int rbpf_occupied_points(rbpf_handle h, int32_t particle, double *out
 {
     if (!h || !n || particle < 0 || particle >= h->d.N || max_points < 0) return RBPF_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));
+    { const int rc_ = flush_pulled(h); if (rc_) return rc_; }
     double *dev = nullptr;
     if (out_xy && max_points > 0) CK(cudaMalloc((void **)&dev, sizeof(double) * 2 * (size_t)max_points));
     rb_launch_occupied_points(h->d, particle, dev, (unsigned long long)max_points, h->d_refstats + 3, h->stream);

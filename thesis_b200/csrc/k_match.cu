@@ -792,7 +792,7 @@ __device__ __noinline__ void ndt_refine(const uint32_t *__restrict__ bm, double 
 // adj = 0: scan-to-map (HybridMap.get_scan_match hybridmap.py:210-261)
 // adj = 1: scan-to-previous-scan (HybridMap.get_scan_adj hybridmap.py:147-191): curr points are
 //          the unsnapped endpoints, occupancy is the previous scan rasterised on the lattice.
-__global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out, int adj)
+__global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_offset, int *__restrict__ slice_out, int adj, int sel)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm = smem;
@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x + p_offset;
     if (c.use_dup && !slice_out && c.dup_of[p] != p) return;                // a bit-identical duplicate: result copied afterwards
+    if (sel && (c.pulled[p] != 0) != (sel == 2)) return;                    // two launches around the arrival of migrated sub-tiles
     const double *pose = c.pose + 3 * (size_t)p, *cov = c.cov + 9 * (size_t)p;
     long long clk_prev = clock64();
     if (tid < MT_NRB) sh->need[tid] = 0u;
@@ -1488,11 +1489,11 @@ __global__ void __launch_bounds__(256) match_copy_dups_kernel(RbCtx c)
     }
 }
 
-void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)
+void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s, int sel, bool copy_dups)
 {
     match_set_attr();
-    match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr, adj);
-    if (c.use_dup) match_copy_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
+    match_kernel<<<c.N, MT_THREADS, rb_match_smem_bytes(), s>>>(c, 0, nullptr, adj, sel);
+    if (c.use_dup && copy_dups) match_copy_dups_kernel<<<(c.N + 255) / 256, 256, 0, s>>>(c);
 }
 
 // Debug/test entry: re-run the last match (same mode) for one particle and dump the
@@ -1501,5 +1502,5 @@ void rb_launch_match(const RbCtx &c, int adj, cudaStream_t s)
 void rb_launch_match_slice(const RbCtx &c, int particle, int *slice_dev, int adj, cudaStream_t s)
 {
     match_set_attr();
-    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev, adj);
+    match_kernel<<<1, MT_THREADS, rb_match_smem_bytes(), s>>>(c, particle, slice_dev, adj, 0);
 }

@@ -197,34 +197,45 @@ __global__ void pull_claim_kernel(RbCtx c, RbPeers peers, uint32_t *mark, uint32
     }
 }
 
-// pass 2: a fresh local sub-tile for every claimed remote one, payload copied across
-// the link (grid-stride over the device-side count); mark = local index
-__global__ void __launch_bounds__(256) pull_tiles_kernel(RbCtx c, RbPeers peers, uint32_t *mark, const uint32_t *__restrict__ list,
-                                                         const unsigned char *__restrict__ list_rank, const int *count)
+// pass 2a: a fresh local sub-tile for every claimed remote one; mark = local index, list_local = the same by claim
+__global__ void __launch_bounds__(256) pull_alloc_kernel(RbCtx c, uint32_t *mark, const uint32_t *__restrict__ list,
+                                                         const unsigned char *__restrict__ list_rank, uint32_t *list_local, const int *count)
 {
-    __shared__ uint32_t s_t;
+    const int n = min(*count, (int)c.pool_tiles);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t t;
+        const int idx = atomicSub(c.free_count, 1) - 1;
+        if (idx < 0) { atomicAdd(c.free_count, 1); atomicExch(&c.flags->pool_exhausted, 1); t = RB_NONE; }
+        else { t = c.free_list[idx]; c.refcnt[t] = 0u; }
+        list_local[i] = t;
+        mark[(size_t)list_rank[i] * c.pool_tiles + list[i]] = t == RB_NONE ? 0xFFFFFFFDu : t;
+    }
+}
+
+// pass 2b: the payloads, copied across the link (grid-stride over the device-side count).  Nothing on this rank reads the
+// new sub-tiles before the particles that own them are matched, so this kernel may run on a side stream beside the
+// rest of the resample and the next scan's matching of the local particles (rbpf_migrate_pull_async).  Measured at 4 GPUs:
+// no gain (6.51 against 6.52 ms per scan) -- beside two resident CTAs of match_kernel an SM has 4,096 registers and no
+// shared memory left, so the copy takes CTA slots from the matcher for as long as it runs, and the migrated particles are
+// matched in a short second launch with a poor tail; a copy kernel small enough to fit beside the matcher (128 threads x
+// 32 registers per SM) was slower still (6.60 ms).  thesis_b200.dist therefore pulls in stream order unless
+// RBPF_DIST_OVERLAP=1.
+__global__ void __launch_bounds__(256) pull_copy_kernel(RbCtx c, RbPeers peers, const uint32_t *__restrict__ list,
+                                                        const unsigned char *__restrict__ list_rank,
+                                                        const uint32_t *__restrict__ list_local, const int *count)
+{
     const int n = min(*count, (int)c.pool_tiles);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const uint32_t rt = list[i];
+        const uint32_t rt = list[i], t = list_local[i];
         const int r = list_rank[i];
-        if (threadIdx.x == 0) {
-            const int idx = atomicSub(c.free_count, 1) - 1;
-            if (idx < 0) { atomicAdd(c.free_count, 1); atomicExch(&c.flags->pool_exhausted, 1); s_t = RB_NONE; }
-            else { s_t = c.free_list[idx]; c.refcnt[s_t] = 0u; }
-            mark[(size_t)r * c.pool_tiles + rt] = s_t == RB_NONE ? 0xFFFFFFFDu : s_t;
-        }
-        __syncthreads();
-        const uint32_t t = s_t;
-        if (t != RB_NONE) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(peers.p[r].pool + (size_t)rt * RB_SUB_BYTES);
-            uint4 *dst = reinterpret_cast<uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES);
-            uint4 v[7];                                                      // 1,600 x 16 B over 256 threads: all loads first
+        if (t == RB_NONE) continue;
+        const uint4 *src = reinterpret_cast<const uint4 *>(peers.p[r].pool + (size_t)rt * RB_SUB_BYTES);
+        uint4 *dst = reinterpret_cast<uint4 *>(c.pool + (size_t)t * RB_SUB_BYTES);
+        uint4 v[7];                                                          // 1,600 x 16 B over 256 threads: all loads first
 #pragma unroll
-            for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) v[k] = src[q]; }
+        for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) v[k] = src[q]; }
 #pragma unroll
-            for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) dst[q] = v[k]; }
-        }
-        __syncthreads();
+        for (int k = 0; k < 7; k++) { const int q = threadIdx.x + 256 * k; if (q < RB_SUB_BYTES / 16) dst[q] = v[k]; }
     }
 }
 
@@ -242,6 +253,7 @@ __global__ void pull_place_kernel(RbCtx c, RbPeers peers, const uint32_t *__rest
     if (lane == 0) {
         c.exists2[j] = peer.exists[s];
         c.weight[j] = 1.0;                                                   // main.py:77-78
+        c.pulled[j] = 1;                                                     // its sub-tiles may still be on their way
     }
     const uint32_t *mk = mark + (size_t)r * c.pool_tiles;
     uint32_t *dst = c.pt2 + (size_t)j * c.nsub;                              // holds the remote indices (pull_claim_kernel)
@@ -266,13 +278,21 @@ __global__ void pull_release_kernel(RbCtx c, uint32_t *mark, const uint32_t *__r
         mark[(size_t)list_rank[i] * c.pool_tiles + list[i]] = RB_NONE;
 }
 
+// copy_stream: where the payload copies run (the caller has made it wait for `s` up to the allocation through ev_alloc);
+// the same stream as `s` keeps everything in order.
 void rb_launch_migrate_pull(const RbCtx &c, const RbPeers &peers, uint32_t *mark, uint32_t *list, unsigned char *list_rank,
-                            int *count, cudaStream_t s)
+                            uint32_t *list_local, int *count, cudaStream_t s, cudaStream_t copy_stream, cudaEvent_t ev_alloc)
 {
     const int wblocks = (c.N * 32 + 255) / 256;
     cudaMemsetAsync(count, 0, sizeof(int), s);
+    cudaMemsetAsync(c.pulled, 0, (size_t)c.N, s);
     pull_claim_kernel<<<wblocks, 256, 0, s>>>(c, peers, mark, list, list_rank, count);
-    pull_tiles_kernel<<<148 * 8, 256, 0, s>>>(c, peers, mark, list, list_rank, count);
+    pull_alloc_kernel<<<148, 256, 0, s>>>(c, mark, list, list_rank, list_local, count);
+    if (copy_stream != s) {
+        cudaEventRecord(ev_alloc, s);
+        cudaStreamWaitEvent(copy_stream, ev_alloc, 0);
+    }
+    pull_copy_kernel<<<148 * 8, 256, 0, copy_stream>>>(c, peers, list, list_rank, list_local, count);
     pull_place_kernel<<<wblocks, 256, 0, s>>>(c, peers, mark);
     pull_release_kernel<<<148, 256, 0, s>>>(c, mark, list, list_rank, count);
 }

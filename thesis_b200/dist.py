@@ -184,7 +184,22 @@ class MigratingSet(ParticleSet):
             self.migrated_particles += int(np.count_nonzero(mine != self.rank))
         else:
             self._ck(lib.rbpf_resample_global(self._h, weights_all.data_ptr(), self.n_global, up, None, None))
-        self._ck(lib.rbpf_migrate_pull(self._h))
+        prof = getattr(self, "_prof", None)
+        if prof is not None:                                  # RBPF_DIST_PROFILE: the plan and the pull apart (adds a sync)
+            import time
+
+            self._torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        # sharded jobs (ShardedParticleSet): the sub-tile payloads travel on the side stream, in front of the barrier;
+        # the emulations of the tests pull in stream order
+        side = getattr(self, "_side", None) if getattr(self, "_overlap_pull", False) else None
+        if side is not None:
+            self._ck(lib.rbpf_migrate_pull_async(self._h, int(side.cuda_stream)))
+        else:
+            self._ck(lib.rbpf_migrate_pull(self._h))
+        if prof is not None:
+            self._torch.cuda.synchronize()
+            prof["pull"] = prof.get("pull", 0.0) + time.perf_counter() - t0
         return did
 
     def finish_resample(self):
@@ -260,7 +275,11 @@ class ShardedParticleSet(MigratingSet):
             self.transport = "nccl"
         self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self._dev)
         self._defer_barrier = os.environ.get("RBPF_DIST_BARRIER", "deferred") != "inline"
-        self._side = torch.cuda.Stream(device=self._dev)
+        # RBPF_DIST_OVERLAP=1: payload copies of the pull beside the rest of the resample and the next scan's matching (needs
+        # the deferred barrier: the barrier has to follow the copies on the side stream).  Off by default: measured at 4 GPUs
+        # it gains nothing (the copy takes CTA slots from the matcher, the migrated particles are matched in a second launch)
+        self._overlap_pull = self._defer_barrier and os.environ.get("RBPF_DIST_OVERLAP", "0") == "1"
+        self._side = torch.cuda.Stream(device=self._dev, priority=-1)
         self._gate = torch.cuda.Event()
 
     def _resample_peer(self, u01, want_ancestors):
