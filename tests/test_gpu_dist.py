@@ -18,12 +18,16 @@ def mods():
     return torch, dist, particles
 
 
-@pytest.mark.parametrize("transport,world", [("nccl", 2), ("peer", 2), ("peer", 3)])
+@pytest.mark.parametrize("transport,world", [("nccl", 2), ("peer", 2), ("peer", 3), ("peer-async", 3)])
 def test_two_rank_emulation_equals_single_set(mods, golden, transport, world):
     """Ranks emulated on one GPU.  "nccl": pack -> (copy) -> unpack; "peer": every rank
     pulls what it needs straight out of the other ranks' buffers (same-process mapping
-    instead of CUDA IPC), then all ranks apply and commit.  Either way the union of the
-    ranks must equal one ParticleSet bit for bit, every step."""
+    instead of CUDA IPC), then all ranks apply and commit.  "peer-async": the payload copies of
+    the pull run on a side stream per rank (rbpf_migrate_pull_async), the barrier is an event behind
+    all of them, the reference-count pass is deferred behind that event
+    (rbpf_resample_apply_local_deferred) and the next scan's matcher takes the local particles first
+    and the migrated ones behind the copies.  Either way the union of the ranks must equal one
+    ParticleSet bit for bit, every step."""
     torch, D, P = mods
     nl, B, K = 6, 180, 30
     N = world * nl
@@ -31,7 +35,13 @@ def test_two_rank_emulation_equals_single_set(mods, golden, transport, world):
     rng = np.random.default_rng(21)
     one = P.ParticleSet(N, B, pool_subtiles=3000)
     ranks = [D.MigratingSet(nl, B, r, world, pool_subtiles=2000) for r in range(world)]
-    if transport == "peer":
+    sides = []
+    if transport == "peer-async":
+        sides = [torch.cuda.Stream() for _ in ranks]
+        bar, gate = torch.cuda.Stream(), torch.cuda.Event()
+        for ps, side in zip(ranks, sides):
+            ps._side, ps._overlap_pull = side, True
+    if transport.startswith("peer"):
         views = [ps.peer_view() for ps in ranks]
         for k, ps in enumerate(ranks):
             for r_ in range(world):
@@ -55,13 +65,21 @@ def test_two_rank_emulation_equals_single_set(mods, golden, transport, world):
             ps.motion(1, u, 1.0, par)
             ps.set_scan(r, ang); ps.scan_match(); ps.weight(z[k * nl:(k + 1) * nl]); ps.integrate(fallback_weights=True)
         w_all = torch.cat([ps.local_weights_tensor().clone() for ps in ranks])       # the all-gather
-        if transport == "peer":
+        if transport.startswith("peer"):
             for ps in ranks:
                 assert ps.plan_and_pull(w_all, u01) == did1
                 assert np.array_equal(ps._anc, anc1), "step %d: ancestors differ from the single set" % step
-            torch.cuda.synchronize()                                                 # the barrier
-            for ps in ranks:
-                ps.finish_resample()
+            if sides:
+                for side in sides:                                                   # the barrier: an event behind every rank's copies
+                    bar.wait_stream(side)
+                gate.record(bar)
+                for ps in ranks:
+                    ps._ck(ps._lib.rbpf_resample_apply_local_deferred(ps._h, int(gate.cuda_event)))
+                    ps._ck(ps._lib.rbpf_resample_commit(ps._h))
+            else:
+                torch.cuda.synchronize()                                             # the barrier
+                for ps in ranks:
+                    ps.finish_resample()
         else:
             packed = [ps.pack_outgoing(w_all, u01) for ps in ranks]
             for k, ps in enumerate(ranks):
