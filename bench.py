@@ -35,9 +35,9 @@ MATCH_BYTES_PER_UPDATE = (240.0 / 360.0) * np.pi * 11.7 ** 2 / 0.0025
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 8,192 particles, per update (`ncu --set full`,
 # profiles/r2_*_raw.csv).  The matcher's is below its algorithmic figure: only blocks under the reference-set mask
 # are fetched and particles that share sub-tiles after a resample hit in L2.
-MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.41e6 + 5.07e6) / 8192       # match_kernel, profiles/r2_match_v8_raw.csv
+MATCH_DRAM_BYTES_PER_UPDATE_NCU = (549.42e6 + 8.45e6) / 8192       # match_kernel, profiles/r2_match_v9_raw.csv
 CAST_DRAM_BYTES_PER_UPDATE_NCU = (472.81e6 + 321.70e6) / 8192      # raycast_cast2_kernel, profiles/r2_cast2_v2_raw.csv
-WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.91e6 + 2.62e6) / 8192        # weight_kernel, profiles/r2_weight_v2_raw.csv
+WEIGHT_DRAM_BYTES_PER_UPDATE_NCU = (86.91e6 + 2.62e6) / 8192        # weight_kernel, profiles/r2_weight_v3_raw.csv
 PREPARE_DRAM_BYTES_PER_UPDATE_NCU = (134.72e6 + 91.77e6) / 8192     # raycast_prepare_kernel, profiles/r2_prepare_raw.csv
 
 

@@ -140,6 +140,7 @@ extern "C" int rbpf_destroy(rbpf_handle h)
 {
     if (!h) return RBPF_ERR_ARG;
     cudaSetDevice(h->cfg.device);
+    if (h->pulled_pending) cudaEventSynchronize(h->ev_copied);   // payload copies of the last pull still read and write our buffers
     cudaStreamSynchronize(h->stream);
     for (auto &pm : h->peers)
         if (pm.attached && pm.ipc)

@@ -149,13 +149,12 @@ def main():
                   fl["particles"], fl["frames"], fl["updates"], fl["triggered"], fl["failed_matches"], fl["seconds"]), ""]
     # ncu
     o += ["## `ncu --set full`, one launch each over 8,192 particles (`bench.py --particles 8192 --steps 3 --warmup 3 --burnin 12`)", ""]
-    for f in ("r2_match_v8_raw.csv", "r2_cast2_v2_raw.csv", "r2_weight_v2_raw.csv", "r2_prepare_raw.csv", "r2_plan_v2_raw.csv",
+    for f in ("r2_match_v9_raw.csv", "r2_cast2_v2_raw.csv", "r2_weight_v3_raw.csv", "r2_prepare_raw.csv", "r2_plan_v2_raw.csv",
               "r2_cast_ordered_raw.csv", "r2_cast_atomic_raw.csv"):
         r = ncu_row(f)
         if r:
             o.append("* `%s` (`%s`): " % (r.pop("kernel"), f) + ", ".join("%s=%s" % kv for kv in r.items()))
-    o += ["", "(`r2_match_v8`, `r2_cast2_v2`, `r2_weight_v2`: the kernels of the final bench line except for the last two small changes --",
-          "the matcher's float64 raster fallback moved out of line, the weight stage's read LUT; `r2_plan_v2`: the windowed plan kernel on",
+    o += ["", "(`r2_match_v9`, `r2_cast2_v2`, `r2_weight_v3`: the kernels of the final bench line; `r2_plan_v2`: the windowed plan kernel on",
           "65,536 weights; `r2_cast_ordered` / `r2_cast_atomic`: the first cast kernel against the atomics experiment on the same launch;",
           "`r2_match_v7_raw.csv`, `r2_cast2_raw.csv`, `r2_weight_raw.csv`: earlier states of the round, kept for the history.)",
           "Launch list of one bench run (`ncu --metrics gpu__time_duration.sum`, 8,192 particles): `r2_launches_8192p.csv`;",
