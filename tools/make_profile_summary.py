@@ -78,11 +78,13 @@ def main():
         o.append("| final (`r2_bench_n1_65536p.json`) " + stages(n1))
         if r1k:
             o.append("| round-1 kernels + phase clocks on this pod, first call of the round (`r2_bench_n1_65536p_round1_kernels.json`) " + stages(r1k))
-        b200 = line("r2_bench_n1_65536p_burnin200.json")
-        if b200:
-            o.append("| 200 burn-in scans (`r2_bench_n1_65536p_burnin200.json`): unique sub-tile fraction %.3f, %d of %d pool sub-tiles in use, %.0f COW copies + %.0f fresh per scan "
-                     % (b200["config"]["unique_subtile_fraction"], b200["config"]["pool_in_use"], b200["config"]["pool_subtiles"],
-                        b200["config"].get("cow_copies_per_scan", 0), b200["config"].get("fresh_subtiles_per_scan", 0)) + stages(b200))
+        for fn in ("r2_bench_n1_65536p_burnin200.json", "r2_bench_n1_65536p_burnin200_midround.json"):
+            b200 = line(fn)
+            if not b200:
+                continue
+            o.append("| 200 burn-in scans (`%s`): unique sub-tile fraction %.3f, %d of %d pool sub-tiles in use, %.0f COW copies + %.0f fresh per scan "
+                         % (fn, b200["config"]["unique_subtile_fraction"], b200["config"]["pool_in_use"], b200["config"]["pool_subtiles"],
+                            b200["config"].get("cow_copies_per_scan", 0), b200["config"].get("fresh_subtiles_per_scan", 0)) + stages(b200))
         o += ["", "`e2e` (host buffers, same scans from the same device snapshot): %.2f M updates/s, %d B in and %d B out per step."
               % (n1["e2e"]["value"] / 1e6, n1["e2e"]["h2d_bytes_per_step"], n1["e2e"]["d2h_bytes_per_step"]), ""]
         o += ["Roofline entries of that line (algorithmic bytes / CUDA-event launch time, peak = measured 6,515.7 GB/s copy):", "",
