@@ -242,7 +242,7 @@ __device__ __noinline__ int2 mt_raster_exact(const double *__restrict__ cs, doub
 }
 
 __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared *sh, const double *ccx, const double *ccy,
-                                                    const float2 *__restrict__ ccf, const MtRot &r, int q, int span_i, int span_j)
+                                                    const float2 *__restrict__ ccf, const MtRot &r, int q, int span_i, int span_j, int &ovf)
 {
     const float2 cf = ccf[q];
     const float vx = fmaf(r.ckf, cf.x, fmaf(-r.skf, cf.y, r.fxf)), vy = fmaf(r.skf, cf.x, fmaf(r.ckf, cf.y, r.fyf));
@@ -255,10 +255,12 @@ __device__ __forceinline__ uint32_t mt_raster_point(const RbCtx &c, MatchShared 
         ox = o.x; oy = o.y;
     }
     int bx = ox + r.xoff, by = oy + r.yoff;
-    if ((unsigned)bx >= (unsigned)(32 * (RB_BM_STRIDE - 1) - span_i) || (unsigned)by >= (unsigned)(RB_BM_ROWS - span_j)) {
-        sh->overflow = 1;                                                  // cannot happen for |c| < 11 m
-        bx = 0; by = 0;
-    }
+    // cannot happen for |c| < 11 m; branch-free (the flag travels in a register: the if-converted store to shared memory
+    // was seven instructions issued, predicated off, for every point)
+    const bool bad = (unsigned)bx >= (unsigned)(32 * (RB_BM_STRIDE - 1) - span_i) || (unsigned)by >= (unsigned)(RB_BM_ROWS - span_j);
+    ovf |= (int)bad;
+    bx = bad ? 0 : bx;
+    by = bad ? 0 : by;
     return ((uint32_t)(by * RB_BM_STRIDE + (bx >> 5)) << MT_PT_WORD_SHIFT) | (uint32_t)(bx & 31);
 }
 
@@ -281,6 +283,7 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
                                         const volatile unsigned long long *best_key = nullptr, int *visited = nullptr)
 {
     const MtRot r = mt_rot(c, sh, k, -nx, -ny);
+    int ovf = 0;
     uint32_t ones = 0, twos = 0, fours = 0, eights = 0;
 #pragma unroll
     for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
@@ -322,6 +325,7 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
                 }
                 if (!__any_sync(0xffffffffu, (gt | eq) != 0u)) {
                     if (visited) *visited += q0;
+                    if (ovf) sh->overflow = 1;
                     return false;
                 }
             }
@@ -330,7 +334,7 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
         __syncwarp();                                                       // the previous chunk has been read
 #pragma unroll
         for (int e = 0; e < MT_CHUNK; e += 32)
-            if (e + lane < n) pts[e + lane] = mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + e + lane, 2 * nx, 2 * ny);
+            if (e + lane < n) pts[e + lane] = mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + e + lane, 2 * nx, 2 * ny, ovf);
         __syncwarp();
         int q = 0;
         for (; q + 16 <= n; q += 16) {
@@ -366,6 +370,7 @@ __device__ __forceinline__ bool mt_pass(const RbCtx &c, MatchShared *sh, const d
 #undef MT_TREE8
     pl[0] = ones; pl[1] = twos; pl[2] = fours; pl[3] = eights;
     if (visited) *visited += M;
+    if (ovf) sh->overflow = 1;
     return true;
 }
 
@@ -409,6 +414,7 @@ __device__ __forceinline__ bool mt_bound_pass(const RbCtx &c, MatchShared *sh, c
     const uint32_t bm_lane = bmg_addr + (uint32_t)((rows_ok ? MT_BSUB * b : 0) * RB_BM_STRIDE * 4);
     const uint32_t rowmask = rows_ok ? colmask : 0u;
     const uint32_t *ptq = pts + MT_BQ * qd;
+    int ovf = 0;
     uint32_t ones = 0, twos = 0, fours = 0, eights = 0, pl[MT_PLANES];
 #pragma unroll
     for (int p = 0; p < MT_PLANES; p++) pl[p] = 0;
@@ -449,6 +455,7 @@ __device__ __forceinline__ bool mt_bound_pass(const RbCtx &c, MatchShared *sh, c
                 }
                 if (!__any_sync(0xffffffffu, (gt | eq) != 0u)) {
                     *visited += q0;
+                    if (ovf) sh->overflow = 1;
                     return false;
                 }
             }
@@ -459,7 +466,7 @@ __device__ __forceinline__ bool mt_bound_pass(const RbCtx &c, MatchShared *sh, c
         for (int e = 0; e < MT_BCHUNK; e += 32) {
             const int idx = e + lane;                                       // point idx of the chunk goes to quarter idx & 3
             if (idx < npad)
-                pts[(idx & 3) * MT_BQ + (idx >> 2)] = idx < n ? mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + idx, 2 * nx, 2 * ny) : MT_NULLPT;
+                pts[(idx & 3) * MT_BQ + (idx >> 2)] = idx < n ? mt_raster_point(c, sh, ccx, ccy, ccf, r, q0 + idx, 2 * nx, 2 * ny, ovf) : MT_NULLPT;
         }
         __syncwarp();
         const int nq = npad >> 2;                                           // multiple of 8
@@ -483,6 +490,7 @@ __device__ __forceinline__ bool mt_bound_pass(const RbCtx &c, MatchShared *sh, c
 #undef MT_LOAD8
 #undef MT_TREE8
     *visited += M;
+    if (ovf) sh->overflow = 1;
     uint32_t T[MT_PLANES] = {ones, twos, fours, eights, pl[4], pl[5], pl[6], pl[7], pl[8]};
     mt_quarter_sum(T);
     uint32_t cand = rowmask;
@@ -1332,6 +1340,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
             // A rotation whose score ends more than 40 below the best has weight zero: with misses counted as the points go by
             // (far points first, they miss first) such a rotation is given up as soon as bs - (M - misses) > 40 is certain.
             const int miss_max = 40 - (bs - M);                             // misses a rotation can afford
+            int ovf = 0;
             for (int k = klo + warp; k <= khi; k += MT_WARPS) {
                 const MtRot r = mt_rot(c, sh, k, bi, bj);
                 int s = 0, seen = 0;
@@ -1339,7 +1348,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                     const int q = q0 + lane;
                     bool hit = false;
                     if (q < M) {
-                        const uint32_t pk = mt_raster_point(c, sh, ccx, ccy, ccf, r, q, 0, 0);
+                        const uint32_t pk = mt_raster_point(c, sh, ccx, ccy, ccf, r, q, 0, 0, ovf);
                         hit = (bm[pk >> MT_PT_WORD_SHIFT] >> (pk & 31)) & 1u;
                     }
                     s += __popc(__ballot_sync(0xffffffffu, hit));
@@ -1353,6 +1362,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) match_kernel(RbCtx c, int p_off
                     T0 += w; T1 += w * k; T2 += w * k * k;
                 }
             }
+            if (ovf) sh->overflow = 1;
             if (lane == 0) { sh->mom_part[warp][6] = T0; sh->mom_part[warp][7] = T1; sh->mom_part[warp][8] = T2; }
         } else if (lane == 0) {
             sh->mom_part[warp][6] = sh->mom_part[warp][7] = sh->mom_part[warp][8] = 0;
