@@ -413,7 +413,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(2 * args.beams * 8 + 4 * 8 + 4 * 8), "d2h_bytes_per_step": int(d2h),
                 "note": "the same K scans as the device-timed loop, from the same device-side snapshot of the particle set; every step "
                         "copies the sweep from pinned host memory and reads all poses and weights back"},
-        # kernels of _librbpf.so per step (ncu launch list profiles/r2_launches_8192p.csv): motion, match, match_copy_dups,
+        # kernels of _librbpf.so per step (ncu launch list profiles/r2_launches_65536p.csv): motion, match, match_copy_dups,
         # weight x2 (samples + fallback), raycast prepare + cast, resample plan + ancestors, gather, refs = 11; sharded runs
         # add the five pull kernels (claim, alloc, copy, place, release); NCCL's own kernels and memsets are not counted
         "gpu_launches": int(args.steps * (11 if world == 1 else 16)),

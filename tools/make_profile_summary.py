@@ -159,7 +159,10 @@ def main():
     o += ["", "(`r2_match_v9`, `r2_cast2_v2`, `r2_weight_v3`: the kernels of the final bench line; `r2_plan_v2`: the windowed plan kernel on",
           "65,536 weights; `r2_cast_ordered` / `r2_cast_atomic`: the first cast kernel against the atomics experiment on the same launch;",
           "`r2_match_v7_raw.csv`, `r2_cast2_raw.csv`, `r2_weight_raw.csv`: earlier states of the round, kept for the history.)",
-          "Launch list of one bench run (`ncu --metrics gpu__time_duration.sum`, 8,192 particles): `r2_launches_8192p.csv`;",
+          "Launch list of one bench run (`ncu --metrics gpu__time_duration.sum --clock-control none`, 65,536 particles, 19 scans):",
+          "`r2_launches_65536p.csv`.  Shares of the launches' total there / of the step in the live bench line: `match_kernel` 51.1 % / 49.9 %,",
+          "`raycast_cast2_kernel` 32.5 % / 33.0 %, `weight_kernel` (both launches) 8.9 % / 8.7 %, `raycast_prepare_kernel` 5.8 % / 6.5 %,",
+          "resample kernels 1.5 % / 1.7 %.",
           "GPU test log of the final tree: `r2_pytest_gpu.log` (74 passed).", ""]
     extra = os.path.join(P, "r2_notes.md")
     if os.path.exists(extra):
