@@ -141,6 +141,15 @@ def main():
               "maps bit for bit (`thesis_b200.dist.dist_parity_check`).  8 ranks x 4,096 = 32,768 particles is configs[3]'s shape.",
               "The exchange (all-gather, plan, pull over NVLink, gather; the barrier and the reference-count pass are off the critical path)",
               "is a fixed cost per scan from 2 GPUs up: 0.65-0.7 ms at the start of the round, 0.45 ms at the end (plan 0.16).", ""]
+    weak = [(n, line("r2_bench_n1_%dp.json" % (65536 // n)), line("r2_scale_n%d.json" % n)) for n in (2, 4, 8)]
+    if all(a and b for _, a, b in weak):
+        o += ["## The same lines read as weak scaling (fixed particles per GPU: one GPU alone against N GPUs)", "",
+              "| particles per GPU | 1 GPU alone, ms/step | N GPUs, ms/step | efficiency |", "|---|---|---|---|"]
+        for n, a, b in weak:
+            o.append("| %d | %.2f (`r2_bench_n1_%dp.json`, `--steps 10 --warmup 3`) | %.2f (N = %d) | %.2f |" % (
+                65536 // n, a["ms_per_step"], b["ms_per_step"], n, a["ms_per_step"] / b["ms_per_step"]))
+        o += ["", "What N GPUs add to a rank's step: the plan over all 65,536 weights instead of the rank's own (0.16 against 0.08 ms at 8,192), the",
+              "all-gather, the pull and the wait for the slowest rank.", ""]
     # parity evidence
     fl = line("r2_full_intel_log_1024p_vs_oracle.json")
     if fl:
