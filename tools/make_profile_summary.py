@@ -147,7 +147,7 @@ def main():
               "| particles per GPU | 1 GPU alone, ms/step | N GPUs, ms/step | efficiency |", "|---|---|---|---|"]
         for n, a, b in weak:
             o.append("| %d | %.2f (`r2_bench_n1_%dp.json`, `--steps 10 --warmup 3`) | %.2f (N = %d) | %.2f |" % (
-                65536 // n, a["ms_per_step"], b["ms_per_step"], n, a["ms_per_step"] / b["ms_per_step"]))
+                65536 // n, a["ms_per_step"], 65536 // n, b["ms_per_step"], n, a["ms_per_step"] / b["ms_per_step"]))
         o += ["", "What N GPUs add to a rank's step: the plan over all 65,536 weights instead of the rank's own (0.16 against 0.08 ms at 8,192), the",
               "all-gather, the pull and the wait for the slowest rank.", ""]
     # parity evidence
